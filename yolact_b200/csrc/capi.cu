@@ -1,0 +1,575 @@
+// C ABI (include/yolact_b200.h).  Every entry point converts C++ exceptions into a status code
+// and a thread-local message; nothing here computes on the CPU beyond packing weights.
+#include <string.h>
+
+#include "engine.cuh"
+
+namespace yb {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace yb
+
+using namespace yb;
+
+#define YB_API_BEGIN try {
+#define YB_API_END                                   \
+  }                                                  \
+  catch (const yb::Error& e) {                       \
+    yb::set_last_error(e.what());                    \
+    return e.code;                                   \
+  }                                                  \
+  catch (const std::exception& e) {                  \
+    yb::set_last_error(std::string("internal: ") + e.what()); \
+    return YB_ERR_INVALID;                           \
+  }                                                  \
+  return YB_OK;
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) YB_CHECK_CUDA(cudaSetDevice(dev));
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+// OIHW fp32 (device) -> [K][Cout] (T), K = (r*KW+s)*Cin + c
+template <typename T>
+__global__ void pack_w_simt_kernel(const float* __restrict__ w, T* __restrict__ out, int Co, int Ci, int taps) {
+  const int64_t total = (int64_t)Co * Ci * taps;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int t = (int)(i % taps);
+    int64_t r = i / taps;
+    int c = (int)(r % Ci);
+    int o = (int)(r / Ci);
+    out[((int64_t)t * Ci + c) * Co + o] = from_f32<T>(w[i]);
+  }
+}
+// OIHW fp32 (device) -> [Cout][tap*Cin + c] half (DCN contraction as a 1x1 conv over gathered columns)
+__global__ void pack_w_dcn_tc_kernel(const float* __restrict__ w, __half* __restrict__ out, int Co, int Ci, int taps) {
+  const int64_t total = (int64_t)Co * Ci * taps;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int t = (int)(i % taps);
+    int64_t r = i / taps;
+    int c = (int)(r % Ci);
+    int o = (int)(r / Ci);
+    out[(int64_t)o * taps * Ci + (int64_t)t * Ci + c] = from_f32<__half>(w[i]);
+  }
+}
+// offset [B,18,HW] + mask [B,9,HW] (NCHW fp32) -> om [B,HW,27]
+__global__ void pack_om_kernel(const float* __restrict__ off, const float* __restrict__ msk, float* __restrict__ om,
+                               int B, int HW) {
+  const int64_t total = (int64_t)B * HW * 27;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int ch = (int)(i % 27);
+    int64_t r = i / 27;
+    int p = (int)(r % HW);
+    int b = (int)(r / HW);
+    om[i] = ch < 18 ? off[((int64_t)b * 18 + ch) * HW + p] : msk[((int64_t)b * 9 + (ch - 18)) * HW + p];
+  }
+}
+
+struct TempPool {  // RAII device temporaries for the op-level hooks
+  std::vector<void*> v;
+  void* get(size_t bytes) {
+    void* p = nullptr;
+    YB_CHECK_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 256)));
+    v.push_back(p);
+    return p;
+  }
+  ~TempPool() {
+    for (void* p : v) cudaFree(p);
+  }
+};
+
+inline int grid1d(int64_t n) { return (int)std::min<int64_t>(148 * 16, (n + 255) / 256); }
+
+}  // namespace
+
+extern "C" {
+
+int yb_abi_version(void) { return YB_ABI_VERSION; }
+const char* yb_last_error(void) { return yb::g_last_error.c_str(); }
+
+int yb_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    yb::set_last_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    return YB_ERR_NO_DEVICE;
+  }
+  return n;
+}
+
+int yb_create(const yb_config* cfg, int device, yb_handle** out) {
+  YB_API_BEGIN
+  YB_REQUIRE(cfg && out, "yb_create: null argument");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    throw Error(YB_ERR_NO_DEVICE, "yb_create: no CUDA device is visible (this library has no CPU fallback)");
+  }
+  YB_REQUIRE(device >= 0 && device < n, "yb_create: bad device index");
+  cudaDeviceProp prop;
+  YB_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  YB_REQUIRE(prop.major == 10, "yb_create: this library is built for sm_100a (Blackwell B200) only");
+  std::unique_ptr<yb_handle> h(new yb_handle());
+  h->cfg = *cfg;
+  h->device = device;
+  h->ops_only = (cfg->backbone == YB_BACKBONE_NONE);
+  if (!h->ops_only) {
+    YB_REQUIRE(cfg->backbone == YB_BACKBONE_RESNET || cfg->backbone == YB_BACKBONE_DARKNET, "unknown backbone");
+    YB_REQUIRE(cfg->num_stages >= 4 && cfg->num_stages <= 5, "num_stages must be 4 or 5");
+    YB_REQUIRE(cfg->fpn_features == 256 || cfg->fpn_features % 64 == 0, "fpn_features must be a multiple of 64");
+    YB_REQUIRE(cfg->num_scales >= 1 && cfg->num_scales <= 4 && cfg->num_ars >= 1 && cfg->num_ars <= 4, "bad anchors");
+    for (int i = 0; i < 3; ++i)
+      YB_REQUIRE(cfg->selected_layers[i] >= 0 && cfg->selected_layers[i] < cfg->num_stages, "bad selected_layers");
+  }
+  YB_REQUIRE(cfg->precision == YB_PREC_F32 || cfg->precision == YB_PREC_F16TC, "unknown precision");
+  YB_REQUIRE(cfg->mask_dim % 4 == 0 && cfg->mask_dim > 0, "mask_dim must be a positive multiple of 4");
+  DeviceGuard g(device);
+  YB_CHECK_CUDA(cudaFree(0));
+  *out = h.release();
+  YB_API_END
+}
+
+int yb_destroy(yb_handle* h) {
+  YB_API_BEGIN
+  if (h) {
+    DeviceGuard g(h->device);
+    cudaDeviceSynchronize();
+    delete h;
+  }
+  YB_API_END
+}
+
+int yb_load_weight(yb_handle* h, const char* name, const float* h_data, const int64_t* shape, int ndim) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && name && h_data && (shape || ndim == 0), "yb_load_weight: null argument");
+  YB_REQUIRE(ndim >= 0 && ndim <= 8, "yb_load_weight: bad ndim");
+  HostTensor t;
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    YB_REQUIRE(shape[i] >= 0, "yb_load_weight: negative dim");
+    t.shape.push_back(shape[i]);
+    n *= shape[i];
+  }
+  t.data.assign(h_data, h_data + n);
+  h->host[name] = std::move(t);
+  h->finalized = false;
+  YB_API_END
+}
+
+int yb_finalize_weights(yb_handle* h) {
+  YB_API_BEGIN
+  YB_REQUIRE(h, "null handle");
+  DeviceGuard g(h->device);
+  h->finalize();
+  YB_API_END
+}
+
+int yb_num_priors(yb_handle* h, int img_h, int img_w, int64_t* num_priors, int32_t* level_hw) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && !h->ops_only, "yb_num_priors: handle has no network");
+  int lhw[5][2];
+  compute_level_sizes(h->cfg, img_h, img_w, lhw, nullptr, nullptr);
+  int64_t P = 0;
+  for (int l = 0; l < 5; ++l) {
+    P += (int64_t)lhw[l][0] * lhw[l][1] * h->cfg.num_scales * h->cfg.num_ars;
+    if (level_hw) {
+      level_hw[2 * l] = lhw[l][0];
+      level_hw[2 * l + 1] = lhw[l][1];
+    }
+  }
+  if (num_priors) *num_priors = P;
+  YB_API_END
+}
+
+int yb_priors(yb_handle* h, int img_h, int img_w, float* d_priors, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && !h->ops_only && d_priors, "yb_priors: bad argument");
+  DeviceGuard g(h->device);
+  int lhw[5][2];
+  compute_level_sizes(h->cfg, img_h, img_w, lhw, nullptr, nullptr);
+  std::vector<float> pri = make_priors_host(h->cfg, lhw);
+  YB_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  YB_CHECK_CUDA(cudaMemcpy(d_priors, pri.data(), pri.size() * 4, cudaMemcpyHostToDevice));
+  YB_API_END
+}
+
+int yb_proto_size(yb_handle* h, int img_h, int img_w, int32_t* ph, int32_t* pw) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && !h->ops_only, "yb_proto_size: handle has no network");
+  int lhw[5][2], a, b;
+  compute_level_sizes(h->cfg, img_h, img_w, lhw, &a, &b);
+  if (ph) *ph = a;
+  if (pw) *pw = b;
+  YB_API_END
+}
+
+int yb_forward(yb_handle* h, const float* d_x, int B, int H, int W, float* d_loc, float* d_conf, float* d_coef,
+               float* d_proto, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && d_x && B > 0 && H > 0 && W > 0, "yb_forward: bad argument");
+  YB_REQUIRE(!h->ops_only, "yb_forward: handle has no network");
+  DeviceGuard g(h->device);
+  h->forward(d_x, B, H, W, d_loc, d_conf, d_coef, d_proto, (cudaStream_t)stream);
+  YB_API_END
+}
+
+int yb_infer(yb_handle* h, const float* d_x, int B, int H, int W, int cross_class, int max_out, float* d_box,
+             float* d_coef_out, int64_t* d_cls, float* d_score, int32_t* d_count, float* d_proto, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && d_x && B > 0 && H > 0 && W > 0, "yb_infer: bad argument");
+  YB_REQUIRE(!h->ops_only, "yb_infer: handle has no network");
+  YB_REQUIRE(d_box && d_coef_out && d_cls && d_score && d_count, "yb_infer: null output");
+  DeviceGuard g(h->device);
+  h->infer(d_x, B, H, W, cross_class, max_out, d_box, d_coef_out, d_cls, d_score, d_count, d_proto,
+           (cudaStream_t)stream);
+  YB_API_END
+}
+
+int yb_debug_feature(yb_handle* h, int which, float* d_out, int32_t* chw, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && h->last_exec && which >= 0 && which < 9, "yb_debug_feature: no forward has run / bad index");
+  DeviceGuard g(h->device);
+  const Act& a = h->last_exec->feats[which];
+  YB_REQUIRE(a.ptr != nullptr, "yb_debug_feature: feature not available for this backbone");
+  if (chw) {
+    chw[0] = a.C;
+    chw[1] = a.H;
+    chw[2] = a.W;
+  }
+  if (d_out) {
+    if (a.f32)
+      launch_nhwc_to_nchw_f32<float>((const float*)a.ptr, d_out, a.B, a.H, a.W, a.C, (cudaStream_t)stream, &h->lc);
+    else
+      launch_nhwc_to_nchw_f32<__half>((const __half*)a.ptr, d_out, a.B, a.H, a.W, a.C, (cudaStream_t)stream, &h->lc);
+  }
+  YB_API_END
+}
+
+int yb_softmax(yb_handle* h, const float* d_in, float* d_out, int64_t rows, int cols, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && d_in && d_out && rows >= 0 && cols > 0, "yb_softmax: bad argument");
+  DeviceGuard g(h->device);
+  launch_softmax_rows(d_in, d_out, rows, cols, (cudaStream_t)stream, &h->lc);
+  YB_API_END
+}
+
+int yb_detect(yb_handle* h, const float* d_loc, const float* d_conf, const float* d_coef, const float* d_priors,
+              int B, int64_t P, int conf_is_logits, int cross_class, int max_out, float* d_box, float* d_coef_out,
+              int64_t* d_cls, float* d_score, int32_t* d_count, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && d_loc && d_conf && d_coef && d_priors && d_box && d_coef_out && d_cls && d_score && d_count,
+             "yb_detect: null argument");
+  YB_REQUIRE(B > 0 && P > 0, "yb_detect: empty input");
+  DeviceGuard g(h->device);
+  DetectParams dp;
+  dp.B = B;
+  dp.P = P;
+  dp.num_classes = h->cfg.num_classes;
+  dp.mask_dim = h->cfg.mask_dim;
+  dp.top_k = h->cfg.nms_top_k;
+  dp.conf_thresh = h->cfg.nms_conf_thresh;
+  dp.nms_thresh = h->cfg.nms_thresh;
+  dp.max_dets = h->cfg.max_num_detections;
+  dp.conf_is_logits = conf_is_logits;
+  dp.cross_class = cross_class;
+  dp.max_out = max_out;
+  YB_REQUIRE(dp.nms_thresh > 0.f, "nms_threshold must be non negative.");  // detection.py:25-26
+  void* ws = h->get_detect_ws(detect_workspace_bytes(B, P, dp.num_classes, dp.top_k));
+  DetectWorkspace dws;
+  detect_workspace_bind(&dws, ws, B, P, dp.num_classes, dp.top_k);
+  launch_detect(dp, d_loc, d_conf, d_coef, d_priors, dws, d_box, d_coef_out, d_cls, d_score, d_count,
+                (cudaStream_t)stream, &h->lc);
+  YB_API_END
+}
+
+int yb_postprocess(yb_handle* h, const float* d_proto, int ph, int pw, int k, const float* d_coef, const float* d_box,
+                   int n, int out_h, int out_w, int crop_masks, int mask_format, void* d_masks, int64_t* d_boxes_px,
+                   float* d_proto_masks, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && d_proto && d_coef && d_box, "yb_postprocess: null argument");
+  YB_REQUIRE(n >= 0, "yb_postprocess: negative detection count");
+  DeviceGuard g(h->device);
+  launch_mask_assembly(d_proto, ph, pw, k, d_coef, d_box, n, out_h, out_w, crop_masks, mask_format, d_masks,
+                       d_boxes_px, d_proto_masks, (cudaStream_t)stream, &h->lc);
+  YB_API_END
+}
+
+int yb_maskiou(yb_handle* h, const float* d_proto_masks, int n, int ph, int pw, const int64_t* d_cls,
+               float* d_maskiou, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && d_proto_masks && d_cls && d_maskiou, "yb_maskiou: null argument");
+  YB_REQUIRE(h->cfg.use_maskiou && h->finalized, "yb_maskiou: network has no maskiou_net / weights not finalized");
+  if (n <= 0) return YB_OK;
+  DeviceGuard g(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  // FastMaskIoUNet (yolact.py:363-375, config.py:785-789): 5x (3x3 s2 p0 + ReLU), 1x1 + ReLU, global max
+  const char* idx[6] = {"0", "2", "4", "6", "8", "10"};
+  int H = ph, W = pw, C = 1;
+  size_t need = 0;
+  {
+    int hh = ph, ww = pw;
+    for (int i = 0; i < 6; ++i) {
+      ConvW& cw = h->convs[std::string("maskiou_net.maskiou_net.") + idx[i]];
+      int k = cw.KH, st = (i < 5) ? 2 : 1;
+      hh = (hh - k) / st + 1;
+      ww = (ww - k) / st + 1;
+      need = std::max(need, (size_t)n * hh * ww * cw.Cout * 4);
+    }
+  }
+  const size_t half = (need + 255) / 256 * 256;
+  char* scratch = (char*)h->get_scratch(2 * half);
+  const float* cur = d_proto_masks;
+  for (int i = 0; i < 6; ++i) {
+    ConvW& cw = h->convs[std::string("maskiou_net.maskiou_net.") + idx[i]];
+    YB_REQUIRE(cw.w_f32 && cw.Cin == C, "yb_maskiou: weights missing");
+    ConvProblem p;
+    p.B = n;
+    p.H = H;
+    p.W = W;
+    p.Cin = C;
+    p.KH = cw.KH;
+    p.KW = cw.KW;
+    p.stride = (i < 5) ? 2 : 1;
+    p.pad = 0;
+    p.Ho = (H - cw.KH) / p.stride + 1;
+    p.Wo = (W - cw.KW) / p.stride + 1;
+    YB_REQUIRE(p.Ho >= 1 && p.Wo >= 1, "yb_maskiou: mask too small for the network");
+    p.Cout = cw.Cout;
+    p.act = ACT_RELU;
+    p.x = cur;
+    float* out = (float*)(scratch + (i & 1) * half);
+    p.y = out;
+    p.y_f32 = 1;
+    p.y_batch_stride = (int64_t)p.Ho * p.Wo * cw.Cout;
+    p.y_pix_stride = cw.Cout;
+    p.bias = cw.bias;
+    launch_simt_conv(p, cw.w_f32, SIMT_F32, s, &h->lc);
+    cur = out;
+    H = p.Ho;
+    W = p.Wo;
+    C = cw.Cout;
+  }
+  launch_maxpool_gather(cur, n, H, W, C, d_cls, d_maskiou, s, &h->lc);
+  YB_API_END
+}
+
+int yb_dcn_forward(yb_handle* h, const float* d_input, const float* d_weight, const float* d_bias,
+                   const float* d_offset, const float* d_mask, float* d_output, int B, int C, int H, int W, int Co,
+                   int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w, int dilation_h,
+                   int dilation_w, int deformable_group, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && d_input && d_weight && d_offset && d_mask && d_output, "yb_dcn_forward: null argument");
+  YB_REQUIRE(kernel_h == 3 && kernel_w == 3, "yb_dcn_forward: only 3x3 kernels (all YOLACT++ DCN layers)");
+  YB_REQUIRE(stride_h == stride_w && pad_h == pad_w && dilation_h == dilation_w, "yb_dcn_forward: anisotropic params");
+  YB_REQUIRE(deformable_group == 1, "yb_dcn_forward: deformable_group must be 1");
+  YB_REQUIRE(C % 16 == 0, "yb_dcn_forward: C must be a multiple of 16");
+  DeviceGuard g(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Ho = (H + 2 * pad_h - (dilation_h * 2 + 1)) / stride_h + 1;
+  const int Wo = (W + 2 * pad_w - (dilation_w * 2 + 1)) / stride_w + 1;
+  TempPool tp;
+  float* om = (float*)tp.get((size_t)B * Ho * Wo * 27 * 4);
+  pack_om_kernel<<<grid1d((int64_t)B * Ho * Wo * 27), 256, 0, s>>>(d_offset, d_mask, om, B, Ho * Wo);
+  YB_CHECK_LAUNCH();
+  const int64_t wn = (int64_t)Co * C * 9;
+  const bool f16 = (h->cfg.precision == YB_PREC_F16TC);
+  if (!f16) {
+    float* x = (float*)tp.get((size_t)B * H * W * C * 4);
+    float* y = (float*)tp.get((size_t)B * Ho * Wo * Co * 4);
+    float* wk = (float*)tp.get((size_t)wn * 4);
+    launch_nchw_f32_to_nhwc<float>(d_input, x, B, C, H, W, s, &h->lc);
+    pack_w_simt_kernel<float><<<grid1d(wn), 256, 0, s>>>(d_weight, wk, Co, C, 9);
+    YB_CHECK_LAUNCH();
+    launch_dcn_simt<float>(x, om, wk, d_bias, y, B, H, W, C, Ho, Wo, Co, stride_h, pad_h, dilation_h, ACT_NONE, 0, s,
+                           &h->lc);
+    launch_nhwc_to_nchw_f32<float>(y, d_output, B, Ho, Wo, Co, s, &h->lc);
+  } else {
+    __half* x = (__half*)tp.get((size_t)B * H * W * C * 2);
+    __half* y = (__half*)tp.get((size_t)B * Ho * Wo * Co * 2);
+    launch_nchw_f32_to_nhwc<__half>(d_input, x, B, C, H, W, s, &h->lc);
+    if (C % 64 == 0) {
+      __half* cols = (__half*)tp.get((size_t)B * Ho * Wo * 9 * C * 2);
+      __half* wk = (__half*)tp.get((size_t)wn * 2);
+      pack_w_dcn_tc_kernel<<<grid1d(wn), 256, 0, s>>>(d_weight, wk, Co, C, 9);
+      YB_CHECK_LAUNCH();
+      launch_dcn_gather_f16(x, om, cols, B, H, W, C, Ho, Wo, stride_h, pad_h, dilation_h, 0, s, &h->lc);
+      ConvProblem p;
+      p.B = B;
+      p.H = Ho;
+      p.W = Wo;
+      p.Cin = 9 * C;
+      p.Ho = Ho;
+      p.Wo = Wo;
+      p.Cout = Co;
+      p.x = cols;
+      p.y = y;
+      p.y_batch_stride = (int64_t)Ho * Wo * Co;
+      p.y_pix_stride = Co;
+      p.bias = d_bias;
+      TcConvPlan* plan = tc_conv_plan_create(p, wk);
+      try {
+        launch_tc_conv(plan, s, &h->lc);
+      } catch (...) {
+        tc_conv_plan_destroy(plan);
+        throw;
+      }
+      tc_conv_plan_destroy(plan);
+    } else {
+      __half* wk = (__half*)tp.get((size_t)wn * 2);
+      pack_w_simt_kernel<__half><<<grid1d(wn), 256, 0, s>>>(d_weight, wk, Co, C, 9);
+      YB_CHECK_LAUNCH();
+      launch_dcn_simt<__half>(x, om, wk, d_bias, y, B, H, W, C, Ho, Wo, Co, stride_h, pad_h, dilation_h, ACT_NONE, 0,
+                              s, &h->lc);
+    }
+    launch_nhwc_to_nchw_f32<__half>(y, d_output, B, Ho, Wo, Co, s, &h->lc);
+  }
+  YB_CHECK_CUDA(cudaStreamSynchronize(s));  // temporaries are freed on return
+  YB_API_END
+}
+
+int yb_conv2d(yb_handle* h, const float* d_x, const float* h_w, const float* h_bias, const float* d_residual,
+              float* d_y, int B, int Ci, int H, int W, int Co, int kh, int kw, int stride, int pad, int act,
+              int precision, int iters, float* ms, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && d_x && h_w && d_y, "yb_conv2d: null argument");
+  YB_REQUIRE(precision >= 0 && precision <= 2, "yb_conv2d: precision must be 0 (f32 simt), 1 (f16 tcgen05), 2 (f16 simt)");
+  DeviceGuard g(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  YB_REQUIRE(Ho >= 1 && Wo >= 1, "yb_conv2d: empty output");
+  TempPool tp;
+  const int taps = kh * kw;
+  const size_t K = (size_t)taps * Ci;
+  const bool f16 = precision != 0;
+  const size_t es = f16 ? 2 : 4;
+  void* x = tp.get((size_t)B * H * W * Ci * es);
+  void* y = tp.get((size_t)B * Ho * Wo * Co * es);
+  void* res = d_residual ? tp.get((size_t)B * Ho * Wo * Co * es) : nullptr;
+  float* bias = nullptr;
+  if (h_bias) {
+    bias = (float*)tp.get((size_t)Co * 4);
+    YB_CHECK_CUDA(cudaMemcpy(bias, h_bias, (size_t)Co * 4, cudaMemcpyHostToDevice));
+  }
+  ConvProblem p;
+  p.B = B;
+  p.H = H;
+  p.W = W;
+  p.Cin = Ci;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.Cout = Co;
+  p.KH = kh;
+  p.KW = kw;
+  p.stride = stride;
+  p.pad = pad;
+  p.act = act;
+  p.x = x;
+  p.y = y;
+  p.y_batch_stride = (int64_t)Ho * Wo * Co;
+  p.y_pix_stride = Co;
+  p.bias = bias;
+  p.residual = res;
+  if (!f16) {
+    launch_nchw_f32_to_nhwc<float>(d_x, (float*)x, B, Ci, H, W, s, &h->lc);
+    if (res) launch_nchw_f32_to_nhwc<float>(d_residual, (float*)res, B, Co, Ho, Wo, s, &h->lc);
+  } else {
+    launch_nchw_f32_to_nhwc<__half>(d_x, (__half*)x, B, Ci, H, W, s, &h->lc);
+    if (res) launch_nchw_f32_to_nhwc<__half>(d_residual, (__half*)res, B, Co, Ho, Wo, s, &h->lc);
+  }
+  std::function<void()> run;
+  TcConvPlan* plan = nullptr;
+  if (precision == 1) {
+    YB_REQUIRE(tc_conv_supported(p), "yb_conv2d: shape not supported by the tcgen05 kernel (Cin % 64, taps <= 9)");
+    std::vector<__half> pk(K * Co);
+    for (int o = 0; o < Co; ++o)
+      for (int c = 0; c < Ci; ++c)
+        for (int t = 0; t < taps; ++t)
+          pk[((size_t)t * Co + o) * Ci + c] = __float2half_rn(h_w[((size_t)o * Ci + c) * taps + t]);
+    __half* wd = (__half*)tp.get(pk.size() * 2);
+    YB_CHECK_CUDA(cudaMemcpy(wd, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    plan = tc_conv_plan_create(p, wd);
+    run = [&]() { launch_tc_conv(plan, s, &h->lc); };
+  } else if (precision == 2) {
+    std::vector<__half> pk(K * Co);
+    for (int o = 0; o < Co; ++o)
+      for (int c = 0; c < Ci; ++c)
+        for (int t = 0; t < taps; ++t)
+          pk[((size_t)t * Ci + c) * Co + o] = __float2half_rn(h_w[((size_t)o * Ci + c) * taps + t]);
+    __half* wd = (__half*)tp.get(pk.size() * 2);
+    YB_CHECK_CUDA(cudaMemcpy(wd, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    run = [&, wd]() { launch_simt_conv(p, wd, SIMT_F16, s, &h->lc); };
+  } else {
+    std::vector<float> pk(K * Co);
+    for (int o = 0; o < Co; ++o)
+      for (int c = 0; c < Ci; ++c)
+        for (int t = 0; t < taps; ++t) pk[((size_t)t * Ci + c) * Co + o] = h_w[((size_t)o * Ci + c) * taps + t];
+    float* wd = (float*)tp.get(pk.size() * 4);
+    YB_CHECK_CUDA(cudaMemcpy(wd, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+    run = [&, wd]() { launch_simt_conv(p, wd, SIMT_F32, s, &h->lc); };
+  }
+  try {
+    run();  // warm-up + result
+    if (iters > 1 || ms) {
+      const int n = std::max(1, iters);
+      cudaEvent_t e0, e1;
+      YB_CHECK_CUDA(cudaEventCreate(&e0));
+      YB_CHECK_CUDA(cudaEventCreate(&e1));
+      YB_CHECK_CUDA(cudaEventRecord(e0, s));
+      for (int i = 0; i < n; ++i) run();
+      YB_CHECK_CUDA(cudaEventRecord(e1, s));
+      YB_CHECK_CUDA(cudaEventSynchronize(e1));
+      float t = 0.f;
+      YB_CHECK_CUDA(cudaEventElapsedTime(&t, e0, e1));
+      if (ms) *ms = t / n;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
+  } catch (...) {
+    if (plan) tc_conv_plan_destroy(plan);
+    throw;
+  }
+  if (plan) tc_conv_plan_destroy(plan);
+  if (!f16)
+    launch_nhwc_to_nchw_f32<float>((const float*)y, d_y, B, Ho, Wo, Co, s, &h->lc);
+  else
+    launch_nhwc_to_nchw_f32<__half>((const __half*)y, d_y, B, Ho, Wo, Co, s, &h->lc);
+  YB_CHECK_CUDA(cudaStreamSynchronize(s));
+  YB_API_END
+}
+
+int64_t yb_launch_count(yb_handle* h) { return h ? h->lc.n : 0; }
+
+int yb_set_profiling(yb_handle* h, int enable) {
+  YB_API_BEGIN
+  YB_REQUIRE(h, "null handle");
+  h->profiling = enable != 0;
+  YB_API_END
+}
+
+int yb_last_forward_ms(yb_handle* h, float* total_ms, float* conv_ms) {
+  YB_API_BEGIN
+  YB_REQUIRE(h, "null handle");
+  if (total_ms) *total_ms = h->last_total_ms;
+  if (conv_ms) *conv_ms = h->last_conv_ms;
+  YB_API_END
+}
+
+int yb_set_graphs(yb_handle* h, int enable) {
+  YB_API_BEGIN
+  YB_REQUIRE(h, "null handle");
+  h->use_graphs = enable != 0;
+  YB_API_END
+}
+
+}  // extern "C"

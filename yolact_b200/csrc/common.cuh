@@ -1,0 +1,88 @@
+// Shared helpers for the yolact_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <stdexcept>
+
+#include "../../include/yolact_b200.h"
+
+namespace yb {
+
+// ---- error plumbing -------------------------------------------------------------------------
+struct Error : public std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& msg);
+
+#define YB_CHECK_CUDA(expr)                                                                    \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      throw ::yb::Error(YB_ERR_CUDA, std::string(#expr) + " failed: " + cudaGetErrorString(_e) + \
+                                         " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    }                                                                                          \
+  } while (0)
+
+#define YB_REQUIRE(cond, msg)                                                                  \
+  do {                                                                                         \
+    if (!(cond)) {                                                                             \
+      throw ::yb::Error(YB_ERR_INVALID, std::string(msg) + " [" #cond "] (" + __FILE__ + ":" + \
+                                            std::to_string(__LINE__) + ")");                   \
+    }                                                                                          \
+  } while (0)
+
+// Checks the launch itself (not completion); cheap and capture-safe.
+#define YB_CHECK_LAUNCH() YB_CHECK_CUDA(cudaGetLastError())
+
+// ---- enums shared by kernels ----------------------------------------------------------------
+enum ActKind : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_LEAKY = 3 };
+
+template <typename T>
+struct DType;
+template <>
+struct DType<float> {
+  static constexpr int kVec = 4;  // elements per 16-byte vector
+};
+template <>
+struct DType<__half> {
+  static constexpr int kVec = 8;
+};
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) {
+  // saturate instead of producing inf: fp16 max is 65504
+  v = fminf(fmaxf(v, -65504.f), 65504.f);
+  return __float2half_rn(v);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.f);
+    case ACT_TANH: return tanhf(v);
+    case ACT_LEAKY: return v > 0.f ? v : 0.1f * v;
+    default: return v;
+  }
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Launch counter (per handle); every launcher takes one of these.
+struct LaunchCounter {
+  int64_t n = 0;
+};
+
+}  // namespace yb

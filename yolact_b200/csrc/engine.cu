@@ -1,0 +1,774 @@
+// Engine: see engine.cuh.  Topology follows the reference graph (file:line cited per block);
+// the execution plan (NHWC, fused epilogues, direct writes into the concatenated head tensors,
+// CUDA graph replay) is this repo's own.
+#include "engine.cuh"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace yb {
+
+// ---------------------------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------------------------
+static void* dmalloc(std::vector<void*>& pool, size_t bytes) {
+  void* p = nullptr;
+  YB_CHECK_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 256)));
+  pool.push_back(p);
+  return p;
+}
+
+Executor::~Executor() {
+  if (graph_fwd) cudaGraphExecDestroy(graph_fwd);
+  if (graph_infer) cudaGraphExecDestroy(graph_infer);
+  for (auto* p : plans) tc_conv_plan_destroy(p);
+  for (void* p : allocs) cudaFree(p);
+}
+
+struct CopySegs {
+  const void* src[8];
+  void* dst[8];
+  unsigned long long bytes[8];
+  int n;
+};
+__global__ void multi_copy_kernel(CopySegs s) {
+  const int seg = blockIdx.y;
+  if (seg >= s.n) return;
+  const unsigned long long nb = s.bytes[seg];
+  const char* src = (const char*)s.src[seg];
+  char* dst = (char*)s.dst[seg];
+  const bool al = ((((uintptr_t)src) | ((uintptr_t)dst) | nb) & 15) == 0;
+  if (al) {
+    const uint4* s4 = (const uint4*)src;
+    uint4* d4 = (uint4*)dst;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nb / 16;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+      d4[i] = s4[i];
+  } else {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nb;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+      dst[i] = src[i];
+  }
+}
+void launch_multi_copy(const void* const* src, void* const* dst, const size_t* bytes, int n, cudaStream_t stream,
+                       LaunchCounter* lc) {
+  CopySegs s;
+  s.n = 0;
+  size_t mx = 0;
+  for (int i = 0; i < n && s.n < 8; ++i) {
+    if (!dst[i] || !src[i] || bytes[i] == 0) continue;
+    s.src[s.n] = src[i];
+    s.dst[s.n] = dst[i];
+    s.bytes[s.n] = bytes[i];
+    mx = std::max(mx, bytes[i]);
+    s.n++;
+  }
+  if (s.n == 0) return;
+  int gx = (int)std::min<size_t>(148 * 8, (mx / 16 + 255) / 256 + 1);
+  multi_copy_kernel<<<dim3(gx, s.n), 256, 0, stream>>>(s);
+  YB_CHECK_LAUNCH();
+  if (lc) lc->n++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// feature-map sizes and priors (PredictionModule.make_priors, yolact.py:214-263)
+// ---------------------------------------------------------------------------------------------
+static int conv_out(int h, int k, int s, int p) { return (h + 2 * p - k) / s + 1; }
+
+void compute_level_sizes(const yb_config& cfg, int H, int W, int level_hw[5][2], int* ph, int* pw) {
+  int hs[8], ws[8];
+  int n = 0;
+  if (cfg.backbone == YB_BACKBONE_RESNET) {
+    int h = conv_out(H, 7, 2, 3), w = conv_out(W, 7, 2, 3);  // stem (backbone.py:77)
+    h = conv_out(h, 3, 2, 1);                                 // maxpool (backbone.py:80)
+    w = conv_out(w, 3, 2, 1);
+    for (int i = 0; i < cfg.num_stages; ++i) {
+      if (i > 0) {
+        h = conv_out(h, 3, 2, 1);
+        w = conv_out(w, 3, 2, 1);
+      }
+      hs[n] = h;
+      ws[n] = w;
+      n++;
+    }
+  } else {
+    int h = H, w = W;  // _preconv 3x3 p1 (backbone.py:267)
+    for (int i = 0; i < cfg.num_stages; ++i) {
+      h = conv_out(h, 3, 2, 1);
+      w = conv_out(w, 3, 2, 1);
+      hs[n] = h;
+      ws[n] = w;
+      n++;
+    }
+  }
+  for (int l = 0; l < 3; ++l) {
+    level_hw[l][0] = hs[cfg.selected_layers[l]];
+    level_hw[l][1] = ws[cfg.selected_layers[l]];
+  }
+  for (int l = 3; l < 5; ++l) {  // FPN downsample layers 3x3 s2 p1 (yolact.py:298-302)
+    level_hw[l][0] = conv_out(level_hw[l - 1][0], 3, 2, 1);
+    level_hw[l][1] = conv_out(level_hw[l - 1][1], 3, 2, 1);
+  }
+  if (ph) *ph = level_hw[0][0] * 2;  // protonet bilinear x2 (config.py:691)
+  if (pw) *pw = level_hw[0][1] * 2;
+}
+
+std::vector<float> make_priors_host(const yb_config& cfg, const int level_hw[5][2]) {
+  // yolact.py:224-246: for j,i over the map; for ars in aspect_ratios (one list); for scale; for ar
+  // Python evaluates in double and torch.Tensor() rounds to fp32 at the end.
+  std::vector<float> out;
+  for (int l = 0; l < 5; ++l) {
+    const int ch = level_hw[l][0], cw = level_hw[l][1];
+    for (int j = 0; j < ch; ++j)
+      for (int i = 0; i < cw; ++i) {
+        const double x = (i + 0.5) / cw;
+        const double y = (j + 0.5) / ch;
+        for (int s = 0; s < cfg.num_scales; ++s)
+          for (int a = 0; a < cfg.num_ars; ++a) {
+            const double scale = (double)cfg.scales[l][s];
+            const double ar = sqrt((double)cfg.ars[a]);  // preapply_sqrt == False
+            const double w = scale * ar / cfg.max_size;  // use_pixel_scales
+            double hgt = scale / ar / cfg.max_size;
+            if (cfg.use_square_anchors) hgt = w;
+            out.push_back((float)x);
+            out.push_back((float)y);
+            out.push_back((float)w);
+            out.push_back((float)hgt);
+          }
+      }
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// network builder
+// ---------------------------------------------------------------------------------------------
+struct NetBuilder {
+  yb_handle* h;
+  Executor* ex;
+  bool dry;
+  bool f16;
+
+  size_t esize(const Act& a) const { return a.f32 ? 4 : (f16 ? 2 : 4); }
+
+  Act alloc_act(int B, int H, int W, int C, bool f32 = false) {
+    Act a;
+    a.B = B;
+    a.H = H;
+    a.W = W;
+    a.C = C;
+    a.f32 = f32 || !f16;
+    if (!dry) a.ptr = dmalloc(ex->allocs, (size_t)a.numel() * (a.f32 ? 4 : 2));
+    return a;
+  }
+
+  struct OutSpec {       // write into an existing fp32 buffer (concatenated head outputs)
+    float* base = nullptr;
+    int64_t batch_stride = 0;
+    int pix_stride = 0;
+  };
+
+  // conv (+ folded BN) (+ residual) (+ activation)
+  Act conv(const std::string& key, const std::string& bn, const Act& in, int k, int stride, int pad, int act,
+           const Act* residual = nullptr, bool out_f32 = false, const OutSpec* ospec = nullptr,
+           bool in_nchw = false, bool res_after_act = false) {
+    ConvProblem p;
+    p.B = in.B;
+    p.H = in.H;
+    p.W = in.W;
+    p.Cin = in.C;
+    p.KH = p.KW = k;
+    p.stride = stride;
+    p.pad = pad;
+    p.act = act;
+    p.res_after_act = res_after_act ? 1 : 0;
+    p.Ho = conv_out(in.H, k, stride, pad);
+    p.Wo = conv_out(in.W, k, stride, pad);
+    p.x = in.ptr;
+    p.x_nchw_f32 = in_nchw ? 1 : 0;
+    const bool tc = f16 && !in_nchw && (in.C % 64 == 0) && !in.f32;
+    const bool simt_half = f16 && !tc && !in.f32;
+    ConvW& w = h->get_conv(key, bn, /*want_tc=*/tc, /*want_f32=*/!tc && !simt_half, /*want_f16=*/simt_half);
+    YB_REQUIRE(w.Cin == in.C && w.KH == k && w.KW == k, ("conv " + key + ": weight shape mismatch").c_str());
+    p.Cout = w.Cout;
+    p.bias = w.bias;
+    Act out;
+    if (ospec) {
+      out.B = in.B;
+      out.H = p.Ho;
+      out.W = p.Wo;
+      out.C = w.Cout;
+      out.f32 = true;
+      out.ptr = ospec->base;
+      p.y = ospec->base;
+      p.y_f32 = 1;
+      p.y_batch_stride = ospec->batch_stride;
+      p.y_pix_stride = ospec->pix_stride;
+    } else {
+      out = alloc_act(in.B, p.Ho, p.Wo, w.Cout, out_f32);
+      p.y = out.ptr;
+      p.y_f32 = (f16 && out.f32) ? 1 : 0;
+      p.y_batch_stride = (int64_t)p.Ho * p.Wo * w.Cout;
+      p.y_pix_stride = w.Cout;
+    }
+    if (residual) {
+      YB_REQUIRE(residual->H == p.Ho && residual->W == p.Wo && residual->C == w.Cout && residual->f32 == !f16,
+                 ("conv " + key + ": residual shape mismatch").c_str());
+      p.residual = residual->ptr;
+    }
+    if (dry) return out;
+    LaunchCounter* lc = &h->lc;
+    Op op;
+    op.is_conv = true;
+    if (tc) {
+      YB_REQUIRE(tc_conv_supported(p), ("conv " + key + ": not supported by the tensor-core kernel").c_str());
+      TcConvPlan* plan = tc_conv_plan_create(p, w.w_tc);
+      ex->plans.push_back(plan);
+      op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
+    } else {
+      int types;
+      if (!f16 || in.f32) {
+        // fp32 activations in; output fp32, or fp16 when this is the stem of the fp16 network
+        types = (f16 && !out.f32) ? SIMT_F32IN_F16OUT : SIMT_F32;
+      } else {
+        types = SIMT_F16;
+      }
+      const void* wp = (types == SIMT_F16) ? (const void*)w.w_f16 : (const void*)w.w_f32;
+      YB_REQUIRE(wp != nullptr, ("conv " + key + ": weights not packed for the SIMT kernel").c_str());
+      op.fn = [p, wp, types, lc](cudaStream_t s) { launch_simt_conv(p, wp, types, s, lc); };
+    }
+    ex->ops.push_back(op);
+    return out;
+  }
+
+  Act maxpool(const Act& in) {
+    Act out = alloc_act(in.B, conv_out(in.H, 3, 2, 1), conv_out(in.W, 3, 2, 1), in.C);
+    if (dry) return out;
+    LaunchCounter* lc = &h->lc;
+    Op op;
+    if (f16)
+      op.fn = [in, out, lc](cudaStream_t s) {
+        launch_maxpool3x3s2<__half>((const __half*)in.ptr, (__half*)out.ptr, in.B, in.H, in.W, in.C, out.H, out.W, s, lc);
+      };
+    else
+      op.fn = [in, out, lc](cudaStream_t s) {
+        launch_maxpool3x3s2<float>((const float*)in.ptr, (float*)out.ptr, in.B, in.H, in.W, in.C, out.H, out.W, s, lc);
+      };
+    ex->ops.push_back(op);
+    return out;
+  }
+
+  // out = bilinear(in -> [Ho,Wo]) (+ add)
+  Act upsample(const Act& in, int Ho, int Wo, float sh, float sw, const Act* add, int relu) {
+    Act out = alloc_act(in.B, Ho, Wo, in.C);
+    if (dry) return out;
+    LaunchCounter* lc = &h->lc;
+    const void* addp = add ? add->ptr : nullptr;
+    Op op;
+    if (f16)
+      op.fn = [in, out, addp, sh, sw, relu, lc](cudaStream_t s) {
+        launch_upsample_bilinear<__half>((const __half*)in.ptr, (const __half*)addp, (__half*)out.ptr, in.B, in.H,
+                                         in.W, in.C, out.H, out.W, sh, sw, relu, s, lc);
+      };
+    else
+      op.fn = [in, out, addp, sh, sw, relu, lc](cudaStream_t s) {
+        launch_upsample_bilinear<float>((const float*)in.ptr, (const float*)addp, (float*)out.ptr, in.B, in.H, in.W,
+                                        in.C, out.H, out.W, sh, sw, relu, s, lc);
+      };
+    ex->ops.push_back(op);
+    return out;
+  }
+
+  // DCN block conv2 (backbone.py:21-26): offset/mask conv + modulated deformable conv + BN + ReLU
+  Act dcn(const std::string& key, const std::string& bn, const Act& in, int stride) {
+    // conv_offset_mask: 3x3, same stride/pad, bias, 27 channels, fp32 output (dcn_v2.py:106-124)
+    Act om = conv(key + ".conv_offset_mask", "", in, 3, stride, 1, ACT_NONE, nullptr, /*out_f32=*/true);
+    const bool tc = f16;
+    ConvW& w = h->get_conv(key, bn, /*want_tc=*/tc, /*want_f32=*/!tc, /*want_f16=*/false, /*dcn_pack=*/true);
+    const int Ho = om.H, Wo = om.W;
+    Act out = alloc_act(in.B, Ho, Wo, w.Cout);
+    if (dry) return out;
+    LaunchCounter* lc = &h->lc;
+    if (!tc) {
+      const float* wp = w.w_f32;
+      const float* bias = w.bias;
+      Op op;
+      op.is_conv = true;
+      const int Cout = w.Cout;
+      op.fn = [in, om, out, wp, bias, stride, Cout, lc](cudaStream_t s) {
+        launch_dcn_simt<float>((const float*)in.ptr, (const float*)om.ptr, wp, bias, (float*)out.ptr, in.B, in.H, in.W,
+                               in.C, out.H, out.W, Cout, stride, 1, 1, ACT_RELU, 1, s, lc);
+      };
+      ex->ops.push_back(op);
+    } else {
+      // gather -> fp16 columns [B,Ho,Wo,9C]; contraction = 1x1 conv with K = 9C on tcgen05
+      Act cols = alloc_act(in.B, Ho, Wo, 9 * in.C);
+      Op g;
+      g.is_conv = true;
+      g.fn = [in, om, cols, stride, lc](cudaStream_t s) {
+        launch_dcn_gather_f16((const __half*)in.ptr, (const float*)om.ptr, (__half*)cols.ptr, in.B, in.H, in.W, in.C,
+                              cols.H, cols.W, stride, 1, 1, 1, s, lc);
+      };
+      ex->ops.push_back(g);
+      ConvProblem p;
+      p.B = in.B;
+      p.H = Ho;
+      p.W = Wo;
+      p.Cin = 9 * in.C;
+      p.Ho = Ho;
+      p.Wo = Wo;
+      p.Cout = w.Cout;
+      p.KH = p.KW = 1;
+      p.stride = 1;
+      p.pad = 0;
+      p.act = ACT_RELU;
+      p.x = cols.ptr;
+      p.y = out.ptr;
+      p.y_batch_stride = (int64_t)Ho * Wo * w.Cout;
+      p.y_pix_stride = w.Cout;
+      p.bias = w.bias;
+      TcConvPlan* plan = tc_conv_plan_create(p, w.w_tc);
+      ex->plans.push_back(plan);
+      Op op;
+      op.is_conv = true;
+      op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
+      ex->ops.push_back(op);
+    }
+    return out;
+  }
+};
+
+static bool block_uses_dcn(const yb_config& cfg, int stage, int j) {
+  // backbone.py:112-118
+  const int blocks = cfg.layers[stage];
+  const int dl = cfg.dcn_layers[stage];
+  if (j == 0) return dl >= blocks;
+  const int interval = cfg.dcn_interval > 0 ? cfg.dcn_interval : 1;
+  return ((j + dl) >= blocks) && (j % interval == 0);
+}
+
+void build_network(yb_handle* h, Executor* ex, bool dry) {
+  const yb_config& cfg = h->cfg;
+  NetBuilder nb{h, ex, dry, cfg.precision == YB_PREC_F16TC};
+  const int B = ex->B, H = ex->H, W = ex->W;
+  const int NC = cfg.num_classes, MD = cfg.mask_dim, A = cfg.num_scales * cfg.num_ars;
+
+  compute_level_sizes(cfg, H, W, ex->level_hw, &ex->ph, &ex->pw);
+  ex->P = 0;
+  int64_t level_off[5];
+  for (int l = 0; l < 5; ++l) {
+    level_off[l] = ex->P;
+    ex->P += (int64_t)ex->level_hw[l][0] * ex->level_hw[l][1] * A;
+  }
+  if (!dry) {
+    ex->d_in = (float*)dmalloc(ex->allocs, (size_t)B * 3 * H * W * 4);
+    ex->loc = (float*)dmalloc(ex->allocs, (size_t)B * ex->P * 4 * 4);
+    ex->conf = (float*)dmalloc(ex->allocs, (size_t)B * ex->P * NC * 4);
+    ex->coef = (float*)dmalloc(ex->allocs, (size_t)B * ex->P * MD * 4);
+    std::vector<float> pri = make_priors_host(cfg, ex->level_hw);
+    YB_REQUIRE((int64_t)pri.size() == ex->P * 4, "prior count mismatch");
+    ex->priors = (float*)dmalloc(ex->allocs, pri.size() * 4);
+    YB_CHECK_CUDA(cudaMemcpy(ex->priors, pri.data(), pri.size() * 4, cudaMemcpyHostToDevice));
+  }
+
+  // ---------------- backbone ----------------
+  Act in;
+  in.B = B;
+  in.H = H;
+  in.W = W;
+  in.C = 3;
+  in.f32 = true;
+  in.ptr = ex->d_in;
+  std::vector<Act> outs;
+  if (cfg.backbone == YB_BACKBONE_RESNET) {
+    // backbone.py:126-139: conv1 7x7/2 + bn1 + relu + maxpool, then Bottleneck stages
+    Act x = nb.conv("backbone.conv1", "backbone.bn1", in, 7, 2, 3, ACT_RELU, nullptr, false, nullptr, /*nchw*/ true);
+    x = nb.maxpool(x);
+    for (int i = 0; i < cfg.num_stages; ++i) {
+      const int stride = (i == 0) ? 1 : 2;
+      for (int j = 0; j < cfg.layers[i]; ++j) {
+        const std::string n = "backbone.layers." + std::to_string(i) + "." + std::to_string(j);
+        // Bottleneck.forward, backbone.py:37-57 (stride on conv2, :22,28)
+        Act o = nb.conv(n + ".conv1", n + ".bn1", x, 1, 1, 0, ACT_RELU);
+        const int s2 = (j == 0) ? stride : 1;
+        if (block_uses_dcn(cfg, i, j))
+          o = nb.dcn(n + ".conv2", n + ".bn2", o, s2);
+        else
+          o = nb.conv(n + ".conv2", n + ".bn2", o, 3, s2, 1, ACT_RELU);
+        Act identity = x;
+        if (j == 0) identity = nb.conv(n + ".downsample.0", n + ".downsample.1", x, 1, stride, 0, ACT_NONE);
+        x = nb.conv(n + ".conv3", n + ".bn3", o, 1, 1, 0, ACT_RELU, &identity);
+      }
+      outs.push_back(x);
+      if (i < 4) ex->feats[i] = x;
+    }
+  } else {
+    // DarkNetBackbone.forward, backbone.py:299-309; conv -> BN -> LeakyReLU(0.1) (:222-233);
+    // DarkNetBlock: conv2(conv1(x)) + x with no activation after the add (:235-247)
+    Act x = nb.conv("backbone._preconv.0", "backbone._preconv.1", in, 3, 1, 1, ACT_LEAKY, nullptr, false, nullptr, true);
+    for (int i = 0; i < cfg.num_stages; ++i) {
+      const std::string ln = "backbone.layers." + std::to_string(i);
+      x = nb.conv(ln + ".0.0", ln + ".0.1", x, 3, 2, 1, ACT_LEAKY);
+      for (int j = 0; j < cfg.layers[i]; ++j) {
+        const std::string n = ln + "." + std::to_string(j + 1);
+        Act o = nb.conv(n + ".conv1.0", n + ".conv1.1", x, 1, 1, 0, ACT_LEAKY);
+        // the add happens AFTER conv2's LeakyReLU and nothing follows it (backbone.py:246-247)
+        x = nb.conv(n + ".conv2.0", n + ".conv2.1", o, 3, 1, 1, ACT_LEAKY, &x, false, nullptr, false, /*res_after_act=*/true);
+      }
+      outs.push_back(x);
+      if (i < 4) ex->feats[i] = x;
+    }
+  }
+
+  // ---------------- FPN (yolact.py:311-361) ----------------
+  Act C[3] = {outs[cfg.selected_layers[0]], outs[cfg.selected_layers[1]], outs[cfg.selected_layers[2]]};
+  // lat_layers / pred_layers are stored in reverse: index 0 <-> deepest level (yolact.py:286-289,324-341)
+  Act x5 = nb.conv("fpn.lat_layers.0", "", C[2], 1, 1, 0, ACT_NONE);
+  Act l4 = nb.conv("fpn.lat_layers.1", "", C[1], 1, 1, 0, ACT_NONE);
+  Act x4 = nb.upsample(x5, l4.H, l4.W, (float)x5.H / (float)l4.H, (float)x5.W / (float)l4.W, &l4, 0);
+  Act l3 = nb.conv("fpn.lat_layers.2", "", C[0], 1, 1, 0, ACT_NONE);
+  Act x3 = nb.upsample(x4, l3.H, l3.W, (float)x4.H / (float)l3.H, (float)x4.W / (float)l3.W, &l3, 0);
+  Act Pl[5];
+  Pl[2] = nb.conv("fpn.pred_layers.0", "", x5, 3, 1, 1, ACT_RELU);
+  Pl[1] = nb.conv("fpn.pred_layers.1", "", x4, 3, 1, 1, ACT_RELU);
+  Pl[0] = nb.conv("fpn.pred_layers.2", "", x3, 3, 1, 1, ACT_RELU);
+  Pl[3] = nb.conv("fpn.downsample_layers.0", "", Pl[2], 3, 2, 1, ACT_NONE);
+  Pl[4] = nb.conv("fpn.downsample_layers.1", "", Pl[3], 3, 2, 1, ACT_NONE);
+  for (int l = 0; l < 5; ++l) ex->feats[4 + l] = Pl[l];
+
+  // ---------------- protonet on P3 (config.py:691, utils/functions.py:163-213, yolact.py:588-599) ----
+  {
+    Act p = nb.conv("proto_net.0", "", Pl[0], 3, 1, 1, ACT_RELU);
+    p = nb.conv("proto_net.2", "", p, 3, 1, 1, ACT_RELU);
+    p = nb.conv("proto_net.4", "", p, 3, 1, 1, ACT_RELU);
+    p = nb.upsample(p, p.H * 2, p.W * 2, 0.5f, 0.5f, nullptr, 1);  // InterpolateModule(scale_factor=2) + ReLU
+    p = nb.conv("proto_net.8", "", p, 3, 1, 1, ACT_RELU);
+    // 1x1 -> mask_dim, then mask_proto_prototype_activation = relu (yolact.py:589); NHWC fp32 == permute(0,2,3,1)
+    p = nb.conv("proto_net.10", "", p, 1, 1, 0, ACT_RELU, nullptr, /*out_f32=*/true);
+    ex->proto = (float*)p.ptr;
+    YB_REQUIRE(p.H == ex->ph && p.W == ex->pw && p.C == MD, "proto shape mismatch");
+  }
+
+  // ---------------- shared prediction head over the 5 levels (yolact.py:133-212, 616-634) -----------
+  for (int l = 0; l < 5; ++l) {
+    const std::string hn = "prediction_layers.0";
+    Act u = nb.conv(hn + ".upfeature.0", "", Pl[l], 3, 1, 1, ACT_RELU);
+    NetBuilder::OutSpec os;
+    os.base = ex->loc ? ex->loc + level_off[l] * 4 : nullptr;
+    os.batch_stride = ex->P * 4;
+    os.pix_stride = A * 4;
+    nb.conv(hn + ".bbox_layer", "", u, 3, 1, 1, ACT_NONE, nullptr, true, &os);
+    os.base = ex->conf ? ex->conf + level_off[l] * NC : nullptr;
+    os.batch_stride = ex->P * NC;
+    os.pix_stride = A * NC;
+    nb.conv(hn + ".conf_layer", "", u, 3, 1, 1, ACT_NONE, nullptr, true, &os);
+    os.base = ex->coef ? ex->coef + level_off[l] * MD : nullptr;
+    os.batch_stride = ex->P * MD;
+    os.pix_stride = A * MD;
+    nb.conv(hn + ".mask_layer", "", u, 3, 1, 1, ACT_TANH, nullptr, true, &os);  // mask_proto_coeff_activation = tanh
+  }
+}
+
+}  // namespace yb
+
+// ---------------------------------------------------------------------------------------------
+// yb_handle
+// ---------------------------------------------------------------------------------------------
+using namespace yb;
+
+yb_handle::~yb_handle() {
+  execs.clear();
+  for (void* p : weight_allocs) cudaFree(p);
+  if (detect_ws) cudaFree(detect_ws);
+  if (scratch) cudaFree(scratch);
+}
+
+void* yb_handle::get_scratch(size_t bytes) {
+  if (bytes > scratch_bytes) {
+    if (scratch) {
+      YB_CHECK_CUDA(cudaDeviceSynchronize());
+      cudaFree(scratch);
+      scratch = nullptr;
+    }
+    YB_CHECK_CUDA(cudaMalloc(&scratch, bytes));
+    scratch_bytes = bytes;
+  }
+  return scratch;
+}
+
+void* yb_handle::get_detect_ws(size_t bytes) {
+  if (bytes > detect_ws_bytes) {
+    if (detect_ws) {
+      YB_CHECK_CUDA(cudaDeviceSynchronize());
+      cudaFree(detect_ws);
+      detect_ws = nullptr;
+    }
+    YB_CHECK_CUDA(cudaMalloc(&detect_ws, bytes));
+    detect_ws_bytes = bytes;
+  }
+  return detect_ws;
+}
+
+static const HostTensor& need(yb_handle* h, const std::string& name) {
+  auto it = h->host.find(name);
+  if (it == h->host.end()) throw Error(YB_ERR_MISSING_WEIGHT, "missing weight: " + name);
+  return it->second;
+}
+
+ConvW& yb_handle::get_conv(const std::string& conv_key, const std::string& bn_key, bool want_tc, bool want_f32,
+                           bool want_f16, bool dcn_pack) {
+  ConvW& cw = convs[conv_key];
+  const HostTensor& w = need(this, conv_key + ".weight");
+  YB_REQUIRE(w.shape.size() == 4, ("weight " + conv_key + " is not 4-D").c_str());
+  const int Co = (int)w.shape[0], Ci = (int)w.shape[1], KH = (int)w.shape[2], KW = (int)w.shape[3];
+  if (cw.Cout == 0) {
+    cw.Cin = Ci;
+    cw.Cout = Co;
+    cw.KH = KH;
+    cw.KW = KW;
+    cw.dcn_pack = dcn_pack;
+  }
+  const bool has_bias = host.count(conv_key + ".bias") > 0;
+  const bool has_bn = !bn_key.empty();
+  const bool need_f32 = want_f32 && !cw.w_f32;
+  const bool need_tc = want_tc && !cw.w_tc;
+  const bool need_f16 = want_f16 && !cw.w_f16;
+  if (!need_f32 && !need_tc && !need_f16 && (cw.bias || (!has_bias && !has_bn))) return cw;
+
+  // fold BatchNorm (eval mode, eps = 1e-5): w' = w * g/sqrt(v+eps); b' = beta + (b - mean) * g/sqrt(v+eps)
+  std::vector<float> scale(Co, 1.f), shift(Co, 0.f);
+  if (has_bias) {
+    const HostTensor& b = need(this, conv_key + ".bias");
+    YB_REQUIRE(b.numel() == Co, ("bias " + conv_key + " has the wrong size").c_str());
+    for (int o = 0; o < Co; ++o) shift[o] = b.data[o];
+  }
+  if (has_bn) {
+    const HostTensor& g = need(this, bn_key + ".weight");
+    const HostTensor& be = need(this, bn_key + ".bias");
+    const HostTensor& mu = need(this, bn_key + ".running_mean");
+    const HostTensor& var = need(this, bn_key + ".running_var");
+    YB_REQUIRE(g.numel() == Co && be.numel() == Co && mu.numel() == Co && var.numel() == Co,
+               ("batchnorm " + bn_key + " has the wrong size").c_str());
+    for (int o = 0; o < Co; ++o) {
+      const float s = g.data[o] / sqrtf(var.data[o] + 1e-5f);
+      scale[o] = s;
+      shift[o] = be.data[o] + (shift[o] - mu.data[o]) * s;
+    }
+  }
+  const int taps = KH * KW;
+  const size_t K = (size_t)taps * Ci;
+  if (need_f32) {
+    std::vector<float> pk(K * Co);
+    for (int o = 0; o < Co; ++o)
+      for (int c = 0; c < Ci; ++c)
+        for (int t = 0; t < taps; ++t)
+          pk[((size_t)t * Ci + c) * Co + o] = w.data[((size_t)o * Ci + c) * taps + t] * scale[o];
+    cw.w_f32 = (float*)dmalloc(weight_allocs, pk.size() * 4);
+    YB_CHECK_CUDA(cudaMemcpy(cw.w_f32, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+  }
+  if (need_f16) {
+    std::vector<__half> pk(K * Co);
+    for (int o = 0; o < Co; ++o)
+      for (int c = 0; c < Ci; ++c)
+        for (int t = 0; t < taps; ++t)
+          pk[((size_t)t * Ci + c) * Co + o] = __float2half_rn(w.data[((size_t)o * Ci + c) * taps + t] * scale[o]);
+    cw.w_f16 = (__half*)dmalloc(weight_allocs, pk.size() * 2);
+    YB_CHECK_CUDA(cudaMemcpy(cw.w_f16, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+  }
+  if (need_tc) {
+    std::vector<__half> pk(K * Co);
+    if (dcn_pack) {
+      // [Cout][tap*Cin + c]: the contraction runs as a 1x1 conv over gathered columns
+      for (int o = 0; o < Co; ++o)
+        for (int c = 0; c < Ci; ++c)
+          for (int t = 0; t < taps; ++t)
+            pk[(size_t)o * K + (size_t)t * Ci + c] = __float2half_rn(w.data[((size_t)o * Ci + c) * taps + t] * scale[o]);
+    } else {
+      for (int o = 0; o < Co; ++o)
+        for (int c = 0; c < Ci; ++c)
+          for (int t = 0; t < taps; ++t)
+            pk[((size_t)t * Co + o) * Ci + c] = __float2half_rn(w.data[((size_t)o * Ci + c) * taps + t] * scale[o]);
+    }
+    cw.w_tc = (__half*)dmalloc(weight_allocs, pk.size() * 2);
+    YB_CHECK_CUDA(cudaMemcpy(cw.w_tc, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+  }
+  if (!cw.bias && (has_bias || has_bn)) {
+    cw.bias = (float*)dmalloc(weight_allocs, (size_t)Co * 4);
+    YB_CHECK_CUDA(cudaMemcpy(cw.bias, shift.data(), (size_t)Co * 4, cudaMemcpyHostToDevice));
+  }
+  return cw;
+}
+
+void yb_handle::finalize() {
+  YB_REQUIRE(!ops_only, "finalize: this handle was created without a network");
+  execs.clear();
+  last_exec = nullptr;
+  // drop previously packed weights (weights may be re-loaded)
+  YB_CHECK_CUDA(cudaDeviceSynchronize());
+  for (void* p : weight_allocs) cudaFree(p);
+  weight_allocs.clear();
+  convs.clear();
+  Executor dry;
+  dry.B = 1;
+  dry.H = cfg.max_size;
+  dry.W = cfg.max_size;
+  build_network(this, &dry, /*dry=*/true);
+  if (cfg.use_maskiou) {
+    const char* idx[6] = {"0", "2", "4", "6", "8", "10"};
+    for (int i = 0; i < 6; ++i) get_conv(std::string("maskiou_net.maskiou_net.") + idx[i], "", false, true, false);
+  }
+  finalized = true;
+}
+
+Executor* yb_handle::get_executor(int B, int H, int W) {
+  YB_REQUIRE(finalized, "forward called before yb_finalize_weights");
+  const std::string key = std::to_string(B) + "x" + std::to_string(H) + "x" + std::to_string(W);
+  auto it = execs.find(key);
+  if (it != execs.end()) return it->second.get();
+  std::unique_ptr<Executor> ex(new Executor());
+  ex->B = B;
+  ex->H = H;
+  ex->W = W;
+  build_network(this, ex.get(), /*dry=*/false);
+  Executor* raw = ex.get();
+  execs[key] = std::move(ex);
+  return raw;
+}
+
+static void run_ops(yb_handle* h, Executor* ex, cudaStream_t stream) {
+  for (auto& op : ex->ops) op.fn(stream);
+}
+
+static void run_ops_profiled(yb_handle* h, Executor* ex, cudaStream_t stream) {
+  // eager, with an event pair around every op; conv share = sum over conv ops
+  std::vector<cudaEvent_t> ev(ex->ops.size() + 1);
+  for (auto& e : ev) YB_CHECK_CUDA(cudaEventCreate(&e));
+  YB_CHECK_CUDA(cudaEventRecord(ev[0], stream));
+  for (size_t i = 0; i < ex->ops.size(); ++i) {
+    ex->ops[i].fn(stream);
+    YB_CHECK_CUDA(cudaEventRecord(ev[i + 1], stream));
+  }
+  YB_CHECK_CUDA(cudaStreamSynchronize(stream));
+  float total = 0.f, conv = 0.f;
+  for (size_t i = 0; i < ex->ops.size(); ++i) {
+    float ms = 0.f;
+    YB_CHECK_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+    total += ms;
+    if (ex->ops[i].is_conv) conv += ms;
+  }
+  h->last_total_ms = total;
+  h->last_conv_ms = conv;
+  for (auto& e : ev) cudaEventDestroy(e);
+}
+
+void yb_handle::forward(const float* d_x, int B, int H, int W, float* d_loc, float* d_conf, float* d_coef,
+                        float* d_proto, cudaStream_t stream) {
+  Executor* ex = get_executor(B, H, W);
+  YB_CHECK_CUDA(cudaMemcpyAsync(ex->d_in, d_x, (size_t)B * 3 * H * W * 4, cudaMemcpyDeviceToDevice, stream));
+  last_exec = ex;
+  if (profiling) {
+    run_ops_profiled(this, ex, stream);
+  } else if (!use_graphs || ex->fwd_calls == 0) {
+    run_ops(this, ex, stream);  // first call eager: validates launches, sets function attributes
+  } else {
+    if (!ex->graph_fwd) {
+      cudaGraph_t g = nullptr;
+      const int64_t before = lc.n;
+      YB_CHECK_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        run_ops(this, ex, stream);
+      } catch (...) {
+        cudaStreamEndCapture(stream, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+      }
+      YB_CHECK_CUDA(cudaStreamEndCapture(stream, &g));
+      lc.n = before;  // capture does not launch
+      YB_CHECK_CUDA(cudaGraphInstantiate(&ex->graph_fwd, g, 0));
+      cudaGraphDestroy(g);
+    }
+    YB_CHECK_CUDA(cudaGraphLaunch(ex->graph_fwd, stream));
+    lc.n += (int64_t)ex->ops.size();
+  }
+  ex->fwd_calls++;
+  const void* src[4] = {ex->loc, ex->conf, ex->coef, ex->proto};
+  void* dst[4] = {d_loc, d_conf, d_coef, d_proto};
+  size_t bytes[4] = {(size_t)B * ex->P * 4 * 4, (size_t)B * ex->P * cfg.num_classes * 4,
+                     (size_t)B * ex->P * cfg.mask_dim * 4, (size_t)B * ex->ph * ex->pw * cfg.mask_dim * 4};
+  launch_multi_copy(src, dst, bytes, 4, stream, &lc);
+}
+
+void yb_handle::infer(const float* d_x, int B, int H, int W, int cross_class, int max_out, float* d_box,
+                      float* d_coef_out, int64_t* d_cls, float* d_score, int32_t* d_count, float* d_proto,
+                      cudaStream_t stream) {
+  Executor* ex = get_executor(B, H, W);
+  DetectParams dp;
+  dp.B = B;
+  dp.P = ex->P;
+  dp.num_classes = cfg.num_classes;
+  dp.mask_dim = cfg.mask_dim;
+  dp.top_k = cfg.nms_top_k;
+  dp.conf_thresh = cfg.nms_conf_thresh;
+  dp.nms_thresh = cfg.nms_thresh;
+  dp.max_dets = cfg.max_num_detections;
+  dp.conf_is_logits = 1;
+  dp.cross_class = cross_class;
+  dp.max_out = max_out;
+  if (!ex->det_ws || ex->det_max_out != max_out || ex->det_cross_class != cross_class) {
+    // (re)build the fused-detect buffers; invalidates the captured graph
+    YB_CHECK_CUDA(cudaDeviceSynchronize());
+    if (ex->graph_infer) {
+      cudaGraphExecDestroy(ex->graph_infer);
+      ex->graph_infer = nullptr;
+    }
+    ex->infer_calls = 0;
+    if (!ex->det_ws) {
+      ex->det_ws = dmalloc(ex->allocs, detect_workspace_bytes(B, ex->P, cfg.num_classes, cfg.nms_top_k));
+      detect_workspace_bind(&ex->dws, ex->det_ws, B, ex->P, cfg.num_classes, cfg.nms_top_k);
+    }
+    ex->det_box = (float*)dmalloc(ex->allocs, (size_t)B * max_out * 4 * 4);
+    ex->det_coef = (float*)dmalloc(ex->allocs, (size_t)B * max_out * cfg.mask_dim * 4);
+    ex->det_cls = (int64_t*)dmalloc(ex->allocs, (size_t)B * max_out * 8);
+    ex->det_score = (float*)dmalloc(ex->allocs, (size_t)B * max_out * 4);
+    ex->det_count = (int32_t*)dmalloc(ex->allocs, (size_t)B * 4);
+    ex->det_max_out = max_out;
+    ex->det_cross_class = cross_class;
+  }
+  auto run_all = [&](cudaStream_t s) {
+    run_ops(this, ex, s);
+    launch_detect(dp, ex->loc, ex->conf, ex->coef, ex->priors, ex->dws, ex->det_box, ex->det_coef, ex->det_cls,
+                  ex->det_score, ex->det_count, s, &lc);
+  };
+  YB_CHECK_CUDA(cudaMemcpyAsync(ex->d_in, d_x, (size_t)B * 3 * H * W * 4, cudaMemcpyDeviceToDevice, stream));
+  last_exec = ex;
+  if (!use_graphs || ex->infer_calls == 0) {
+    run_all(stream);
+  } else {
+    if (!ex->graph_infer) {
+      cudaGraph_t g = nullptr;
+      const int64_t before = lc.n;
+      YB_CHECK_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        run_all(stream);
+      } catch (...) {
+        cudaStreamEndCapture(stream, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+      }
+      YB_CHECK_CUDA(cudaStreamEndCapture(stream, &g));
+      lc.n = before;
+      YB_CHECK_CUDA(cudaGraphInstantiate(&ex->graph_infer, g, 0));
+      cudaGraphDestroy(g);
+    }
+    YB_CHECK_CUDA(cudaGraphLaunch(ex->graph_infer, stream));
+    lc.n += (int64_t)ex->ops.size() + (cross_class ? 2 : 3);
+  }
+  ex->infer_calls++;
+  const void* src[6] = {ex->det_box, ex->det_coef, ex->det_cls, ex->det_score, ex->det_count, ex->proto};
+  void* dst[6] = {d_box, d_coef_out, d_cls, d_score, d_count, d_proto};
+  size_t bytes[6] = {(size_t)B * max_out * 16, (size_t)B * max_out * cfg.mask_dim * 4, (size_t)B * max_out * 8,
+                     (size_t)B * max_out * 4, (size_t)B * 4, (size_t)B * ex->ph * ex->pw * cfg.mask_dim * 4};
+  launch_multi_copy(src, dst, bytes, 6, stream, &lc);
+}

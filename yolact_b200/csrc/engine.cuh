@@ -1,0 +1,123 @@
+// Host-side engine: weight store (reference state_dict names), BatchNorm folding + repacking,
+// per-input-shape executors (activation buffers, kernel plans, CUDA graph), Detect workspaces.
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace yb {
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+// One convolution's device-resident parameters (BatchNorm already folded).
+struct ConvW {
+  int Cin = 0, Cout = 0, KH = 0, KW = 0;
+  float* w_f32 = nullptr;    // [KH*KW*Cin][Cout]           (SIMT fp32)
+  __half* w_f16 = nullptr;   // [KH*KW*Cin][Cout]           (SIMT fp16)
+  __half* w_tc = nullptr;    // [KH*KW][Cout][Cin]          (tcgen05), or [1][Cout][9*Cin] for DCN
+  float* bias = nullptr;     // [Cout] or null
+  bool dcn_pack = false;
+};
+
+// NHWC activation (element type float in YB_PREC_F32, __half in YB_PREC_F16TC unless f32 is set)
+struct Act {
+  void* ptr = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+  bool f32 = false;
+  int64_t numel() const { return (int64_t)B * H * W * C; }
+};
+
+struct Op {
+  std::function<void(cudaStream_t)> fn;
+  bool is_conv = false;
+};
+
+struct Executor {
+  int B = 0, H = 0, W = 0;
+  std::vector<void*> allocs;
+  std::vector<TcConvPlan*> plans;
+  std::vector<Op> ops;           // the conv stack (yb_forward)
+  float* d_in = nullptr;         // NCHW fp32 copy of the input (stable address for graph replay)
+  float* loc = nullptr;          // [B,P,4]
+  float* conf = nullptr;         // [B,P,C] logits
+  float* coef = nullptr;         // [B,P,k]
+  float* proto = nullptr;        // [B,ph,pw,k]
+  float* priors = nullptr;       // [P,4]
+  int64_t P = 0;
+  int ph = 0, pw = 0;
+  int level_hw[5][2] = {};
+  Act feats[9];                  // C2..C5 (0..3), P3..P7 (4..8)
+  // fused Detect (yb_infer)
+  void* det_ws = nullptr;
+  DetectWorkspace dws;
+  float* det_box = nullptr;
+  float* det_coef = nullptr;
+  int64_t* det_cls = nullptr;
+  float* det_score = nullptr;
+  int32_t* det_count = nullptr;
+  int det_max_out = 0;
+  int det_cross_class = -1;
+  // graphs
+  cudaGraphExec_t graph_fwd = nullptr;
+  cudaGraphExec_t graph_infer = nullptr;
+  int fwd_calls = 0, infer_calls = 0;
+  ~Executor();
+};
+
+}  // namespace yb
+
+struct yb_handle {
+  yb_config cfg;
+  int device = 0;
+  bool ops_only = false;
+  bool finalized = false;
+  bool use_graphs = true;
+  bool profiling = false;
+  float last_total_ms = 0.f, last_conv_ms = 0.f;
+  yb::LaunchCounter lc;
+  std::map<std::string, yb::HostTensor> host;
+  std::map<std::string, yb::ConvW> convs;
+  std::map<std::string, std::unique_ptr<yb::Executor>> execs;
+  std::vector<void*> weight_allocs;
+  yb::Executor* last_exec = nullptr;
+  // standalone op workspaces
+  void* detect_ws = nullptr;
+  size_t detect_ws_bytes = 0;
+  void* scratch = nullptr;   // maskiou / dcn / conv2d temporaries
+  size_t scratch_bytes = 0;
+  ~yb_handle();
+
+  // ---- weights
+  yb::ConvW& get_conv(const std::string& conv_key, const std::string& bn_key, bool want_tc, bool want_f32,
+                      bool want_f16, bool dcn_pack = false);
+  void finalize();
+  // ---- executors
+  yb::Executor* get_executor(int B, int H, int W);
+  void forward(const float* d_x, int B, int H, int W, float* d_loc, float* d_conf, float* d_coef, float* d_proto,
+               cudaStream_t stream);
+  void infer(const float* d_x, int B, int H, int W, int cross_class, int max_out, float* d_box, float* d_coef_out,
+             int64_t* d_cls, float* d_score, int32_t* d_count, float* d_proto, cudaStream_t stream);
+  void* get_scratch(size_t bytes);
+  void* get_detect_ws(size_t bytes);
+};
+
+namespace yb {
+// builds the op list for a given input shape; dry == true only resolves weights / shapes
+void build_network(yb_handle* h, Executor* ex, bool dry);
+void compute_level_sizes(const yb_config& cfg, int H, int W, int level_hw[5][2], int* ph, int* pw);
+std::vector<float> make_priors_host(const yb_config& cfg, const int level_hw[5][2]);
+void launch_multi_copy(const void* const* src, void* const* dst, const size_t* bytes, int n, cudaStream_t stream,
+                       LaunchCounter* lc);
+}  // namespace yb

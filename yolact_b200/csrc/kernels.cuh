@@ -1,0 +1,126 @@
+// Launcher declarations for every kernel of the path.  One launcher == one kernel launch
+// (each bumps LaunchCounter).  All launchers are asynchronous on `stream`.
+#pragma once
+#include "common.cuh"
+
+namespace yb {
+
+// -------------------------------------------------------------------------------------------
+// Convolution problem description shared by the SIMT and the tcgen05 kernels.
+// Activations are NHWC.  Output addressing is  y[b * y_batch_stride + pix * y_pix_stride + c]
+// (elements), which lets the 5 head levels write straight into the concatenated
+// [B, P, D] tensors the reference builds with permute+view+cat (yolact.py:169-173,633-634).
+// -------------------------------------------------------------------------------------------
+struct ConvProblem {
+  int B = 0, H = 0, W = 0, Cin = 0;
+  int Ho = 0, Wo = 0, Cout = 0;
+  int KH = 1, KW = 1, stride = 1, pad = 0;
+  int act = ACT_NONE;
+  const void* x = nullptr;         // NHWC (T) or, when x_nchw_f32, NCHW fp32 (network input)
+  int x_nchw_f32 = 0;
+  void* y = nullptr;
+  int y_f32 = 0;                   // output element type is float even when activations are half
+  int64_t y_batch_stride = 0;      // elements
+  int y_pix_stride = 0;            // elements
+  const float* bias = nullptr;     // [Cout] fp32 (BN folded), nullable
+  const void* residual = nullptr;  // dense NHWC [B,Ho,Wo,Cout], activation dtype, nullable
+  int res_after_act = 0;           // 1: y = act(conv) + residual (DarkNetBlock, backbone.py:246-247)
+};
+
+enum SimtTypes : int {
+  SIMT_F32 = 0,        // x float (NHWC or NCHW), w float, y float
+  SIMT_F32IN_F16OUT,   // x float (NCHW stem), w float, y half
+  SIMT_F16,            // x half, w half, y half (or float when y_f32)
+};
+
+// w: [KH*KW*Cin][Cout], element type float (SIMT_F32*) or half (SIMT_F16)
+void launch_simt_conv(const ConvProblem& p, const void* w, int types, cudaStream_t stream,
+                      LaunchCounter* lc);
+
+// ---- tcgen05 implicit-GEMM convolution (fp16 in, fp32 accumulate) ----------------------------
+struct TcConvPlan;  // opaque: tensor maps + tiling; built once per (layer, shape, pointers)
+// w_packed: device half [KH*KW][CoutPad][Cin], CoutPad = round_up(Cout,16). Requires Cin % 64 == 0.
+TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed);
+void tc_conv_plan_destroy(TcConvPlan* plan);
+bool tc_conv_supported(const ConvProblem& p);
+void launch_tc_conv(const TcConvPlan* plan, cudaStream_t stream, LaunchCounter* lc);
+
+// ---- pointwise -------------------------------------------------------------------------------
+// 3x3 stride-2 pad-1 max pool, NHWC (backbone.py:80)
+template <typename T>
+void launch_maxpool3x3s2(const T* x, T* y, int B, int H, int W, int C, int Ho, int Wo,
+                         cudaStream_t stream, LaunchCounter* lc);
+// y = bilinear(x -> [Ho,Wo], align_corners=False) (+ add), NHWC.  scale_h/scale_w are the
+// source/destination ratios PyTorch uses (in/out, or 1/scale_factor).  relu: clamp at 0.
+template <typename T>
+void launch_upsample_bilinear(const T* x, const T* add, T* y, int B, int H, int W, int C, int Ho,
+                              int Wo, float scale_h, float scale_w, int relu, cudaStream_t stream,
+                              LaunchCounter* lc);
+// layout / dtype conversion between the kernels' NHWC(T) and the API's NCHW fp32
+template <typename T>
+void launch_nhwc_to_nchw_f32(const T* x, float* y, int B, int H, int W, int C, cudaStream_t stream,
+                             LaunchCounter* lc);
+template <typename T>
+void launch_nchw_f32_to_nhwc(const float* x, T* y, int B, int C, int H, int W, cudaStream_t stream,
+                             LaunchCounter* lc);
+void launch_softmax_rows(const float* in, float* out, int64_t rows, int cols, cudaStream_t stream,
+                         LaunchCounter* lc);
+void launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t stream, LaunchCounter* lc);
+
+// ---- Detect ------------------------------------------------------------------------------------
+struct DetectWorkspace {
+  // all device pointers, sized by detect_workspace_bytes
+  float* scoresT = nullptr;     // [B][C-1][P]  compacted, class-major
+  int32_t* cand_prior = nullptr;  // [B][P]
+  int32_t* cand_cls = nullptr;    // [B][P]  argmax fg class per prior (cross-class mode)
+  int32_t* cand_count = nullptr;  // [B]
+  float* pool_score = nullptr;    // [B][C-1][top_k]
+  int32_t* pool_prior = nullptr;  // [B][C-1][top_k]
+  float* pool_box = nullptr;      // [B][C-1][top_k][4]
+  int32_t* pool_n = nullptr;      // [B][C-1]  kept per class (entries are flagged, see kernel)
+};
+size_t detect_workspace_bytes(int B, int64_t P, int num_classes, int top_k);
+void detect_workspace_bind(DetectWorkspace* ws, void* base, int B, int64_t P, int num_classes,
+                           int top_k);
+struct DetectParams {
+  int B = 0;
+  int64_t P = 0;
+  int num_classes = 81;
+  int mask_dim = 32;
+  int top_k = 200;
+  float conf_thresh = 0.05f;
+  float nms_thresh = 0.5f;
+  int max_dets = 100;
+  int conf_is_logits = 0;
+  int cross_class = 0;
+  int max_out = 100;
+};
+void launch_detect(const DetectParams& dp, const float* loc, const float* conf, const float* coef,
+                   const float* priors, const DetectWorkspace& ws, float* box, float* coef_out,
+                   int64_t* cls, float* score, int32_t* count, cudaStream_t stream,
+                   LaunchCounter* lc);
+
+// ---- mask assembly -----------------------------------------------------------------------------
+void launch_mask_assembly(const float* proto, int ph, int pw, int k, const float* coef,
+                          const float* box, int n, int out_h, int out_w, int crop, int mask_format,
+                          void* masks, int64_t* boxes_px, float* proto_masks, cudaStream_t stream,
+                          LaunchCounter* lc);
+// global max over HxW per (n, c) then gather channel cls[n] (yolact.py:373, output_utils.py:83)
+void launch_maxpool_gather(const float* x_nhwc, int n, int H, int W, int C, const int64_t* cls,
+                           float* out, cudaStream_t stream, LaunchCounter* lc);
+
+// ---- DCNv2 -------------------------------------------------------------------------------------
+// x NHWC (T) [B,H,W,C]; om = offset/mask conv output NHWC fp32 [B,Ho,Wo,27] (18 offsets
+// interleaved (dh,dw) per tap, then 9 masks: logits when mask_logits, dcn_v2.py:118-124); w: [9*C][Cout] (T);
+// y NHWC (T).  Fused deformable gather + contraction + bias + activation.
+template <typename T>
+void launch_dcn_simt(const T* x, const float* om, const T* w, const float* bias, T* y, int B, int H,
+                     int W, int C, int Ho, int Wo, int Cout, int stride, int pad, int dil, int act,
+                     int mask_logits, cudaStream_t stream, LaunchCounter* lc);
+// Deformable gather only: writes the modulated, bilinearly sampled columns as NHWC half
+// [B,Ho,Wo,9*C] (tap-major) so the tcgen05 1x1 contraction can consume them.
+void launch_dcn_gather_f16(const __half* x, const float* om, __half* cols, int B, int H, int W,
+                           int C, int Ho, int Wo, int stride, int pad, int dil, int mask_logits,
+                           cudaStream_t stream, LaunchCounter* lc);
+
+}  // namespace yb

@@ -1,0 +1,298 @@
+// Mask assembly: ONE kernel for  proto @ coef^T -> sigmoid -> crop -> bilinear upsample -> > 0.5
+//
+// Reference: postprocess lincomb path (layers/output_utils.py:58-99), crop / sanitize_coordinates
+// (layers/box_utils.py:327-373), F.interpolate(..., mode='bilinear', align_corners=False)
+// (output_utils.py:91), masks.gt_(0.5) (output_utils.py:94), box sanitise + .long() (:97-99).
+//
+// The reference materialises [ph,pw,n] (matmul), [ph,pw,n] (sigmoid), 4 boolean crop tensors,
+// [n,ph,pw] (permute) and [n,h,w] (interpolate) in HBM.  Here the only HBM traffic is the
+// prototype read (L2 resident, 2.4 MB) and the final mask write, which is the roofline:
+//     algorithmic bytes = ph*pw*k*4 + n*h*w*sizeof(mask element).
+//
+// Work decomposition: CTA = (band of BAND output rows, group of detections).  For each detection
+// the CTA evaluates the cropped sigmoid mask on the few prototype rows the band interpolates from
+// (crop happens BEFORE the upsample, output_utils.py:72-74: each output pixel interpolates four
+// already-cropped values), parks them in shared memory and streams out the band.
+#include "kernels.cuh"
+
+namespace yb {
+
+namespace {
+
+constexpr int MT = 256;  // threads
+
+struct ColTab {  // per output column / row interpolation entry
+  int i0, i1;
+  float l0, l1;
+};
+
+__device__ __forceinline__ ColTab interp_entry(int dst, float scale, int in_size) {
+  // ATen area_pixel_compute_source_index, align_corners=False
+  float s = fmaxf(__fsub_rn(__fmul_rn(scale, (float)dst + 0.5f), 0.5f), 0.f);
+  ColTab t;
+  t.i0 = (int)s;
+  if (t.i0 > in_size - 1) t.i0 = in_size - 1;
+  t.i1 = t.i0 + (t.i0 < in_size - 1 ? 1 : 0);
+  t.l1 = __fsub_rn(s, (float)t.i0);
+  t.l0 = __fsub_rn(1.f, t.l1);
+  return t;
+}
+
+// sanitize_coordinates(cast=False) (box_utils.py:327-346)
+__device__ __forceinline__ void sanitize(float a, float b, int size, int padding, float* lo, float* hi) {
+  float x1 = __fmul_rn(a, (float)size), x2 = __fmul_rn(b, (float)size);
+  float mn = fminf(x1, x2), mx = fmaxf(x1, x2);
+  *lo = fmaxf(__fsub_rn(mn, (float)padding), 0.f);
+  *hi = fminf(__fadd_rn(mx, (float)padding), (float)size);
+}
+
+template <int FORMAT>
+__global__ void __launch_bounds__(MT)
+mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
+                     const float* __restrict__ coef, const float* __restrict__ box, int n, int out_h,
+                     int out_w, int crop, int band, int group, int max_rows, float scale_h,
+                     float scale_w, void* __restrict__ masks_v) {
+  extern __shared__ unsigned char smem_raw[];
+  ColTab* coltab = reinterpret_cast<ColTab*>(smem_raw);                 // [out_w]
+  float* mrows = reinterpret_cast<float*>(coltab + out_w);               // [max_rows][pw]
+  float* s_coef = mrows + (size_t)max_rows * pw;                         // [k]
+
+  const int tid = threadIdx.x;
+  const int y0 = blockIdx.x * band;
+  const int y1 = min(y0 + band, out_h);
+  const int d0 = blockIdx.y * group;
+  const int d1 = min(d0 + group, n);
+
+  for (int x = tid; x < out_w; x += MT) coltab[x] = interp_entry(x, scale_w, pw);
+  // prototype rows this band reads
+  const ColTab rt0 = interp_entry(y0, scale_h, ph);
+  const ColTab rt1 = interp_entry(y1 - 1, scale_h, ph);
+  const int r_lo = rt0.i0;
+  const int r_hi = rt1.i1;
+  const int nrows = r_hi - r_lo + 1;  // <= max_rows by construction on the host
+  __syncthreads();
+
+  const size_t plane = (size_t)out_h * out_w;
+  const int wpr = (out_w + 31) >> 5;  // words per row, bit format
+
+  for (int d = d0; d < d1; ++d) {
+    // crop window in prototype coordinates (box_utils.py:359-371)
+    float cx1 = 0.f, cx2 = (float)pw, cy1 = 0.f, cy2 = (float)ph;
+    if (crop) {
+      const float* bx = box + (size_t)d * 4;
+      sanitize(bx[0], bx[2], pw, 1, &cx1, &cx2);
+      sanitize(bx[1], bx[3], ph, 1, &cy1, &cy2);
+    }
+    // does any prototype row of this band survive the crop?
+    bool any = false;
+    for (int r = r_lo; r <= r_hi; ++r) any |= ((float)r >= cy1 && (float)r < cy2);
+    any &= (cx1 < cx2);
+
+    if (any) {
+      for (int j = tid; j < k; j += MT) s_coef[j] = coef[(size_t)d * k + j];
+      __syncthreads();
+      for (int pos = tid; pos < nrows * pw; pos += MT) {
+        const int r = pos / pw, c = pos - r * pw;
+        const int pr = r_lo + r;
+        float v = 0.f;
+        const bool inside = ((float)c >= cx1) && ((float)c < cx2) && ((float)pr >= cy1) && ((float)pr < cy2);
+        if (inside) {
+          const float4* pp = reinterpret_cast<const float4*>(proto + ((size_t)pr * pw + c) * k);
+          float acc = 0.f;
+          for (int j = 0; j < k / 4; ++j) {
+            float4 q = __ldg(pp + j);
+            acc = fmaf(q.x, s_coef[4 * j + 0], acc);
+            acc = fmaf(q.y, s_coef[4 * j + 1], acc);
+            acc = fmaf(q.z, s_coef[4 * j + 2], acc);
+            acc = fmaf(q.w, s_coef[4 * j + 3], acc);
+          }
+          v = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-acc)));  // torch.sigmoid
+        }
+        mrows[pos] = v;
+      }
+      __syncthreads();
+    }
+
+    // ---- stream out the band -------------------------------------------------------------
+    if (FORMAT == YB_MASK_BITS) {
+      uint32_t* out = reinterpret_cast<uint32_t*>(masks_v) + (size_t)d * out_h * wpr;
+      const int words = (y1 - y0) * wpr;
+      for (int wi = tid; wi < words; wi += MT) {
+        const int yy = wi / wpr, wx = wi - yy * wpr;
+        const int y = y0 + yy;
+        uint32_t bits = 0u;
+        if (any) {
+          const ColTab rt = interp_entry(y, scale_h, ph);
+          const float* ra = mrows + (size_t)(rt.i0 - r_lo) * pw;
+          const float* rb = mrows + (size_t)(rt.i1 - r_lo) * pw;
+          const int xe = min(out_w - wx * 32, 32);
+          for (int j = 0; j < xe; ++j) {
+            const ColTab ct = coltab[wx * 32 + j];
+            float top = __fadd_rn(__fmul_rn(ct.l0, ra[ct.i0]), __fmul_rn(ct.l1, ra[ct.i1]));
+            float bot = __fadd_rn(__fmul_rn(ct.l0, rb[ct.i0]), __fmul_rn(ct.l1, rb[ct.i1]));
+            float v = __fadd_rn(__fmul_rn(rt.l0, top), __fmul_rn(rt.l1, bot));
+            bits |= (v > 0.5f ? 1u : 0u) << j;
+          }
+        }
+        out[(size_t)y * wpr + wx] = bits;
+      }
+    } else {
+      const int npix = (y1 - y0) * out_w;
+      for (int pi = tid; pi < npix; pi += MT) {
+        const int yy = pi / out_w, x = pi - yy * out_w;
+        const int y = y0 + yy;
+        float res = 0.f;
+        if (any) {
+          const ColTab rt = interp_entry(y, scale_h, ph);
+          const ColTab ct = coltab[x];
+          const float* ra = mrows + (size_t)(rt.i0 - r_lo) * pw;
+          const float* rb = mrows + (size_t)(rt.i1 - r_lo) * pw;
+          float top = __fadd_rn(__fmul_rn(ct.l0, ra[ct.i0]), __fmul_rn(ct.l1, ra[ct.i1]));
+          float bot = __fadd_rn(__fmul_rn(ct.l0, rb[ct.i0]), __fmul_rn(ct.l1, rb[ct.i1]));
+          float v = __fadd_rn(__fmul_rn(rt.l0, top), __fmul_rn(rt.l1, bot));
+          res = v > 0.5f ? 1.f : 0.f;
+        }
+        const size_t o = (size_t)d * plane + (size_t)y * out_w + x;
+        if (FORMAT == YB_MASK_F32)
+          reinterpret_cast<float*>(masks_v)[o] = res;
+        else
+          reinterpret_cast<unsigned char*>(masks_v)[o] = (unsigned char)res;
+      }
+    }
+    __syncthreads();  // mrows / s_coef reuse
+  }
+}
+
+// boxes: sanitize_coordinates(cast=False) for x with w, y with h, then .long() (output_utils.py:97-99)
+__global__ void boxes_px_kernel(const float* __restrict__ box, int n, int out_h, int out_w,
+                                int64_t* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x1, x2, y1, y2;
+  sanitize(box[i * 4 + 0], box[i * 4 + 2], out_w, 0, &x1, &x2);
+  sanitize(box[i * 4 + 1], box[i * 4 + 3], out_h, 0, &y1, &y2);
+  out[i * 4 + 0] = (int64_t)x1;  // truncation toward zero, like Tensor.long()
+  out[i * 4 + 1] = (int64_t)y1;
+  out[i * 4 + 2] = (int64_t)x2;
+  out[i * 4 + 3] = (int64_t)y2;
+}
+
+// Cropped sigmoid masks at prototype resolution [n,ph,pw] (FastMaskIoUNet input, output_utils.py:77-82)
+__global__ void __launch_bounds__(MT)
+proto_masks_kernel(const float* __restrict__ proto, int ph, int pw, int k,
+                   const float* __restrict__ coef, const float* __restrict__ box, int crop,
+                   float* __restrict__ out) {
+  __shared__ float s_coef[128];
+  const int r = blockIdx.x, d = blockIdx.y;
+  for (int j = threadIdx.x; j < k; j += MT) s_coef[j] = coef[(size_t)d * k + j];
+  __syncthreads();
+  float cx1 = 0.f, cx2 = (float)pw, cy1 = 0.f, cy2 = (float)ph;
+  if (crop) {
+    const float* bx = box + (size_t)d * 4;
+    sanitize(bx[0], bx[2], pw, 1, &cx1, &cx2);
+    sanitize(bx[1], bx[3], ph, 1, &cy1, &cy2);
+  }
+  for (int c = threadIdx.x; c < pw; c += MT) {
+    float v = 0.f;
+    if ((float)c >= cx1 && (float)c < cx2 && (float)r >= cy1 && (float)r < cy2) {
+      const float4* pp = reinterpret_cast<const float4*>(proto + ((size_t)r * pw + c) * k);
+      float acc = 0.f;
+      for (int j = 0; j < k / 4; ++j) {
+        float4 q = __ldg(pp + j);
+        acc = fmaf(q.x, s_coef[4 * j + 0], acc);
+        acc = fmaf(q.y, s_coef[4 * j + 1], acc);
+        acc = fmaf(q.z, s_coef[4 * j + 2], acc);
+        acc = fmaf(q.w, s_coef[4 * j + 3], acc);
+      }
+      v = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-acc)));
+    }
+    out[((size_t)d * ph + r) * pw + c] = v;
+  }
+}
+
+// out[i] = max_{h,w} x[i,h,w,cls[i]]   (F.max_pool2d over the full map + gather)
+__global__ void maxpool_gather_kernel(const float* __restrict__ x, int HW, int C,
+                                      const int64_t* __restrict__ cls, float* __restrict__ out) {
+  const int i = blockIdx.x;
+  const int c = (int)cls[i];
+  float m = -INFINITY;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) m = fmaxf(m, x[((size_t)i * HW + p) * C + c]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float s[32];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = s[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, s[w]);
+    out[i] = r;
+  }
+}
+
+}  // namespace
+
+void launch_mask_assembly(const float* proto, int ph, int pw, int k, const float* coef,
+                          const float* box, int n, int out_h, int out_w, int crop, int mask_format,
+                          void* masks, int64_t* boxes_px, float* proto_masks, cudaStream_t stream,
+                          LaunchCounter* lc) {
+  if (n <= 0) return;
+  YB_REQUIRE(k % 4 == 0 && k <= 128, "mask_assembly: mask_dim must be a multiple of 4 and <= 128");
+  YB_REQUIRE(out_h > 0 && out_w > 0 && ph > 0 && pw > 0, "mask_assembly: bad sizes");
+  const float scale_h = (float)ph / (float)out_h;
+  const float scale_w = (float)pw / (float)out_w;
+  if (boxes_px) {
+    boxes_px_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(box, n, out_h, out_w, boxes_px);
+    YB_CHECK_LAUNCH();
+    if (lc) lc->n++;
+  }
+  if (proto_masks) {
+    proto_masks_kernel<<<dim3(ph, n), MT, 0, stream>>>(proto, ph, pw, k, coef, box, crop, proto_masks);
+    YB_CHECK_LAUNCH();
+    if (lc) lc->n++;
+  }
+  if (masks) {
+    int band = 8;
+    int max_rows;
+    size_t smem;
+    for (;;) {
+      max_rows = (int)((double)(band - 1) * scale_h) + 4;
+      smem = (size_t)out_w * sizeof(ColTab) + (size_t)max_rows * pw * sizeof(float) + (size_t)k * sizeof(float);
+      if (smem <= 200 * 1024 || band == 1) break;
+      band = band / 2;
+    }
+    YB_REQUIRE(smem <= 200 * 1024, "mask_assembly: output too wide for the shared-memory tables");
+    const int bands = ceil_div(out_h, band);
+    // enough CTAs for >= 2 waves of 148 SMs, but keep groups large for prototype reuse in L1
+    int group = n;
+    while (group > 1 && (int64_t)bands * ceil_div(n, group) < 2 * 148) group = (group + 1) / 2;
+    dim3 grid(bands, ceil_div(n, group));
+#define YB_LAUNCH_MASK(FMT)                                                                       \
+  do {                                                                                            \
+    if (smem > 48 * 1024)                                                                         \
+      YB_CHECK_CUDA(cudaFuncSetAttribute(mask_assembly_kernel<FMT>,                               \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mask_assembly_kernel<FMT><<<grid, MT, smem, stream>>>(proto, ph, pw, k, coef, box, n, out_h,  \
+                                                         out_w, crop, band, group, max_rows,     \
+                                                         scale_h, scale_w, masks);               \
+  } while (0)
+    switch (mask_format) {
+      case YB_MASK_F32: YB_LAUNCH_MASK(YB_MASK_F32); break;
+      case YB_MASK_U8: YB_LAUNCH_MASK(YB_MASK_U8); break;
+      case YB_MASK_BITS: YB_LAUNCH_MASK(YB_MASK_BITS); break;
+      default: YB_REQUIRE(false, "mask_assembly: unknown mask format");
+    }
+#undef YB_LAUNCH_MASK
+    YB_CHECK_LAUNCH();
+    if (lc) lc->n++;
+  }
+}
+
+void launch_maxpool_gather(const float* x_nhwc, int n, int H, int W, int C, const int64_t* cls,
+                           float* out, cudaStream_t stream, LaunchCounter* lc) {
+  if (n <= 0) return;
+  maxpool_gather_kernel<<<n, 128, 0, stream>>>(x_nhwc, H * W, C, cls, out);
+  YB_CHECK_LAUNCH();
+  if (lc) lc->n++;
+}
+
+}  // namespace yb

@@ -1,0 +1,586 @@
+// Implicit-GEMM convolution on 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Replaces cuDNN nn.Conv2d + BatchNorm2d + ReLU (+ residual add) of the reference's backbone /
+// FPN / protonet / prediction head (backbone.py:37-57,126-139; yolact.py:311-361,133-212;
+// utils/functions.py:163-213) and the SGEMM of DCNv2 (dcn_v2_cuda.cu:149-163).
+//
+// GEMM view (no im2col buffer anywhere):
+//   D[M = output pixels of one spatial tile, N = Cout tile] = sum over taps (r,s) and 64-channel
+//   chunks of  A_tap[M, 64] * W_tap[N, 64]^T,   fp16 operands, fp32 accumulation in TMEM.
+// A operand: the activation tensor is NHWC fp16; a 4-D TMA tensor map {C, W, H, B} loads the box
+//   {64 channels, tw, th, 1} whose origin is shifted by the tap offset.  Out-of-bounds rows /
+//   columns (the conv's zero padding) are zero-filled by TMA itself.  tw*th <= 128 rows land in
+//   shared memory as 128-byte rows with the 128B swizzle == the canonical K-major SWIZZLE_128B
+//   UMMA layout, so the MMA consumes them with no repacking.
+//   Stride-2 convs use one tensor map per input phase (py,px) (a strided *view* of the same
+//   buffer: element strides doubled), and the tap table selects (phase map, dx, dy).
+// B operand: weights packed [tap][Cout][Cin] fp16, 3-D map, box {64, BN, 1}.
+// Pipeline: warp 0 = TMA producer, warp 1 = TMEM alloc + single-thread tcgen05.mma issue,
+//   warps 2..5 = epilogue (tcgen05.ld -> +bias -> +residual -> activation -> 16-byte stores).
+//   `stages`-deep mbarrier ring (full/empty), tcgen05.commit releases shared memory slots.
+#include <cuda.h>  // CUtensorMap + enums only; the encode entry point is fetched at run time
+#include <vector>
+#include "kernels.cuh"
+
+namespace yb {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;              // fp16 elements = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_TAPS = 9;
+constexpr int MAX_STAGES = 8;
+
+struct alignas(64) TcParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  int ntaps, kchunks, stages;
+  int tap_map[MAX_TAPS], tap_dx[MAX_TAPS], tap_dy[MAX_TAPS];
+  int tw, th, tiles_x, tiles_y;
+  int Ho, Wo, Cout;
+  int a_box_bytes;      // tw*th*128
+  uint32_t idesc;
+  // epilogue
+  void* y;
+  const float* bias;
+  const __half* residual;
+  long long y_batch_stride;
+  long long res_batch_stride;
+  int y_pix_stride;
+  int y_f32;
+  int act;
+  int vec_ok;
+  int res_after_act;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* desc, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* desc, uint64_t* bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::f16 (fp16 in, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 = 1024>>4
+//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS)
+tc_conv_kernel(const __grid_constant__ TcParams p) {
+  constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ uint64_t full_bar[MAX_STAGES];
+  __shared__ uint64_t empty_bar[MAX_STAGES];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t s_tmem_base;
+
+  // 1024-byte alignment required by SWIZZLE_128B (host adds 1024 bytes of slack)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+  const int num_kb = p.ntaps * p.kchunks;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x;
+  t /= p.tiles_x;
+  const int ty = t % p.tiles_y;
+  const int b = t / p.tiles_y;
+  const int x0 = tx * p.tw, y0 = ty * p.th;
+  const int n0 = blockIdx.y * BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmA[0]);
+  }
+  if (warp == 1) tmem_alloc<BN>(&s_tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)p.a_box_bytes + (uint32_t)B_STAGE_BYTES;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t it = (uint32_t)(kb / stages);
+        mbar_wait(&empty_bar[s], (it & 1u) ^ 1u);
+        const int tap = kb / p.kchunks;
+        const int kc = kb - tap * p.kchunks;
+        uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+        uint8_t* sb = sa + A_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], tx_bytes);
+        tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[s], kc * BLOCK_K, x0 + p.tap_dx[tap],
+                    y0 + p.tap_dy[tap], b);
+        tma_load_3d(sb, &p.tmB, &full_bar[s], kc * BLOCK_K, n0, tap);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t it = (uint32_t)(kb / stages);
+        mbar_wait(&full_bar[s], it & 1u);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + A_STAGE_BYTES;
+        const uint64_t da = make_sw128_desc(sa);
+        const uint64_t db = make_sw128_desc(sb);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 field
+          umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc,
+                   (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees this smem slot once the MMAs above have read it
+      }
+      umma_commit(&tmem_full_bar);   // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 -> TMEM lane quadrant warp%4) =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;  // accumulator row == tile-local output pixel
+    const int ly = row / p.tw, lx = row - ly * p.tw;
+    const int oy = y0 + ly, ox = x0 + lx;
+    const bool row_ok = (row < p.tw * p.th) && (oy < p.Ho) && (ox < p.Wo);
+    const long long pix = (long long)oy * p.Wo + ox;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+
+    float* yf = reinterpret_cast<float*>(p.y) + (long long)b * p.y_batch_stride + pix * p.y_pix_stride;
+    __half* yh = reinterpret_cast<__half*>(p.y) + (long long)b * p.y_batch_stride + pix * p.y_pix_stride;
+    const __half* res = p.residual ? p.residual + (long long)b * p.res_batch_stride + pix * p.Cout : nullptr;
+
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.Cout) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+      if (!row_ok) continue;
+      const int nbase = n0 + c0;
+      const int nvalid = min(32, p.Cout - nbase);
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) v[j] += __ldg(p.bias + nbase + j);
+      }
+      if (p.res_after_act) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+      }
+      if (res) {
+        if (p.vec_ok && nvalid == 32) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 raw = __ldg(reinterpret_cast<const uint4*>(res + nbase) + q);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f = __half22float2(h2[j]);
+              v[q * 8 + 2 * j] += f.x;
+              v[q * 8 + 2 * j + 1] += f.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) v[j] += __half2float(res[nbase + j]);
+        }
+      }
+      if (!p.res_after_act) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+      }
+
+      if (p.y_f32) {
+        if (p.vec_ok && nvalid == 32) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            reinterpret_cast<float4*>(yf + nbase)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) yf[nbase + j] = v[j];
+        }
+      } else {
+        if (p.vec_ok && nvalid == 32) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o2[j] = __halves2half2(from_f32<__half>(v[q * 8 + 2 * j]), from_f32<__half>(v[q * 8 + 2 * j + 1]));
+            reinterpret_cast<uint4*>(yh + nbase)[q] = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) yh[nbase + j] = from_f32<__half>(v[j]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  YB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+  YB_REQUIRE(qres == cudaDriverEntryPointSuccess && ptr, "cuTensorMapEncodeTiled not available from the driver");
+  fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  return fn;
+}
+
+void encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box) {
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    YB_REQUIRE(box[i] >= 1 && box[i] <= 256, "tensor map: box dim out of range");
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstr[i] = strides_bytes[i];
+    YB_REQUIRE(strides_bytes[i] % 16 == 0, "tensor map: stride must be a multiple of 16 bytes");
+  }
+  YB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base must be 16-byte aligned");
+  CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                               gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw Error(YB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+}
+
+int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+}  // namespace
+
+struct TcConvPlan {
+  TcParams prm;
+  int BN = 128;
+  dim3 grid;
+  size_t smem_bytes = 0;
+};
+
+bool tc_conv_supported(const ConvProblem& p) {
+  if (p.x_nchw_f32) return false;
+  if (p.Cin % BLOCK_K != 0) return false;
+  if (p.KH * p.KW > MAX_TAPS) return false;
+  if (p.stride != 1 && p.stride != 2) return false;
+  if (p.Cout < 1) return false;
+  return true;
+}
+
+TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed) {
+  YB_REQUIRE(tc_conv_supported(p), "tc_conv: unsupported problem");
+  YB_REQUIRE(p.Ho == (p.H + 2 * p.pad - p.KH) / p.stride + 1, "tc_conv: bad Ho");
+  YB_REQUIRE(p.Wo == (p.W + 2 * p.pad - p.KW) / p.stride + 1, "tc_conv: bad Wo");
+  auto* plan = new TcConvPlan();
+  TcParams& q = plan->prm;
+  memset(&q, 0, sizeof(q));
+  const int s = p.stride;
+  q.ntaps = p.KH * p.KW;
+  q.kchunks = p.Cin / BLOCK_K;
+
+  // ---- geometry: can the whole problem be flattened into one pixel axis? (1x1, stride 1, dense out)
+  const bool dense_out = (p.y_batch_stride == (int64_t)p.Ho * p.Wo * p.y_pix_stride);
+  const bool flat = (q.ntaps == 1 && s == 1 && p.pad == 0 && dense_out);
+  int Bv = p.B, Hov = p.Ho, Wov = p.Wo;
+  if (flat) {
+    Wov = p.B * p.Ho * p.Wo;
+    Hov = 1;
+    Bv = 1;
+  }
+  // ---- spatial tile (tw x th <= 128) with the best fill
+  int best_tw = 1, best_th = 1;
+  double best_eff = -1.0;
+  for (int tw = 1; tw <= std::min(Wov, 128); ++tw) {
+    int th = std::min(Hov, 128 / tw);
+    if (th < 1) continue;
+    if (tw > 256 || th > 256) continue;
+    long long tiles = (long long)ceil_div(Wov, tw) * ceil_div(Hov, th);
+    double eff = (double)Wov * Hov / ((double)tiles * 128.0);
+    if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && tw > best_tw)) {
+      best_eff = eff;
+      best_tw = tw;
+      best_th = th;
+    }
+  }
+  q.tw = best_tw;
+  q.th = best_th;
+  q.tiles_x = ceil_div(Wov, q.tw);
+  q.tiles_y = ceil_div(Hov, q.th);
+  q.Ho = Hov;
+  q.Wo = Wov;
+  q.Cout = p.Cout;
+  q.a_box_bytes = q.tw * q.th * BLOCK_K * 2;
+  const long long m_tiles = (long long)q.tiles_x * q.tiles_y * Bv;
+
+  // ---- N tile: minimise waves * (BN + fixed cost)
+  {
+    const int cands[4] = {256, 128, 64, 32};
+    double best = 1e30;
+    int bn_best = 32;
+    for (int i = 0; i < 4; ++i) {
+      int bn = cands[i];
+      if (bn > 32 && bn >= 2 * p.Cout) continue;  // more than half the tile would be padding
+      long long ctas = m_tiles * ceil_div(p.Cout, bn);
+      long long waves = (ctas + 147) / 148;
+      double cost = (double)waves * (bn + 64);
+      if (cost < best - 1e-9) {
+        best = cost;
+        bn_best = bn;
+      }
+    }
+    plan->BN = bn_best;
+  }
+  const int BN = plan->BN;
+  const int stage_bytes = A_STAGE_BYTES + BN * BLOCK_K * 2;
+  int stages = std::min(MAX_STAGES, (200 * 1024) / stage_bytes);
+  stages = std::max(1, std::min(stages, q.ntaps * q.kchunks));
+  q.stages = stages;
+  plan->smem_bytes = (size_t)stages * stage_bytes + 1024;
+  plan->grid = dim3((unsigned)m_tiles, (unsigned)ceil_div(p.Cout, BN));
+
+  // ---- instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major, N, M=128
+  q.idesc = (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) |
+            ((uint32_t)(BLOCK_M >> 4) << 24);
+
+  // ---- A tensor maps
+  const __half* x = reinterpret_cast<const __half*>(p.x);
+  if (flat) {
+    uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)Wov, 1, 1};
+    uint64_t str[3] = {(uint64_t)p.Cin * 2, (uint64_t)Wov * p.Cin * 2, (uint64_t)Wov * p.Cin * 2};
+    uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)q.tw, (uint32_t)q.th, 1};
+    encode_map(&q.tmA[0], x, 4, dims, str, box);
+    q.tap_map[0] = 0;
+    q.tap_dx[0] = 0;
+    q.tap_dy[0] = 0;
+  } else {
+    bool used[4] = {false, false, false, false};
+    for (int r = 0; r < p.KH; ++r)
+      for (int c = 0; c < p.KW; ++c) {
+        int qy = r - p.pad, qx = c - p.pad;
+        int py = ((qy % s) + s) % s, px = ((qx % s) + s) % s;
+        int tap = r * p.KW + c;
+        q.tap_map[tap] = py * s + px;
+        q.tap_dy[tap] = floordiv(qy - py, s);
+        q.tap_dx[tap] = floordiv(qx - px, s);
+        used[py * s + px] = true;
+      }
+    for (int py = 0; py < s; ++py)
+      for (int px = 0; px < s; ++px) {
+        if (!used[py * s + px]) continue;
+        int Hv = (p.H - py + s - 1) / s, Wv = (p.W - px + s - 1) / s;
+        YB_REQUIRE(Hv >= 1 && Wv >= 1, "tc_conv: empty phase view");
+        const __half* base = x + ((size_t)py * p.W + px) * p.Cin;
+        uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)Wv, (uint64_t)Hv, (uint64_t)p.B};
+        uint64_t str[3] = {(uint64_t)s * p.Cin * 2, (uint64_t)s * p.W * p.Cin * 2,
+                           (uint64_t)p.H * p.W * p.Cin * 2};
+        uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)q.tw, (uint32_t)q.th, 1};
+        encode_map(&q.tmA[py * s + px], base, 4, dims, str, box);
+      }
+  }
+  // ---- B tensor map: [tap][Cout][Cin]
+  {
+    uint64_t dims[3] = {(uint64_t)p.Cin, (uint64_t)p.Cout, (uint64_t)q.ntaps};
+    uint64_t str[2] = {(uint64_t)p.Cin * 2, (uint64_t)p.Cout * p.Cin * 2};
+    uint32_t box[3] = {(uint32_t)BLOCK_K, (uint32_t)BN, 1};
+    encode_map(&q.tmB, w_packed, 3, dims, str, box);
+  }
+  // ---- epilogue
+  q.y = p.y;
+  q.bias = p.bias;
+  q.residual = reinterpret_cast<const __half*>(p.residual);
+  q.y_f32 = p.y_f32;
+  q.act = p.act;
+  q.res_after_act = p.res_after_act;
+  q.y_pix_stride = p.y_pix_stride;
+  if (flat) {
+    q.y_batch_stride = 0;
+    q.res_batch_stride = 0;
+  } else {
+    q.y_batch_stride = p.y_batch_stride;
+    q.res_batch_stride = (long long)p.Ho * p.Wo * p.Cout;
+  }
+  const int esz = p.y_f32 ? 4 : 2;
+  const int vec_elems = 16 / esz;
+  bool vec_ok = (p.y_pix_stride % vec_elems == 0) && (p.y_batch_stride % vec_elems == 0) &&
+                ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+  if (p.residual) vec_ok = vec_ok && (p.Cout % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+  q.vec_ok = vec_ok ? 1 : 0;
+  return plan;
+}
+
+void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
+
+template <int BN>
+static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
+  static bool attr_set = false;
+  static size_t attr_bytes = 0;
+  if (!attr_set || plan->smem_bytes > attr_bytes) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(220 * 1024)));
+    attr_set = true;
+    attr_bytes = 220 * 1024;
+  }
+  tc_conv_kernel<BN><<<plan->grid, NUM_THREADS, plan->smem_bytes, stream>>>(plan->prm);
+}
+
+void launch_tc_conv(const TcConvPlan* plan, cudaStream_t stream, LaunchCounter* lc) {
+  switch (plan->BN) {
+    case 256: launch_bn<256>(plan, stream); break;
+    case 128: launch_bn<128>(plan, stream); break;
+    case 64: launch_bn<64>(plan, stream); break;
+    case 32: launch_bn<32>(plan, stream); break;
+    default: YB_REQUIRE(false, "tc_conv: bad BN");
+  }
+  YB_CHECK_LAUNCH();
+  if (lc) lc->n++;
+}
+
+}  // namespace yb
