@@ -166,7 +166,8 @@ YB_API int yb_postprocess(yb_handle* h, const float* d_proto, int ph, int pw, in
                    int crop_masks, int mask_format, void* d_masks, int64_t* d_boxes_px,
                    float* d_proto_masks, void* stream);
 
-/* maskiou_net on [n,1,ph,pw] fp32 masks -> d_maskiou [n] = net(mask)[i, cls[i]] */
+/* maskiou_net on [n,1,ph,pw] fp32 masks -> d_maskiou [n] = net(mask)[i, cls[i]];
+ * d_cls == NULL: d_maskiou [n, num_classes-1] = net(mask) (FastMaskIoUNet.forward itself). */
 YB_API int yb_maskiou(yb_handle* h, const float* d_proto_masks, int n, int ph, int pw,
                const int64_t* d_cls, float* d_maskiou, void* stream);
 

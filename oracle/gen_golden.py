@@ -1,0 +1,273 @@
+"""Generates tests/golden/*.npz by running the REAL reference (/root/reference) on this container's CPU.
+
+Run here (the GPU box has no /root/reference):   python oracle/gen_golden.py
+The committed .npz files are what pins oracle/yolact_oracle.py and the CUDA path to the reference.
+
+Shims (never edits to the reference): stub pycocotools / matplotlib in
+sys.modules, torch.cuda.current_device -> 0, and -- for YOLACT++ configs -- a `dcn_v2` module whose
+DCN has the reference's parameter names and calls torchvision.ops.deform_conv2d (the vendored CUDA
+extension cannot be built: THC headers).  The deterministic weights come from oracle/weights.py.
+"""
+import copy
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def install_shims():
+    for m in ["pycocotools", "pycocotools.mask", "pycocotools.coco", "pycocotools.cocoeval", "matplotlib",
+              "matplotlib.pyplot"]:
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules["pycocotools.coco"].COCO = object
+    torch.cuda.current_device = lambda: 0
+    # use_jit=False (yolact.py:25): FastMaskIoUNet.forward is not a script_method and cannot run as a
+    # ScriptModule on torch 2.x; the reference takes this same path whenever >1 GPU is visible
+    torch.cuda.device_count = lambda: 2
+    import torchvision
+    from torch import nn
+
+    class DCN(nn.Module):
+        """Parameter-name compatible stand-in for external/DCNv2/dcn_v2.py:97-128."""
+
+        def __init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation=1, deformable_groups=1):
+            super().__init__()
+            self.stride, self.padding, self.dilation = stride, padding, dilation
+            self.weight = nn.Parameter(torch.empty(out_channels, in_channels, kernel_size, kernel_size))
+            self.bias = nn.Parameter(torch.zeros(out_channels))
+            self.conv_offset_mask = nn.Conv2d(in_channels, 27, kernel_size, stride=stride, padding=padding, bias=True)
+            nn.init.normal_(self.weight, std=0.01)
+
+        def forward(self, x):
+            out = self.conv_offset_mask(x)
+            o1, o2, mask = torch.chunk(out, 3, dim=1)
+            offset = torch.cat((o1, o2), dim=1)
+            mask = torch.sigmoid(mask)
+            return torchvision.ops.deform_conv2d(x, offset, self.weight, self.bias, stride=self.stride,
+                                                 padding=self.padding, dilation=self.dilation, mask=mask)
+
+    mod = types.ModuleType("dcn_v2")
+    mod.DCN = DCN
+    sys.modules["dcn_v2"] = mod
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+
+
+def npz_save(name, **arrs):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print("wrote %s (%.2f MB)" % (path, os.path.getsize(path) / 1e6))
+
+
+def to_np(t):
+    return t.detach().cpu().numpy()
+
+
+def gen_network_case(tag, config_name, B, H, W, post_hw, seed=0, row_stride=1):
+    from data.config import cfg, set_cfg
+    import yolact as ref_yolact
+    from layers.output_utils import postprocess
+    from oracle.weights import deterministic_state_dict, deterministic_input
+
+    set_cfg(config_name)
+    cfg.mask_proto_debug = False
+    net = ref_yolact.Yolact()
+    net.load_state_dict(deterministic_state_dict(net.state_dict(), seed))
+    net.detect.use_fast_nms = True
+    net.detect.use_cross_class_nms = False
+    x = deterministic_input(B, H, W, 1234 + seed)
+    out = {"x": to_np(x), "config": np.array(config_name), "seed": np.array(seed), "post_hw": np.array(post_hw)}
+    with torch.no_grad():
+        # train() makes forward return the raw head tensors (yolact.py:639-647); freeze_bn() keeps
+        # BatchNorm in eval mode (running statistics), i.e. exactly the inference arithmetic
+        net.train()
+        net.freeze_bn()
+        raw = net(x)
+        out["row_stride"] = np.array(row_stride)
+        for k in ("loc", "conf", "mask"):
+            out["raw_" + k] = to_np(raw[k]).astype(np.float32)[:, ::row_stride]
+        for k in ("priors", "proto"):
+            out["raw_" + k] = to_np(raw[k]).astype(np.float32)
+        # intermediate features (backbone stage outputs + FPN levels) for stage-level parity
+        bb = net.backbone(x)
+        for i, f in enumerate(bb):
+            out["feat_c%d_absmean" % i] = np.array(float(f.abs().mean()))
+            out["feat_c%d_sample" % i] = to_np(f[:, ::7, ::3, ::3]).astype(np.float32)
+        net.eval()
+        preds = net(x)
+    counts = []
+    for b in range(B):
+        det = preds[b]["detection"]
+        n = 0 if det is None else int(det["score"].shape[0])
+        counts.append(n)
+        if det is None:
+            continue
+        for k in ("box", "mask", "class", "score"):
+            out["det%d_%s" % (b, k)] = to_np(det[k])
+        ph, pw = post_hw
+        p2 = copy.deepcopy([{"detection": {k: v.clone() for k, v in det.items()}, "net": net}])
+        with torch.no_grad():
+            classes, scores, boxes, masks = postprocess(p2, pw, ph, batch_idx=0, crop_masks=True, score_threshold=0)
+        out["post%d_classes" % b] = to_np(classes)
+        if isinstance(scores, list):
+            out["post%d_scores" % b] = to_np(scores[0])
+            out["post%d_scores_maskiou" % b] = to_np(scores[1])
+        else:
+            out["post%d_scores" % b] = to_np(scores)
+        out["post%d_boxes" % b] = to_np(boxes)
+        out["post%d_masks_packed" % b] = np.packbits(to_np(masks).astype(np.uint8), axis=-1)
+    out["det_counts"] = np.array(counts)
+    sm = torch.softmax(raw["conf"], -1)[..., 1:].max(-1)[0]
+    qs = [float(torch.quantile(sm.flatten(), q)) for q in (0.5, 0.9, 0.99, 1.0)]
+    top = to_np(preds[0]["detection"]["score"])[:5] if preds[0]["detection"] is not None else []
+    print(tag, config_name, "P =", raw["loc"].shape[1], "detections per image:", counts,
+          "max|conf logit| %.2f" % float(raw["conf"].abs().max()), "proto max %.2f" % float(raw["proto"].max()),
+          "fg-score quantiles 50/90/99/100:", ["%.3f" % q for q in qs], "n>0.05:", int((sm > 0.05).sum()),
+          "top scores", top, "coef absmax %.2f" % float(raw["mask"].abs().max()))
+    npz_save(tag, **out)
+
+
+def gen_detect_unit(seed=3):
+    """Synthetic pred_outs straight into the reference Detect (fast_nms and cc_fast_nms)."""
+    from data.config import cfg, set_cfg
+    from layers import Detect
+    set_cfg("yolact_base_config")
+    r = np.random.RandomState(seed)
+    B, P, C, K = 2, 3000, 81, 32
+    # priors: random centre-size boxes; loc: N(0,1); scores: peaked, unique
+    priors = np.concatenate([r.uniform(0.05, 0.95, (P, 2)), r.uniform(0.03, 0.4, (P, 2))], 1).astype(np.float32)
+    loc = r.standard_normal((B, P, 4)).astype(np.float32)
+    logits = (r.standard_normal((B, P, C)) * 2.0).astype(np.float32)
+    logits[:, :, 0] += 3.0
+    hot = r.rand(B, P) < 0.25
+    cls = r.randint(1, C, size=(B, P))
+    for b in range(B):
+        idx = np.nonzero(hot[b])[0]
+        logits[b, idx, cls[b, idx]] += r.uniform(2.0, 9.0, size=idx.size).astype(np.float32)
+    conf = torch.softmax(torch.from_numpy(logits), -1)
+    mask = np.tanh(r.standard_normal((B, P, K))).astype(np.float32)
+    out = {"loc": loc, "conf": to_np(conf), "mask": mask, "priors": priors}
+    for cc in (False, True):
+        d = Detect(C, bkg_label=0, top_k=200, conf_thresh=0.05, nms_thresh=0.5)
+        d.use_fast_nms = True
+        d.use_cross_class_nms = cc
+        res = d({"loc": torch.from_numpy(loc), "conf": conf, "mask": torch.from_numpy(mask),
+                 "priors": torch.from_numpy(priors)}, None)
+        tag = "cc" if cc else "fast"
+        for b in range(B):
+            det = res[b]["detection"]
+            for k in ("box", "mask", "class", "score"):
+                out["%s%d_%s" % (tag, b, k)] = to_np(det[k])
+            print("detect_unit", tag, b, "n =", det["score"].shape[0])
+    npz_save("detect_unit", **out)
+
+
+def gen_postprocess_unit(seed=5):
+    from data.config import cfg, set_cfg
+    from layers.output_utils import postprocess
+    set_cfg("yolact_base_config")
+    cfg.mask_proto_debug = False
+    r = np.random.RandomState(seed)
+    n, ph, pw, K = 23, 138, 138, 32
+    proto = np.maximum(r.standard_normal((ph, pw, K)), 0).astype(np.float32)
+    # smooth the prototypes so masks have structure
+    proto = (proto + np.roll(proto, 1, 0) + np.roll(proto, 1, 1) + np.roll(proto, (2, 3), (0, 1))) / 4
+    coef = np.tanh(r.standard_normal((n, K))).astype(np.float32)
+    c = r.uniform(0.15, 0.85, (n, 2))
+    wh = r.uniform(0.05, 0.6, (n, 2))
+    box = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    box[3, [0, 2]] = box[3, [2, 0]]      # x1 > x2: sanitize must swap
+    box[5] = [-0.1, 0.2, 0.5, 1.2]       # partially outside the image
+    score = np.sort(r.uniform(0.1, 0.99, n).astype(np.float32))[::-1].copy()
+    cls = r.randint(0, 80, n).astype(np.int64)
+    out = {"proto": proto, "coef": coef, "box": box, "score": score, "cls": cls}
+    for (h, w) in ((550, 550), (203, 277), (64, 96)):
+        for crop in (True, False):
+            det = {"box": torch.from_numpy(box.copy()), "mask": torch.from_numpy(coef), "class": torch.from_numpy(cls),
+                   "score": torch.from_numpy(score), "proto": torch.from_numpy(proto)}
+            with torch.no_grad():
+                classes, scores, boxes, masks = postprocess([{"detection": det, "net": None}], w, h, crop_masks=crop)
+            tag = "%dx%d_%s" % (h, w, "crop" if crop else "nocrop")
+            out["boxes_" + tag] = to_np(boxes)
+            out["masks_" + tag] = np.packbits(to_np(masks).astype(np.uint8), axis=-1)
+            print("postprocess_unit", tag, "mask fill %.4f" % float(masks.mean()))
+    npz_save("postprocess_unit", **out)
+
+
+def gen_dcn_unit(seed=7):
+    """DCNv2 op: torchvision.ops.deform_conv2d (the practical stand-in for the reference extension),
+    cross-checked against the numpy restatement of the reference's CUDA kernel, plus the reference's own
+    zero-offset identity (external/DCNv2/test.py:32-67)."""
+    import torchvision
+    from oracle.yolact_oracle import dcn_v2_forward
+    r = np.random.RandomState(seed)
+    out = {}
+    for tag, (B, C, H, W, Co, stride) in {"s1": (2, 16, 13, 11, 24, 1), "s2": (1, 32, 14, 17, 16, 2)}.items():
+        x = r.standard_normal((B, C, H, W)).astype(np.float32)
+        w = (r.standard_normal((Co, C, 3, 3)) * 0.1).astype(np.float32)
+        bias = r.standard_normal(Co).astype(np.float32)
+        Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+        offset = (r.standard_normal((B, 18, Ho, Wo)) * 2.0).astype(np.float32)
+        mask = (1 / (1 + np.exp(-r.standard_normal((B, 9, Ho, Wo))))).astype(np.float32)
+        y = torchvision.ops.deform_conv2d(torch.from_numpy(x), torch.from_numpy(offset), torch.from_numpy(w),
+                                          torch.from_numpy(bias), stride=stride, padding=1, dilation=1,
+                                          mask=torch.from_numpy(mask)).numpy()
+        y2 = dcn_v2_forward(x, offset, mask, w, bias, stride, 1, 1)
+        print("dcn_unit", tag, "torchvision vs restatement max abs diff", float(np.abs(y - y2).max()))
+        assert np.abs(y - y2).max() < 2e-5
+        out.update({tag + "_x": x, tag + "_w": w, tag + "_bias": bias, tag + "_offset": offset, tag + "_mask": mask,
+                    tag + "_y": y, tag + "_stride": np.array(stride)})
+    # zero-offset identity: weight = identity at the centre tap, mask = 0.5 -> 2*out == input
+    C = 8
+    x = r.standard_normal((2, C, 9, 9)).astype(np.float32)
+    w = np.zeros((C, C, 3, 3), np.float32)
+    for i in range(C):
+        w[i, i, 1, 1] = 1.0
+    y = dcn_v2_forward(x, np.zeros((2, 18, 9, 9), np.float32), np.full((2, 9, 9, 9), 0.5, np.float32), w,
+                       np.zeros(C, np.float32), 1, 1, 1)
+    assert np.abs(2 * y - x).max() < 1e-10, "zero-offset identity failed"
+    print("dcn_unit zero-offset identity ok")
+    npz_save("dcn_unit", **out)
+
+
+def gen_state_keys():
+    """state_dict key -> shape for every published config."""
+    import json
+    from data.config import cfg, set_cfg
+    import yolact as ref_yolact
+    out = {}
+    for name in ("yolact_base_config", "yolact_resnet50_config", "yolact_im700_config", "yolact_darknet53_config",
+                 "yolact_plus_base_config", "yolact_plus_resnet50_config"):
+        set_cfg(name)
+        net = ref_yolact.Yolact()
+        out[name] = {k: list(v.shape) for k, v in net.state_dict().items()}
+        x = torch.zeros(1, 3, cfg.max_size, cfg.max_size)
+        print(name, len(out[name]), "keys")
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "state_keys.json"), "w") as f:
+        json.dump(out, f)
+
+
+if __name__ == "__main__":
+    install_shims()
+    torch.set_num_threads(8)
+    which = sys.argv[1:] or ["units", "nets"]
+    if "keys" in which or "units" in which:
+        gen_state_keys()
+    if "units" in which:
+        gen_detect_unit()
+        gen_postprocess_unit()
+        gen_dcn_unit()
+    if "nets" in which:
+        gen_network_case("net_resnet50_160", "yolact_resnet50_config", 1, 160, 160, (120, 150))
+        gen_network_case("net_base_192x160_b2", "yolact_base_config", 2, 192, 160, (100, 100))
+        gen_network_case("net_plus_resnet50_256", "yolact_plus_resnet50_config", 1, 256, 256, (160, 160), row_stride=4)
+        gen_network_case("net_darknet53_160", "yolact_darknet53_config", 1, 160, 160, (96, 128))

@@ -1,0 +1,92 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/yolact_b200.h declares,
+the host mirror reproduces the reference's state_dict keys, and the product path fails loudly
+(no CPU fallback) when no GPU is present."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+import yolact_b200
+from yolact_b200 import _lib
+from yolact_b200.config import CONFIGS
+from tests.conftest import GOLDEN, ROOT
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "yolact_b200.h")).read()
+    return sorted(set(re.findall(r"^YB_API\s+[\w\s\*]+?\b(yb_[a-z0-9_]+)\s*\(", src, flags=re.M)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    assert os.path.exists(_lib.LIB_PATH), "build the library first: python -m yolact_b200.build"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), "library does not export %s" % s
+    # and the ctypes table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == syms
+    assert _lib.load().yb_abi_version() == 1
+
+
+def test_config_struct_matches_header_layout():
+    # yb_config is plain int32/float fields: 4-byte packed, so sizeof must equal 4 * field count
+    n_words = 1 + 1 + 5 + 4 + 1 + 3 + 1 + 1 + 1 + 1 + 1 + 20 + 1 + 4 + 1 + 1 + 1 + 1 + 1 + 1 + 1
+    assert ctypes.sizeof(_lib.YbConfig) == 4 * n_words
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_state_dict_keys_match_reference(name):
+    ref = json.load(open(os.path.join(GOLDEN, "state_keys.json")))[name]
+    net = yolact_b200.Yolact(CONFIGS[name].copy())
+    mine = {k: list(v.shape) for k, v in net.state_dict().items()}
+    assert mine == ref
+
+
+def test_set_cfg_and_side_effects():
+    c = yolact_b200.set_cfg("yolact_im700_config")
+    assert c.max_size == 700 and c.pred_scales == [[30], [61], [122], [244], [488]]   # config.py:721
+    c = yolact_b200.set_cfg("yolact_plus_base")
+    assert c.use_maskiou and not c.use_square_anchors and abs(c.pred_scales[0][1] - 30.238105197476955) < 1e-9
+    yolact_b200.Yolact()
+    assert yolact_b200.cfg.mask_dim == 32 and yolact_b200.cfg.num_heads == 5          # yolact.py:425,445
+    yolact_b200.set_cfg("yolact_base_config")
+
+
+def test_dcn_placement_rule():
+    from yolact_b200.yolact import _block_uses_dcn
+    # yolact_plus_base: [0,4,23,3], interval 3 -> every stage-first block + every 3rd block = 11 DCNs
+    layers, dcn = [3, 4, 23, 3], [0, 4, 23, 3]
+    n = sum(_block_uses_dcn(layers[i], dcn[i], 3, j) for i in range(4) for j in range(layers[i]))
+    assert n == 11
+    layers, dcn = [3, 4, 6, 3], [0, 4, 6, 3]
+    n = sum(_block_uses_dcn(layers[i], dcn[i], 1, j) for i in range(4) for j in range(layers[i]))
+    assert n == 13
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    net = yolact_b200.Yolact(CONFIGS["yolact_resnet50_config"].copy())
+    net.eval()
+    with pytest.raises(_lib.YbError):
+        net(torch.zeros(1, 3, 64, 64))
+    # the C ABI itself refuses too
+    lib = _lib.load()
+    yc = _lib.YbConfig()
+    yc.backbone = _lib.YB_BACKBONE_NONE
+    yc.mask_dim = 32
+    h = ctypes.c_void_p()
+    assert lib.yb_create(ctypes.byref(yc), 0, ctypes.byref(h)) == -5   # YB_ERR_NO_DEVICE
+    assert b"no CUDA device" in lib.yb_last_error()
+
+
+def test_product_never_imports_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "yolact_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

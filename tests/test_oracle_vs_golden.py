@@ -1,0 +1,107 @@
+"""Pins oracle/yolact_oracle.py (the CPU restatement) to the REAL reference through the committed
+golden vectors (tests/golden/*.npz, produced by oracle/gen_golden.py from /root/reference)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import yolact_oracle as O
+from oracle.weights import deterministic_state_dict
+from tests.helpers import cfg_for, unpack_masks, rel_err
+from tests.conftest import load_golden
+
+NET_CASES = ["net_resnet50_160", "net_base_192x160_b2", "net_plus_resnet50_256", "net_darknet53_160"]
+
+
+def _oracle_net(case):
+    import yolact_b200
+    g = load_golden(case)
+    cfg = cfg_for(str(g["config"]))
+    net = yolact_b200.Yolact(cfg)
+    sd = deterministic_state_dict(net.state_dict(), int(g["seed"]))
+    return g, cfg, O.ConvStackOracle(cfg, sd)
+
+
+@pytest.mark.parametrize("case", NET_CASES)
+def test_conv_stack_matches_reference(case):
+    g, cfg, orc = _oracle_net(case)
+    out = orc.forward(torch.from_numpy(g["x"]))
+    rs = int(g["row_stride"])
+    # fp32 CPU vs fp32 CPU: only summation-order noise
+    assert np.array_equal(out["priors"].numpy(), g["raw_priors"])
+    assert rel_err(out["proto"].numpy(), g["raw_proto"]) < 2e-5
+    assert rel_err(out["loc"].numpy()[:, ::rs], g["raw_loc"]) < 2e-5
+    assert rel_err(out["conf"].numpy()[:, ::rs], g["raw_conf"]) < 2e-5
+    assert rel_err(out["mask"].numpy()[:, ::rs], g["raw_mask"]) < 2e-5
+
+
+@pytest.mark.parametrize("case", ["net_resnet50_160", "net_base_192x160_b2", "net_darknet53_160"])
+def test_detect_and_postprocess_match_reference(case):
+    g, cfg, orc = _oracle_net(case)
+    conf = O.softmax_rows(g["raw_conf"])
+    for b in range(g["x"].shape[0]):
+        det = O.detect_one(g["raw_loc"][b], conf[b], g["raw_mask"][b], g["raw_priors"])
+        assert det is not None and det["score"].shape[0] == int(g["det_counts"][b])
+        assert np.array_equal(det["class"], g["det%d_class" % b])            # class ids: exact
+        np.testing.assert_allclose(det["score"], g["det%d_score" % b], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(det["box"], g["det%d_box" % b], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(det["mask"], g["det%d_mask" % b], rtol=0, atol=1e-6)
+        ph, pw = (int(v) for v in g["post_hw"])
+        det["proto"] = g["raw_proto"][b]
+        classes, scores, boxes, masks = O.postprocess_one(det, pw, ph)
+        ref = unpack_masks(g["post%d_masks_packed" % b], pw)
+        assert np.array_equal(boxes, g["post%d_boxes" % b])
+        assert (masks != ref).mean() < 1e-4                                   # binarised: a few ulp-level flips at most
+
+
+def test_detect_unit_fast_and_cross_class():
+    g = load_golden("detect_unit")
+    for b in range(2):
+        for tag, cc in (("fast", False), ("cc", True)):
+            det = O.detect_one(g["loc"][b], g["conf"][b], g["mask"][b], g["priors"], cross_class=cc)
+            assert np.array_equal(det["class"], g["%s%d_class" % (tag, b)])
+            np.testing.assert_allclose(det["score"], g["%s%d_score" % (tag, b)], rtol=0, atol=1e-6)
+            np.testing.assert_allclose(det["box"], g["%s%d_box" % (tag, b)], rtol=0, atol=2e-6)
+            np.testing.assert_allclose(det["mask"], g["%s%d_mask" % (tag, b)], rtol=0, atol=0)
+
+
+def test_postprocess_unit():
+    g = load_golden("postprocess_unit")
+    det = {"box": g["box"], "mask": g["coef"], "class": g["cls"], "score": g["score"], "proto": g["proto"]}
+    for (h, w) in ((550, 550), (203, 277), (64, 96)):
+        for crop in (True, False):
+            tag = "%dx%d_%s" % (h, w, "crop" if crop else "nocrop")
+            classes, scores, boxes, masks = O.postprocess_one(dict(det), w, h, crop_masks=crop)
+            assert np.array_equal(boxes, g["boxes_" + tag])
+            ref = unpack_masks(g["masks_" + tag], w)
+            assert (masks != ref).mean() < 1e-4, tag
+
+
+def test_plus_maskiou_scores():
+    g, cfg, orc = _oracle_net("net_plus_resnet50_256")
+    b = 0
+    det = {k: g["det%d_%s" % (b, k)] for k in ("box", "mask", "class", "score")}
+    det["proto"] = g["raw_proto"][b]
+    fn = lambda pm: orc.maskiou(torch.from_numpy(pm).unsqueeze(1)).numpy()
+    ph, pw = (int(v) for v in g["post_hw"])
+    classes, scores, boxes, masks = O.postprocess_one(det, pw, ph, maskiou_fn=fn)
+    assert isinstance(scores, list)                                           # output_utils.py:84-88
+    np.testing.assert_allclose(scores[0], g["post0_scores"], atol=1e-6)
+    np.testing.assert_allclose(scores[1], g["post0_scores_maskiou"], rtol=2e-4, atol=1e-6)
+    assert (masks != unpack_masks(g["post0_masks_packed"], pw)).mean() < 1e-4
+
+
+def test_dcn_restatement():
+    g = load_golden("dcn_unit")
+    for tag in ("s1", "s2"):
+        y = O.dcn_v2_forward(g[tag + "_x"], g[tag + "_offset"], g[tag + "_mask"], g[tag + "_w"], g[tag + "_bias"],
+                             int(g[tag + "_stride"]), 1, 1)
+        assert np.abs(y - g[tag + "_y"]).max() < 2e-5
+    # reference's own known answer: zero offsets, mask 0.5, identity kernel -> 2*out == in (test.py:32-67)
+    r = np.random.RandomState(0)
+    C = 8
+    x = r.standard_normal((2, C, 7, 9)).astype(np.float32)
+    w = np.zeros((C, C, 3, 3), np.float32)
+    w[np.arange(C), np.arange(C), 1, 1] = 1
+    y = O.dcn_v2_forward(x, np.zeros((2, 18, 7, 9), np.float32), np.full((2, 9, 7, 9), 0.5, np.float32), w,
+                         np.zeros(C, np.float32), 1, 1, 1)
+    assert np.abs(2 * y - x).max() < 1e-10

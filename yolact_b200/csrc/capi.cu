@@ -308,7 +308,7 @@ int yb_postprocess(yb_handle* h, const float* d_proto, int ph, int pw, int k, co
 int yb_maskiou(yb_handle* h, const float* d_proto_masks, int n, int ph, int pw, const int64_t* d_cls,
                float* d_maskiou, void* stream) {
   YB_API_BEGIN
-  YB_REQUIRE(h && d_proto_masks && d_cls && d_maskiou, "yb_maskiou: null argument");
+  YB_REQUIRE(h && d_proto_masks && d_maskiou, "yb_maskiou: null argument");
   YB_REQUIRE(h->cfg.use_maskiou && h->finalized, "yb_maskiou: network has no maskiou_net / weights not finalized");
   if (n <= 0) return YB_OK;
   DeviceGuard g(h->device);

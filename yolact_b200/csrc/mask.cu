@@ -210,11 +210,12 @@ proto_masks_kernel(const float* __restrict__ proto, int ph, int pw, int k,
   }
 }
 
-// out[i] = max_{h,w} x[i,h,w,cls[i]]   (F.max_pool2d over the full map + gather)
+// out[i] = max_{h,w} x[i,h,w,cls[i]]   (F.max_pool2d over the full map + gather);
+// cls == nullptr: out[i][c] for every channel (grid.y = C), i.e. FastMaskIoUNet.forward itself
 __global__ void maxpool_gather_kernel(const float* __restrict__ x, int HW, int C,
                                       const int64_t* __restrict__ cls, float* __restrict__ out) {
   const int i = blockIdx.x;
-  const int c = (int)cls[i];
+  const int c = cls ? (int)cls[i] : (int)blockIdx.y;
   float m = -INFINITY;
   for (int p = threadIdx.x; p < HW; p += blockDim.x) m = fmaxf(m, x[((size_t)i * HW + p) * C + c]);
 #pragma unroll
@@ -225,7 +226,10 @@ __global__ void maxpool_gather_kernel(const float* __restrict__ x, int HW, int C
   if (threadIdx.x == 0) {
     float r = s[0];
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, s[w]);
-    out[i] = r;
+    if (cls)
+      out[i] = r;
+    else
+      out[(size_t)i * C + c] = r;
   }
 }
 
@@ -290,7 +294,7 @@ void launch_mask_assembly(const float* proto, int ph, int pw, int k, const float
 void launch_maxpool_gather(const float* x_nhwc, int n, int H, int W, int C, const int64_t* cls,
                            float* out, cudaStream_t stream, LaunchCounter* lc) {
   if (n <= 0) return;
-  maxpool_gather_kernel<<<n, 128, 0, stream>>>(x_nhwc, H * W, C, cls, out);
+  maxpool_gather_kernel<<<dim3(n, cls ? 1 : C), 128, 0, stream>>>(x_nhwc, H * W, C, cls, out);
   YB_CHECK_LAUNCH();
   if (lc) lc->n++;
 }
