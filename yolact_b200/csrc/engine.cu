@@ -483,6 +483,12 @@ yb_handle::~yb_handle() {
   for (void* p : weight_allocs) cudaFree(p);
   if (detect_ws) cudaFree(detect_ws);
   if (scratch) cudaFree(scratch);
+  if (cap_stream) cudaStreamDestroy(cap_stream);
+}
+
+cudaStream_t yb_handle::capture_stream() {
+  if (!cap_stream) YB_CHECK_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+  return cap_stream;
 }
 
 void* yb_handle::get_scratch(size_t bytes) {
@@ -676,15 +682,18 @@ void yb_handle::forward(const float* d_x, int B, int H, int W, float* d_loc, flo
     if (!ex->graph_fwd) {
       cudaGraph_t g = nullptr;
       const int64_t before = lc.n;
-      YB_CHECK_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      // capture on a private stream (the caller's stream may be the legacy default stream, which
+      // cannot be captured); the instantiated graph is then launched into the caller's stream
+      cudaStream_t cs = capture_stream();
+      YB_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
       try {
-        run_ops(this, ex, stream);
+        run_ops(this, ex, cs);
       } catch (...) {
-        cudaStreamEndCapture(stream, &g);
+        cudaStreamEndCapture(cs, &g);
         if (g) cudaGraphDestroy(g);
         throw;
       }
-      YB_CHECK_CUDA(cudaStreamEndCapture(stream, &g));
+      YB_CHECK_CUDA(cudaStreamEndCapture(cs, &g));
       lc.n = before;  // capture does not launch
       YB_CHECK_CUDA(cudaGraphInstantiate(&ex->graph_fwd, g, 0));
       cudaGraphDestroy(g);
@@ -749,15 +758,16 @@ void yb_handle::infer(const float* d_x, int B, int H, int W, int cross_class, in
     if (!ex->graph_infer) {
       cudaGraph_t g = nullptr;
       const int64_t before = lc.n;
-      YB_CHECK_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      cudaStream_t cs = capture_stream();
+      YB_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
       try {
-        run_all(stream);
+        run_all(cs);
       } catch (...) {
-        cudaStreamEndCapture(stream, &g);
+        cudaStreamEndCapture(cs, &g);
         if (g) cudaGraphDestroy(g);
         throw;
       }
-      YB_CHECK_CUDA(cudaStreamEndCapture(stream, &g));
+      YB_CHECK_CUDA(cudaStreamEndCapture(cs, &g));
       lc.n = before;
       YB_CHECK_CUDA(cudaGraphInstantiate(&ex->graph_infer, g, 0));
       cudaGraphDestroy(g);

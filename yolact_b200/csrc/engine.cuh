@@ -97,6 +97,8 @@ struct yb_handle {
   size_t detect_ws_bytes = 0;
   void* scratch = nullptr;   // maskiou / dcn / conv2d temporaries
   size_t scratch_bytes = 0;
+  cudaStream_t cap_stream = nullptr;  // private stream used only for CUDA-graph capture
+  cudaStream_t capture_stream();
   ~yb_handle();
 
   // ---- weights
