@@ -105,3 +105,20 @@ def test_dcn_restatement():
     y = O.dcn_v2_forward(x, np.zeros((2, 18, 7, 9), np.float32), np.full((2, 9, 7, 9), 0.5, np.float32), w,
                          np.zeros(C, np.float32), 1, 1, 1)
     assert np.abs(2 * y - x).max() < 1e-10
+
+
+def test_torch_port_matches_numpy_oracle_and_golden():
+    """oracle/torch_port.py (the CPU-baseline implementation bench.py times) against the golden vectors."""
+    from oracle import torch_port as T
+    g = load_golden("detect_unit")
+    t = torch.from_numpy
+    for b in range(2):
+        det = T.detect_one(t(g["loc"][b]), t(g["conf"][b]), t(g["mask"][b]), t(g["priors"]))
+        assert np.array_equal(det["class"].numpy(), g["fast%d_class" % b])
+        np.testing.assert_allclose(det["score"].numpy(), g["fast%d_score" % b], atol=1e-6)
+        np.testing.assert_allclose(det["box"].numpy(), g["fast%d_box" % b], atol=2e-6)
+    g = load_golden("postprocess_unit")
+    det = {"box": t(g["box"]), "mask": t(g["coef"]), "class": t(g["cls"]), "score": t(g["score"]), "proto": t(g["proto"])}
+    classes, scores, boxes, masks = T.postprocess_one(det, 277, 203)
+    assert np.array_equal(boxes.numpy(), g["boxes_203x277_crop"])
+    assert (masks.numpy() != unpack_masks(g["masks_203x277_crop"], 277)).mean() < 1e-4

@@ -1,5 +1,6 @@
 // C ABI (include/yolact_b200.h).  Every entry point converts C++ exceptions into a status code
 // and a thread-local message; nothing here computes on the CPU beyond packing weights.
+#include <stdlib.h>
 #include <string.h>
 
 #include "engine.cuh"
@@ -124,6 +125,7 @@ int yb_create(const yb_config* cfg, int device, yb_handle** out) {
   h->cfg = *cfg;
   h->device = device;
   h->ops_only = (cfg->backbone == YB_BACKBONE_NONE);
+  if (const char* at = getenv("YB_AUTOTUNE")) h->autotune = (atoi(at) != 0);
   if (!h->ops_only) {
     YB_REQUIRE(cfg->backbone == YB_BACKBONE_RESNET || cfg->backbone == YB_BACKBONE_DARKNET, "unknown backbone");
     YB_REQUIRE(cfg->num_stages >= 4 && cfg->num_stages <= 5, "num_stages must be 4 or 5");

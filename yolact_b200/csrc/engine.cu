@@ -224,7 +224,7 @@ struct NetBuilder {
     op.is_conv = true;
     if (tc) {
       YB_REQUIRE(tc_conv_supported(p), ("conv " + key + ": not supported by the tensor-core kernel").c_str());
-      TcConvPlan* plan = tc_conv_plan_create(p, w.w_tc);
+      TcConvPlan* plan = autotune_tc(p, w.w_tc);
       ex->plans.push_back(plan);
       op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
     } else {
@@ -329,7 +329,7 @@ struct NetBuilder {
       p.y_batch_stride = (int64_t)Ho * Wo * w.Cout;
       p.y_pix_stride = w.Cout;
       p.bias = w.bias;
-      TcConvPlan* plan = tc_conv_plan_create(p, w.w_tc);
+      TcConvPlan* plan = autotune_tc(p, w.w_tc);
       ex->plans.push_back(plan);
       Op op;
       op.is_conv = true;
@@ -337,6 +337,59 @@ struct NetBuilder {
       ex->ops.push_back(op);
     }
     return out;
+  }
+
+  // Plan-time autotuning of the tcgen05 kernel's N tile and pipeline depth: each candidate is timed on the
+  // layer's real buffers (contents irrelevant) with CUDA events; the fastest plan is kept.  Small layers
+  // are launch/wave-quantisation bound and large-K ones L2-bandwidth bound, so no single rule fits.
+  TcConvPlan* autotune_tc(const ConvProblem& p, const __half* w) {
+    if (!h->autotune) return tc_conv_plan_create(p, w);
+    const int bns[4] = {256, 128, 64, 32};
+    const int sts[3] = {0, 3, 2};
+    TcConvPlan* best = nullptr;
+    float best_ms = 1e30f;
+    cudaEvent_t e0, e1;
+    YB_CHECK_CUDA(cudaEventCreate(&e0));
+    YB_CHECK_CUDA(cudaEventCreate(&e1));
+    for (int bi = 0; bi < 4; ++bi) {
+      const int bn = bns[bi];
+      if (bn > 32 && bn >= 2 * p.Cout) continue;
+      int last_stages = -1;
+      for (int si = 0; si < 3; ++si) {
+        TcConvPlan* cand = tc_conv_plan_create(p, w, bn, sts[si]);
+        if (tc_conv_plan_stages(cand) == last_stages) {  // override had no effect
+          tc_conv_plan_destroy(cand);
+          continue;
+        }
+        last_stages = tc_conv_plan_stages(cand);
+        float ms = 1e30f;
+        try {
+          for (int i = 0; i < 2; ++i) launch_tc_conv(cand, 0, nullptr);
+          YB_CHECK_CUDA(cudaEventRecord(e0, 0));
+          for (int i = 0; i < 4; ++i) launch_tc_conv(cand, 0, nullptr);
+          YB_CHECK_CUDA(cudaEventRecord(e1, 0));
+          YB_CHECK_CUDA(cudaEventSynchronize(e1));
+          YB_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        } catch (...) {
+          tc_conv_plan_destroy(cand);
+          if (best) tc_conv_plan_destroy(best);
+          cudaEventDestroy(e0);
+          cudaEventDestroy(e1);
+          throw;
+        }
+        if (ms < best_ms) {
+          if (best) tc_conv_plan_destroy(best);
+          best = cand;
+          best_ms = ms;
+        } else {
+          tc_conv_plan_destroy(cand);
+        }
+      }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    YB_REQUIRE(best != nullptr, "autotune: no candidate");
+    return best;
   }
 };
 

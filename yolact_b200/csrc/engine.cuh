@@ -85,6 +85,7 @@ struct yb_handle {
   bool finalized = false;
   bool use_graphs = true;
   bool profiling = false;
+  bool autotune = true;     // YB_AUTOTUNE=0 disables plan-time autotuning of the tcgen05 tiles
   float last_total_ms = 0.f, last_conv_ms = 0.f;
   yb::LaunchCounter lc;
   std::map<std::string, yb::HostTensor> host;

@@ -40,7 +40,11 @@ void launch_simt_conv(const ConvProblem& p, const void* w, int types, cudaStream
 // ---- tcgen05 implicit-GEMM convolution (fp16 in, fp32 accumulate) ----------------------------
 struct TcConvPlan;  // opaque: tensor maps + tiling; built once per (layer, shape, pointers)
 // w_packed: device half [KH*KW][CoutPad][Cin], CoutPad = round_up(Cout,16). Requires Cin % 64 == 0.
-TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed);
+// bn_override in {32,64,128,256} / stages_override > 0 pin the N tile / pipeline depth (autotuner); 0 = heuristic
+TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override = 0,
+                                int stages_override = 0);
+int tc_conv_plan_bn(const TcConvPlan* plan);
+int tc_conv_plan_stages(const TcConvPlan* plan);
 void tc_conv_plan_destroy(TcConvPlan* plan);
 bool tc_conv_supported(const ConvProblem& p);
 void launch_tc_conv(const TcConvPlan* plan, cudaStream_t stream, LaunchCounter* lc);

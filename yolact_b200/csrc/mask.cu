@@ -137,26 +137,63 @@ mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
         out[(size_t)y * wpr + wx] = bits;
       }
     } else {
-      const int npix = (y1 - y0) * out_w;
-      for (int pi = tid; pi < npix; pi += MT) {
-        const int yy = pi / out_w, x = pi - yy * out_w;
-        const int y = y0 + yy;
-        float res = 0.f;
+      // The band of one detection is contiguous in memory: stream it as aligned 4-pixel quads
+      // (16-byte stores for fp32, 4-byte for uint8); quads may straddle a row boundary.
+      const size_t band_off = (size_t)d * plane + (size_t)y0 * out_w;
+      const int L = (y1 - y0) * out_w;
+      const int lead = (int)(band_off & 3);
+      const int nq = (L + lead + 3) >> 2;
+      for (int q = tid; q < nq; q += MT) {
+        const int i0 = 4 * q - lead;
+        float res[4] = {0.f, 0.f, 0.f, 0.f};
         if (any) {
-          const ColTab rt = interp_entry(y, scale_h, ph);
-          const ColTab ct = coltab[x];
-          const float* ra = mrows + (size_t)(rt.i0 - r_lo) * pw;
-          const float* rb = mrows + (size_t)(rt.i1 - r_lo) * pw;
-          float top = __fadd_rn(__fmul_rn(ct.l0, ra[ct.i0]), __fmul_rn(ct.l1, ra[ct.i1]));
-          float bot = __fadd_rn(__fmul_rn(ct.l0, rb[ct.i0]), __fmul_rn(ct.l1, rb[ct.i1]));
-          float v = __fadd_rn(__fmul_rn(rt.l0, top), __fmul_rn(rt.l1, bot));
-          res = v > 0.5f ? 1.f : 0.f;
+          int idx = max(i0, 0);
+          int yy = idx / out_w, x = idx - yy * out_w;
+          int cur_y = -1;
+          ColTab rt;
+          const float *ra = mrows, *rb = mrows;
+          bool row_live = false;
+          for (int j = max(0, -i0); j < 4 && i0 + j < L; ++j) {
+            if (yy != cur_y) {
+              cur_y = yy;
+              rt = interp_entry(y0 + yy, scale_h, ph);
+              ra = mrows + (size_t)(rt.i0 - r_lo) * pw;
+              rb = mrows + (size_t)(rt.i1 - r_lo) * pw;
+              // both source rows outside the crop window -> the whole output row is zero
+              row_live = ((float)rt.i0 >= cy1 && (float)rt.i0 < cy2) || ((float)rt.i1 >= cy1 && (float)rt.i1 < cy2);
+            }
+            if (row_live) {
+              const ColTab ct = coltab[x];
+              if (((float)ct.i0 >= cx1 && (float)ct.i0 < cx2) || ((float)ct.i1 >= cx1 && (float)ct.i1 < cx2)) {
+                float top = __fadd_rn(__fmul_rn(ct.l0, ra[ct.i0]), __fmul_rn(ct.l1, ra[ct.i1]));
+                float bot = __fadd_rn(__fmul_rn(ct.l0, rb[ct.i0]), __fmul_rn(ct.l1, rb[ct.i1]));
+                float v = __fadd_rn(__fmul_rn(rt.l0, top), __fmul_rn(rt.l1, bot));
+                res[j] = v > 0.5f ? 1.f : 0.f;
+              }
+            }
+            if (++x == out_w) {
+              x = 0;
+              ++yy;
+            }
+          }
         }
-        const size_t o = (size_t)d * plane + (size_t)y * out_w + x;
-        if (FORMAT == YB_MASK_F32)
-          reinterpret_cast<float*>(masks_v)[o] = res;
-        else
-          reinterpret_cast<unsigned char*>(masks_v)[o] = (unsigned char)res;
+        if (i0 >= 0 && i0 + 4 <= L) {
+          if (FORMAT == YB_MASK_F32)
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(masks_v) + band_off + i0) =
+                make_float4(res[0], res[1], res[2], res[3]);
+          else
+            *reinterpret_cast<uchar4*>(reinterpret_cast<unsigned char*>(masks_v) + band_off + i0) =
+                make_uchar4((unsigned char)res[0], (unsigned char)res[1], (unsigned char)res[2], (unsigned char)res[3]);
+        } else {
+          for (int j = 0; j < 4; ++j) {
+            const int idx = i0 + j;
+            if (idx < 0 || idx >= L) continue;
+            if (FORMAT == YB_MASK_F32)
+              reinterpret_cast<float*>(masks_v)[band_off + idx] = res[j];
+            else
+              reinterpret_cast<unsigned char*>(masks_v)[band_off + idx] = (unsigned char)res[j];
+          }
+        }
       }
     }
     __syncthreads();  // mrows / s_coef reuse
@@ -255,6 +292,7 @@ void launch_mask_assembly(const float* proto, int ph, int pw, int k, const float
     if (lc) lc->n++;
   }
   if (masks) {
+    YB_REQUIRE((reinterpret_cast<uintptr_t>(masks) & 15) == 0, "mask_assembly: masks must be 16-byte aligned");
     int band = 8;
     int max_rows;
     size_t smem;

@@ -37,6 +37,10 @@ constexpr int MAX_STAGES = 8;
 struct alignas(64) TcParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
+  CUtensorMap tmY;      // output tile store  (epi_tma)
+  CUtensorMap tmR;      // residual tile load (epi_tma && residual)
+  int epi_tma;          // 1: fp16 NHWC output goes smem -> TMA store, residual comes in by TMA
+  int res_off;          // byte offset of the residual staging buffers inside dynamic smem
   int ntaps, kchunks, stages;
   int tap_map[MAX_TAPS], tap_dx[MAX_TAPS], tap_dy[MAX_TAPS];
   int tw, th, tiles_x, tiles_y;
@@ -105,6 +109,19 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* desc, ui
       "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const void* desc, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -179,6 +196,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   __shared__ uint64_t full_bar[MAX_STAGES];
   __shared__ uint64_t empty_bar[MAX_STAGES];
   __shared__ uint64_t tmem_full_bar;
+  __shared__ uint64_t res_full_bar[2];
   __shared__ uint32_t s_tmem_base;
 
   // 1024-byte alignment required by SWIZZLE_128B (host adds 1024 bytes of slack)
@@ -204,9 +222,12 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&tmem_full_bar, 1);
+    mbar_init(&res_full_bar[0], 1);
+    mbar_init(&res_full_bar[1], 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmA[0]);
+    if (p.epi_tma) tma_prefetch_desc(&p.tmY);
   }
   if (warp == 1) tmem_alloc<BN>(&s_tmem_base);
   tc_fence_before();
@@ -262,6 +283,85 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
     const int oy = y0 + ly, ox = x0 + lx;
     const bool row_ok = (row < p.tw * p.th) && (oy < p.Ho) && (ox < p.Wo);
     const long long pix = (long long)oy * p.Wo + ox;
+    if (p.epi_tma) {
+      // ---- staged epilogue: TMEM -> regs -> (+bias, +residual from smem, act) -> swizzled smem tile
+      //      -> one TMA store per 64-channel chunk (full 128-byte lines, OOB rows clipped by hardware)
+      const bool issuer = (warp == 2 && lane == 0);
+      const bool has_res = (p.residual != nullptr);
+      const int ncols = min(BN, p.Cout - n0);
+      const int nchunks = (ncols + 63) >> 6;
+      uint8_t* out_base = smem;                 // aliases the pipeline buffers: free once tmem_full fires
+      uint8_t* res_base = smem + p.res_off;     // dedicated, so the first two chunks prefetch during the mainloop
+      if (issuer && has_res) {
+        for (int c = 0; c < min(nchunks, 2); ++c) {
+          mbar_expect_tx(&res_full_bar[c], (uint32_t)p.a_box_bytes);
+          tma_load_4d(res_base + c * A_STAGE_BYTES, &p.tmR, &res_full_bar[c], n0 + c * 64, x0, y0, b);
+        }
+      }
+      mbar_wait(&tmem_full_bar, 0);
+      tc_fence_after();
+      const uint32_t sw = (uint32_t)(row & 7);
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        uint8_t* out_tile = out_base + buf * A_STAGE_BYTES;
+        uint8_t* res_tile = res_base + buf * A_STAGE_BYTES;
+        if (c >= 2) {
+          if (issuer) bulk_wait_read<1>();  // the store that used this buffer two chunks ago has read it
+          epi_bar_sync();
+        }
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 64), r0);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 64 + 32), r1);
+        if (has_res) mbar_wait(&res_full_bar[buf], (uint32_t)((c >> 1) & 1));
+        const int nbase = n0 + c * 64;
+#pragma unroll
+        for (int j8 = 0; j8 < 8; ++j8) {   // 8 channels (16 bytes) at a time
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = j8 * 8 + j;
+            v[j] = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]);
+            if (p.bias && nbase + col < p.Cout) v[j] += __ldg(p.bias + nbase + col);
+          }
+          if (p.res_after_act) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act);
+          }
+          const uint32_t off = (uint32_t)row * 128u + (((uint32_t)j8 ^ sw) << 4);
+          if (has_res) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(res_tile + off);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(h2[j]);
+              v[2 * j] += f.x;
+              v[2 * j + 1] += f.y;
+            }
+          }
+          if (!p.res_after_act) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act);
+          }
+          uint4 o;
+          __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o2[j] = __halves2half2(from_f32<__half>(v[2 * j]), from_f32<__half>(v[2 * j + 1]));
+          *reinterpret_cast<uint4*>(out_tile + off) = o;
+        }
+        fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+        epi_bar_sync();
+        if (issuer) {
+          tma_store_4d(&p.tmY, out_tile, nbase, x0, y0, b);
+          bulk_commit();
+          if (has_res && c + 2 < nchunks) {   // everyone is done reading res_tile[buf]: refill it
+            mbar_expect_tx(&res_full_bar[buf], (uint32_t)p.a_box_bytes);
+            tma_load_4d(res_tile, &p.tmR, &res_full_bar[buf], n0 + (c + 2) * 64, x0, y0, b);
+          }
+        }
+      }
+      if (issuer) bulk_wait_read<0>();  // smem must outlive the bulk reads
+    } else {
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
 
@@ -341,6 +441,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
         }
       }
     }
+    }  // direct-store epilogue
   }
 
   tc_fence_before();
@@ -415,7 +516,7 @@ bool tc_conv_supported(const ConvProblem& p) {
   return true;
 }
 
-TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed) {
+TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override, int stages_override) {
   YB_REQUIRE(tc_conv_supported(p), "tc_conv: unsupported problem");
   YB_REQUIRE(p.Ho == (p.H + 2 * p.pad - p.KH) / p.stride + 1, "tc_conv: bad Ho");
   YB_REQUIRE(p.Wo == (p.W + 2 * p.pad - p.KW) / p.stride + 1, "tc_conv: bad Wo");
@@ -477,13 +578,27 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed) {
       }
     }
     plan->BN = bn_best;
+    if (bn_override == 32 || bn_override == 64 || bn_override == 128 || bn_override == 256) plan->BN = bn_override;
   }
   const int BN = plan->BN;
   const int stage_bytes = A_STAGE_BYTES + BN * BLOCK_K * 2;
-  int stages = std::min(MAX_STAGES, (200 * 1024) / stage_bytes);
+  // ---- epilogue mode: fp16 NHWC outputs with 16-byte aligned rows go through smem + TMA store
+  const int esz = p.y_f32 ? 4 : 2;
+  const int vec_elems = 16 / esz;
+  bool vec_ok = (p.y_pix_stride % vec_elems == 0) && (p.y_batch_stride % vec_elems == 0) &&
+                ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+  if (p.residual) vec_ok = vec_ok && (p.Cout % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+  q.vec_ok = vec_ok ? 1 : 0;
+  q.epi_tma = (!p.y_f32 && vec_ok && p.Cout % 8 == 0) ? 1 : 0;
+  const int res_bytes = (q.epi_tma && p.residual) ? 2 * A_STAGE_BYTES : 0;
+  int stages = std::min(MAX_STAGES, (200 * 1024 - res_bytes) / stage_bytes);
+  if (stages_override > 0) stages = std::min(stages, stages_override);
   stages = std::max(1, std::min(stages, q.ntaps * q.kchunks));
   q.stages = stages;
-  plan->smem_bytes = (size_t)stages * stage_bytes + 1024;
+  size_t pipe_bytes = (size_t)stages * stage_bytes;
+  if (q.epi_tma) pipe_bytes = std::max(pipe_bytes, (size_t)2 * A_STAGE_BYTES);  // two output staging tiles alias it
+  q.res_off = (int)pipe_bytes;
+  plan->smem_bytes = pipe_bytes + res_bytes + 1024;
   plan->grid = dim3((unsigned)m_tiles, (unsigned)ceil_div(p.Cout, BN));
 
   // ---- instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major, N, M=128
@@ -547,16 +662,33 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed) {
     q.y_batch_stride = p.y_batch_stride;
     q.res_batch_stride = (long long)p.Ho * p.Wo * p.Cout;
   }
-  const int esz = p.y_f32 ? 4 : 2;
-  const int vec_elems = 16 / esz;
-  bool vec_ok = (p.y_pix_stride % vec_elems == 0) && (p.y_batch_stride % vec_elems == 0) &&
-                ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
-  if (p.residual) vec_ok = vec_ok && (p.Cout % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
-  q.vec_ok = vec_ok ? 1 : 0;
+  if (q.epi_tma) {
+    // output / residual tile maps: same geometry as the accumulator tile, 64-channel boxes
+    uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)q.tw, (uint32_t)q.th, 1};
+    if (flat) {
+      uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)Wov, 1, 1};
+      uint64_t ystr[3] = {(uint64_t)p.y_pix_stride * 2, (uint64_t)Wov * p.y_pix_stride * 2, (uint64_t)Wov * p.y_pix_stride * 2};
+      encode_map(&q.tmY, p.y, 4, dims, ystr, box);
+      if (p.residual) {
+        uint64_t rstr[3] = {(uint64_t)p.Cout * 2, (uint64_t)Wov * p.Cout * 2, (uint64_t)Wov * p.Cout * 2};
+        encode_map(&q.tmR, p.residual, 4, dims, rstr, box);
+      }
+    } else {
+      uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.B};
+      uint64_t ystr[3] = {(uint64_t)p.y_pix_stride * 2, (uint64_t)p.Wo * p.y_pix_stride * 2, (uint64_t)p.y_batch_stride * 2};
+      encode_map(&q.tmY, p.y, 4, dims, ystr, box);
+      if (p.residual) {
+        uint64_t rstr[3] = {(uint64_t)p.Cout * 2, (uint64_t)p.Wo * p.Cout * 2, (uint64_t)p.Ho * p.Wo * p.Cout * 2};
+        encode_map(&q.tmR, p.residual, 4, dims, rstr, box);
+      }
+    }
+  }
   return plan;
 }
 
 void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
+int tc_conv_plan_bn(const TcConvPlan* plan) { return plan->BN; }
+int tc_conv_plan_stages(const TcConvPlan* plan) { return plan->prm.stages; }
 
 template <int BN>
 static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
