@@ -198,6 +198,8 @@ YB_API int64_t yb_launch_count(yb_handle* h);
  * events on `stream` when profiling was enabled with yb_set_profiling(h,1). */
 YB_API int yb_set_profiling(yb_handle* h, int enable);
 YB_API int yb_last_forward_ms(yb_handle* h, float* total_ms, float* conv_ms);
+/* Per-op CSV ("layer name,ms\n") of the last profiled yb_forward (yb_set_profiling(h,1)). */
+YB_API int yb_last_forward_profile(yb_handle* h, char* buf, int64_t cap);
 /* Enable/disable CUDA-graph replay of yb_forward (default on). */
 YB_API int yb_set_graphs(yb_handle* h, int enable);
 

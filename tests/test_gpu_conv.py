@@ -103,6 +103,9 @@ TC_CASES = [
     (1, 256, 9, 9, 256, 3, 2, 1, 0, False),      # FPN downsample 9 -> 5
     (1, 64, 138, 138, 64, 3, 1, 1, 1, False),    # stage 1 3x3
     (1, 1152, 20, 20, 128, 1, 1, 0, 1, False),   # DCN contraction as 1x1 over 9*C columns
+    (1, 64, 20, 20, 32, 1, 1, 0, 3, False),      # Darknet block conv1: fp16 output narrower than the 64-channel store box
+    (2, 256, 35, 35, 1024, 1, 1, 0, 1, True),    # stage-3 conv3: 16 residual/output chunks per tile row
+    (1, 256, 69, 69, 72, 3, 1, 1, 1, False),     # Cout = 72: last chunk is 8 channels wide
 ]
 
 

@@ -126,6 +126,7 @@ int yb_create(const yb_config* cfg, int device, yb_handle** out) {
   h->device = device;
   h->ops_only = (cfg->backbone == YB_BACKBONE_NONE);
   if (const char* at = getenv("YB_AUTOTUNE")) h->autotune = (atoi(at) != 0);
+  if (const char* st = getenv("YB_STEM_TC")) h->stem_on_tc = (atoi(st) != 0);
   if (!h->ops_only) {
     YB_REQUIRE(cfg->backbone == YB_BACKBONE_RESNET || cfg->backbone == YB_BACKBONE_DARKNET, "unknown backbone");
     YB_REQUIRE(cfg->num_stages >= 4 && cfg->num_stages <= 5, "num_stages must be 4 or 5");
@@ -564,6 +565,17 @@ int yb_last_forward_ms(yb_handle* h, float* total_ms, float* conv_ms) {
   YB_REQUIRE(h, "null handle");
   if (total_ms) *total_ms = h->last_total_ms;
   if (conv_ms) *conv_ms = h->last_conv_ms;
+  YB_API_END
+}
+
+int yb_last_forward_profile(yb_handle* h, char* buf, int64_t cap) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && buf && cap > 0, "yb_last_forward_profile: bad argument");
+  YB_REQUIRE(h->last_exec, "yb_last_forward_profile: no forward has run");
+  std::string s;
+  for (auto& op : h->last_exec->ops) s += op.name + "," + std::to_string(op.last_ms) + "\n";
+  if ((int64_t)s.size() + 1 > cap) s.resize((size_t)cap - 1);
+  memcpy(buf, s.c_str(), s.size() + 1);
   YB_API_END
 }
 

@@ -24,6 +24,7 @@ Executor::~Executor() {
   if (graph_fwd) cudaGraphExecDestroy(graph_fwd);
   if (graph_infer) cudaGraphExecDestroy(graph_infer);
   for (auto* p : plans) tc_conv_plan_destroy(p);
+  for (auto* p : stem_plans) stem_tc_plan_destroy(p);
   for (void* p : allocs) cudaFree(p);
 }
 
@@ -190,7 +191,10 @@ struct NetBuilder {
     p.x_nchw_f32 = in_nchw ? 1 : 0;
     const bool tc = f16 && !in_nchw && (in.C % 64 == 0) && !in.f32;
     const bool simt_half = f16 && !tc && !in.f32;
-    ConvW& w = h->get_conv(key, bn, /*want_tc=*/tc, /*want_f32=*/!tc && !simt_half, /*want_f16=*/simt_half);
+    const bool stem_tc = f16 && in_nchw && !ospec && !out_f32 && !residual && h->stem_on_tc &&
+                         stem_tc_supported(k, stride, pad, in.C, h->peek_cout(key));
+    ConvW& w = stem_tc ? h->get_conv(key, bn, /*want_tc=*/true, false, false, /*pack=*/2)
+                       : h->get_conv(key, bn, /*want_tc=*/tc, /*want_f32=*/!tc && !simt_half, /*want_f16=*/simt_half);
     YB_REQUIRE(w.Cin == in.C && w.KH == k && w.KW == k, ("conv " + key + ": weight shape mismatch").c_str());
     p.Cout = w.Cout;
     p.bias = w.bias;
@@ -222,10 +226,21 @@ struct NetBuilder {
     LaunchCounter* lc = &h->lc;
     Op op;
     op.is_conv = true;
+    op.name = key + " " + std::to_string(in.C) + "->" + std::to_string(w.Cout) + " k" + std::to_string(k) + "s" +
+              std::to_string(stride) + " " + std::to_string(p.Ho) + "x" + std::to_string(p.Wo);
+    if (stem_tc) {
+      StemTcPlan* sp = stem_tc_plan_create((const float*)in.ptr, w.w_tc, w.bias, (__half*)out.ptr, in.B, in.H, in.W, k,
+                                           stride, pad, w.Cout, act);
+      ex->stem_plans.push_back(sp);
+      op.fn = [sp, lc](cudaStream_t s) { launch_stem_tc(sp, s, lc); };
+      ex->ops.push_back(op);
+      return out;
+    }
     if (tc) {
       YB_REQUIRE(tc_conv_supported(p), ("conv " + key + ": not supported by the tensor-core kernel").c_str());
       TcConvPlan* plan = autotune_tc(p, w.w_tc);
       ex->plans.push_back(plan);
+      op.name += " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) + " st=" + std::to_string(tc_conv_plan_stages(plan));
       op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
     } else {
       int types;
@@ -248,6 +263,7 @@ struct NetBuilder {
     if (dry) return out;
     LaunchCounter* lc = &h->lc;
     Op op;
+    op.name = "maxpool";
     if (f16)
       op.fn = [in, out, lc](cudaStream_t s) {
         launch_maxpool3x3s2<__half>((const __half*)in.ptr, (__half*)out.ptr, in.B, in.H, in.W, in.C, out.H, out.W, s, lc);
@@ -267,6 +283,7 @@ struct NetBuilder {
     LaunchCounter* lc = &h->lc;
     const void* addp = add ? add->ptr : nullptr;
     Op op;
+    op.name = "upsample " + std::to_string(Ho) + "x" + std::to_string(Wo);
     if (f16)
       op.fn = [in, out, addp, sh, sw, relu, lc](cudaStream_t s) {
         launch_upsample_bilinear<__half>((const __half*)in.ptr, (const __half*)addp, (__half*)out.ptr, in.B, in.H,
@@ -286,7 +303,7 @@ struct NetBuilder {
     // conv_offset_mask: 3x3, same stride/pad, bias, 27 channels, fp32 output (dcn_v2.py:106-124)
     Act om = conv(key + ".conv_offset_mask", "", in, 3, stride, 1, ACT_NONE, nullptr, /*out_f32=*/true);
     const bool tc = f16;
-    ConvW& w = h->get_conv(key, bn, /*want_tc=*/tc, /*want_f32=*/!tc, /*want_f16=*/false, /*dcn_pack=*/true);
+    ConvW& w = h->get_conv(key, bn, /*want_tc=*/tc, /*want_f32=*/!tc, /*want_f16=*/false, /*pack=*/1);
     const int Ho = om.H, Wo = om.W;
     Act out = alloc_act(in.B, Ho, Wo, w.Cout);
     if (dry) return out;
@@ -307,6 +324,7 @@ struct NetBuilder {
       Act cols = alloc_act(in.B, Ho, Wo, 9 * in.C);
       Op g;
       g.is_conv = true;
+      g.name = key + " dcn_gather";
       g.fn = [in, om, cols, stride, lc](cudaStream_t s) {
         launch_dcn_gather_f16((const __half*)in.ptr, (const float*)om.ptr, (__half*)cols.ptr, in.B, in.H, in.W, in.C,
                               cols.H, cols.W, stride, 1, 1, 1, s, lc);
@@ -333,6 +351,7 @@ struct NetBuilder {
       ex->plans.push_back(plan);
       Op op;
       op.is_conv = true;
+      op.name = key + " dcn_contract K=" + std::to_string(p.Cin);
       op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
       ex->ops.push_back(op);
     }
@@ -344,6 +363,13 @@ struct NetBuilder {
   // are launch/wave-quantisation bound and large-K ones L2-bandwidth bound, so no single rule fits.
   TcConvPlan* autotune_tc(const ConvProblem& p, const __half* w) {
     if (!h->autotune) return tc_conv_plan_create(p, w);
+    // identical layer shapes (e.g. the 23 blocks of stage 3) share one decision
+    const std::string tkey = std::to_string(p.B) + "," + std::to_string(p.H) + "," + std::to_string(p.W) + "," +
+                             std::to_string(p.Cin) + "," + std::to_string(p.Cout) + "," + std::to_string(p.KH) + "," +
+                             std::to_string(p.stride) + "," + std::to_string(p.pad) + "," + (p.residual ? "r" : "-") +
+                             (p.y_f32 ? "f" : "h") + std::to_string(p.y_pix_stride) + "," + std::to_string((long long)p.y_batch_stride);
+    auto it = h->tune_cache.find(tkey);
+    if (it != h->tune_cache.end()) return tc_conv_plan_create(p, w, it->second.first, it->second.second);
     const int bns[4] = {256, 128, 64, 32};
     const int sts[3] = {0, 3, 2};
     TcConvPlan* best = nullptr;
@@ -357,16 +383,16 @@ struct NetBuilder {
       int last_stages = -1;
       for (int si = 0; si < 3; ++si) {
         TcConvPlan* cand = tc_conv_plan_create(p, w, bn, sts[si]);
-        if (tc_conv_plan_stages(cand) == last_stages) {  // override had no effect
+        if (tc_conv_plan_bn(cand) != bn || tc_conv_plan_stages(cand) == last_stages) {  // override had no effect
           tc_conv_plan_destroy(cand);
           continue;
         }
         last_stages = tc_conv_plan_stages(cand);
         float ms = 1e30f;
         try {
-          for (int i = 0; i < 2; ++i) launch_tc_conv(cand, 0, nullptr);
+          for (int i = 0; i < 3; ++i) launch_tc_conv(cand, 0, nullptr);
           YB_CHECK_CUDA(cudaEventRecord(e0, 0));
-          for (int i = 0; i < 4; ++i) launch_tc_conv(cand, 0, nullptr);
+          for (int i = 0; i < 10; ++i) launch_tc_conv(cand, 0, nullptr);
           YB_CHECK_CUDA(cudaEventRecord(e1, 0));
           YB_CHECK_CUDA(cudaEventSynchronize(e1));
           YB_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
@@ -389,6 +415,7 @@ struct NetBuilder {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     YB_REQUIRE(best != nullptr, "autotune: no candidate");
+    h->tune_cache[tkey] = std::make_pair(tc_conv_plan_bn(best), tc_conv_plan_stages(best));
     return best;
   }
 };
@@ -570,6 +597,11 @@ void* yb_handle::get_detect_ws(size_t bytes) {
   return detect_ws;
 }
 
+int yb_handle::peek_cout(const std::string& conv_key) const {
+  auto it = host.find(conv_key + ".weight");
+  return (it == host.end() || it->second.shape.empty()) ? 0 : (int)it->second.shape[0];
+}
+
 static const HostTensor& need(yb_handle* h, const std::string& name) {
   auto it = h->host.find(name);
   if (it == h->host.end()) throw Error(YB_ERR_MISSING_WEIGHT, "missing weight: " + name);
@@ -577,7 +609,7 @@ static const HostTensor& need(yb_handle* h, const std::string& name) {
 }
 
 ConvW& yb_handle::get_conv(const std::string& conv_key, const std::string& bn_key, bool want_tc, bool want_f32,
-                           bool want_f16, bool dcn_pack) {
+                           bool want_f16, int pack) {
   ConvW& cw = convs[conv_key];
   const HostTensor& w = need(this, conv_key + ".weight");
   YB_REQUIRE(w.shape.size() == 4, ("weight " + conv_key + " is not 4-D").c_str());
@@ -587,7 +619,7 @@ ConvW& yb_handle::get_conv(const std::string& conv_key, const std::string& bn_ke
     cw.Cout = Co;
     cw.KH = KH;
     cw.KW = KW;
-    cw.dcn_pack = dcn_pack;
+    cw.pack = pack;
   }
   const bool has_bias = host.count(conv_key + ".bias") > 0;
   const bool has_bn = !bn_key.empty();
@@ -638,7 +670,15 @@ ConvW& yb_handle::get_conv(const std::string& conv_key, const std::string& bn_ke
   }
   if (need_tc) {
     std::vector<__half> pk(K * Co);
-    if (dcn_pack) {
+    if (pack == 2) {
+      // stem: [Cout][Kpad], k = c*taps + t (the OIHW flattening), zero padded to a multiple of 64
+      const size_t kpad = (size_t)stem_tc_kpad(KH);
+      pk.assign(kpad * Co, __float2half_rn(0.f));
+      for (int o = 0; o < Co; ++o)
+        for (int c = 0; c < Ci; ++c)
+          for (int t = 0; t < taps; ++t)
+            pk[(size_t)o * kpad + (size_t)c * taps + t] = __float2half_rn(w.data[((size_t)o * Ci + c) * taps + t] * scale[o]);
+    } else if (pack == 1) {
       // [Cout][tap*Cin + c]: the contraction runs as a 1x1 conv over gathered columns
       for (int o = 0; o < Co; ++o)
         for (int c = 0; c < Ci; ++c)
@@ -715,6 +755,7 @@ static void run_ops_profiled(yb_handle* h, Executor* ex, cudaStream_t stream) {
     float ms = 0.f;
     YB_CHECK_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
     total += ms;
+    ex->ops[i].last_ms = ms;
     if (ex->ops[i].is_conv) conv += ms;
   }
   h->last_total_ms = total;

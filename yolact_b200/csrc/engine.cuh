@@ -28,7 +28,7 @@ struct ConvW {
   __half* w_f16 = nullptr;   // [KH*KW*Cin][Cout]           (SIMT fp16)
   __half* w_tc = nullptr;    // [KH*KW][Cout][Cin]          (tcgen05), or [1][Cout][9*Cin] for DCN
   float* bias = nullptr;     // [Cout] or null
-  bool dcn_pack = false;
+  int pack = 0;              // 0 normal, 1 DCN ([Cout][9*Cin]), 2 stem ([Cout][Kpad], OIHW order)
 };
 
 // NHWC activation (element type float in YB_PREC_F32, __half in YB_PREC_F16TC unless f32 is set)
@@ -42,12 +42,15 @@ struct Act {
 struct Op {
   std::function<void(cudaStream_t)> fn;
   bool is_conv = false;
+  std::string name;   // layer key, for yb_last_forward_profile
+  float last_ms = 0.f;
 };
 
 struct Executor {
   int B = 0, H = 0, W = 0;
   std::vector<void*> allocs;
   std::vector<TcConvPlan*> plans;
+  std::vector<StemTcPlan*> stem_plans;
   std::vector<Op> ops;           // the conv stack (yb_forward)
   float* d_in = nullptr;         // NCHW fp32 copy of the input (stable address for graph replay)
   float* loc = nullptr;          // [B,P,4]
@@ -85,6 +88,7 @@ struct yb_handle {
   bool finalized = false;
   bool use_graphs = true;
   bool profiling = false;
+  bool stem_on_tc = true;   // YB_STEM_TC=0 falls back to the SIMT stem
   bool autotune = true;     // YB_AUTOTUNE=0 disables plan-time autotuning of the tcgen05 tiles
   float last_total_ms = 0.f, last_conv_ms = 0.f;
   yb::LaunchCounter lc;
@@ -92,6 +96,7 @@ struct yb_handle {
   std::map<std::string, yb::ConvW> convs;
   std::map<std::string, std::unique_ptr<yb::Executor>> execs;
   std::vector<void*> weight_allocs;
+  std::map<std::string, std::pair<int, int>> tune_cache;  // layer shape -> (BN, stages) picked by the autotuner
   yb::Executor* last_exec = nullptr;
   // standalone op workspaces
   void* detect_ws = nullptr;
@@ -104,7 +109,8 @@ struct yb_handle {
 
   // ---- weights
   yb::ConvW& get_conv(const std::string& conv_key, const std::string& bn_key, bool want_tc, bool want_f32,
-                      bool want_f16, bool dcn_pack = false);
+                      bool want_f16, int pack = 0);
+  int peek_cout(const std::string& conv_key) const;
   void finalize();
   // ---- executors
   yb::Executor* get_executor(int B, int H, int W);

@@ -49,6 +49,16 @@ void tc_conv_plan_destroy(TcConvPlan* plan);
 bool tc_conv_supported(const ConvProblem& p);
 void launch_tc_conv(const TcConvPlan* plan, cudaStream_t stream, LaunchCounter* lc);
 
+// ---- stem on tcgen05 (3-channel NCHW fp32 frame -> NHWC fp16) ---------------------------------------
+struct StemTcPlan;
+bool stem_tc_supported(int ks, int stride, int pad, int cin, int cout);
+int stem_tc_kpad(int ks);   // K = 3*ks*ks rounded up to 64
+// w_packed: device half [cout][kpad], k = c*ks*ks + r*ks + s (OIHW flattening), zero padded
+StemTcPlan* stem_tc_plan_create(const float* x_nchw, const __half* w_packed, const float* bias, __half* y, int B,
+                                int H, int W, int ks, int stride, int pad, int cout, int act);
+void stem_tc_plan_destroy(StemTcPlan* plan);
+void launch_stem_tc(const StemTcPlan* plan, cudaStream_t stream, LaunchCounter* lc);
+
 // ---- pointwise -------------------------------------------------------------------------------
 // 3x3 stride-2 pad-1 max pool, NHWC (backbone.py:80)
 template <typename T>

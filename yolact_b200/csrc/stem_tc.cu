@@ -1,0 +1,231 @@
+// Network stem on tcgen05: conv KxK over the 3-channel NCHW fp32 input frame (+ folded BN + activation)
+// -> NHWC fp16.  ResNet: 7x7/2 pad 3, 3->64, ReLU (backbone.py:77-79,129-131).  Darknet: 3x3/1 pad 1,
+// 3->32, LeakyReLU(0.1) (backbone.py:267, :222-233).
+//
+// Cin = 3 is useless for TMA (6 bytes per pixel) so the A operand is built by the CUDA cores:
+// each of the 128 worker threads owns one output pixel, gathers its KxKx3 patch straight from the
+// fp32 NCHW frame (zero padding by predication, layout conversion and fp32->fp16 cast fused in),
+// and writes it as one K-major SWIZZLE_128B row of the UMMA A tile in shared memory
+// (k = c*K*K + r*K + s, the OIHW flattening, so the weights need no permutation).  A fifth warp
+// TMA-loads the [Cout][Kpad] weight tile, issues ceil(K/16) tcgen05.mma (M=128, N=Cout) and commits;
+// the workers then read their accumulator row from TMEM and store one full 64/128-byte line each.
+// Several CTAs per SM overlap gather / MMA / epilogue of different tiles.
+#include "tc_common.cuh"
+
+namespace yb {
+
+using namespace tc;
+
+namespace {
+
+constexpr int ST_M = 128;
+constexpr int ST_THREADS = 160;  // warps 0-3 workers (TMEM lane quadrant == warp), warp 4 MMA
+
+struct alignas(64) StemParams {
+  CUtensorMap tmW;
+  const float* x;
+  const float* bias;
+  __half* y;
+  int B, H, W, Ho, Wo;
+  long long M;
+  uint32_t idesc;
+  int act;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int KS, int STRIDE, int PAD, int COUT>
+__global__ void __launch_bounds__(ST_THREADS)
+stem_tc_kernel(const __grid_constant__ StemParams p) {
+  constexpr int K = 3 * KS * KS;
+  constexpr int ATOMS = (K + 63) / 64;
+  constexpr int KSTEPS = (K + 15) / 16;
+  constexpr int A_ATOM_BYTES = ST_M * 128;
+  constexpr int B_ATOM_BYTES = COUT * 128;
+
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ uint64_t a_full, b_full, tmem_full;
+  __shared__ uint32_t s_tmem;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + ATOMS * A_ATOM_BYTES;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&a_full, 128);
+    mbar_init(&b_full, 1);
+    mbar_init(&tmem_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmW);
+  }
+  if (warp == 4) tmem_alloc<COUT>(&s_tmem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(&b_full, ATOMS * B_ATOM_BYTES);
+      for (int a = 0; a < ATOMS; ++a) tma_load_3d(sB + a * B_ATOM_BYTES, &p.tmW, &b_full, a * 64, 0, 0);
+      mbar_wait(&b_full, 0);
+      mbar_wait(&a_full, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < KSTEPS; ++j) {
+        const int atom = j >> 2, kk = j & 3;
+        const uint64_t da = make_sw128_desc(smem_u32(sA + atom * A_ATOM_BYTES)) + (uint64_t)(2 * kk);
+        const uint64_t db = make_sw128_desc(smem_u32(sB + atom * B_ATOM_BYTES)) + (uint64_t)(2 * kk);
+        umma_f16(tmem_base, da, db, p.idesc, j > 0 ? 1u : 0u);
+      }
+      umma_commit(&tmem_full);
+    }
+  } else {
+    const int row = tid;
+    const long long m = (long long)blockIdx.x * ST_M + row;
+    const bool valid = m < p.M;
+    int b = 0, ho = 0, wo = 0;
+    if (valid) {
+      wo = (int)(m % p.Wo);
+      const long long t = m / p.Wo;
+      ho = (int)(t % p.Ho);
+      b = (int)(t / p.Ho);
+    }
+    const int hb = ho * STRIDE - PAD, wb = wo * STRIDE - PAD;
+    unsigned rmask = 0, cmask = 0;
+#pragma unroll
+    for (int r = 0; r < KS; ++r) {
+      if (valid && hb + r >= 0 && hb + r < p.H) rmask |= 1u << r;
+      if (valid && wb + r >= 0 && wb + r < p.W) cmask |= 1u << r;
+    }
+    const size_t plane = (size_t)p.H * p.W;
+    const float* xb = p.x + (size_t)b * 3 * plane + (long long)hb * p.W + wb;  // may point before the frame: guarded
+    const uint32_t sw = (uint32_t)(row & 7);
+#pragma unroll
+    for (int kg = 0; kg < ATOMS * 8; ++kg) {
+      uint4 pk;
+      __half2* h2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = kg * 8 + j2 * 2 + e;   // compile-time after unrolling
+          float val = 0.f;
+          if (k < K) {
+            const int c = k / (KS * KS), r = (k % (KS * KS)) / KS, s = k % KS;
+            if (((rmask >> r) & 1u) && ((cmask >> s) & 1u)) val = __ldg(xb + (size_t)c * plane + r * p.W + s);
+          }
+          v[e] = val;
+        }
+        h2[j2] = __halves2half2(from_f32<__half>(v[0]), from_f32<__half>(v[1]));
+      }
+      const int atom = kg >> 3;
+      *reinterpret_cast<uint4*>(sA + atom * A_ATOM_BYTES + row * 128 + ((((uint32_t)kg & 7u) ^ sw) << 4)) = pk;
+    }
+    fence_proxy_async();   // generic-proxy smem writes -> visible to tcgen05.mma (async proxy)
+    mbar_arrive(&a_full);
+
+    // ---- epilogue: one accumulator row per thread -> bias -> activation -> one contiguous line
+    mbar_wait(&tmem_full, 0);
+    tc_fence_after();
+    __half* yrow = p.y + m * COUT;
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      if (!valid) continue;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = c0 + q * 8 + 2 * j;
+          float v0 = __uint_as_float(r[q * 8 + 2 * j]) + (p.bias ? __ldg(p.bias + col) : 0.f);
+          float v1 = __uint_as_float(r[q * 8 + 2 * j + 1]) + (p.bias ? __ldg(p.bias + col + 1) : 0.f);
+          o2[j] = __halves2half2(from_f32<__half>(apply_act(v0, p.act)), from_f32<__half>(apply_act(v1, p.act)));
+        }
+        reinterpret_cast<uint4*>(yrow + c0)[q] = o;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<COUT>(tmem_base);
+  }
+}
+
+template <int KS, int STRIDE, int PAD, int COUT>
+void launch_variant(const StemParams& prm, cudaStream_t stream) {
+  constexpr int K = 3 * KS * KS;
+  constexpr int ATOMS = (K + 63) / 64;
+  const size_t smem = (size_t)ATOMS * (ST_M * 128 + COUT * 128) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<KS, STRIDE, PAD, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    attr = true;
+  }
+  const unsigned grid = (unsigned)((prm.M + ST_M - 1) / ST_M);
+  stem_tc_kernel<KS, STRIDE, PAD, COUT><<<grid, ST_THREADS, smem, stream>>>(prm);
+}
+
+}  // namespace
+
+struct StemTcPlan {
+  StemParams prm;
+  int ks, stride, pad, cout;
+};
+
+bool stem_tc_supported(int ks, int stride, int pad, int cin, int cout) {
+  return cin == 3 && ((ks == 7 && stride == 2 && pad == 3 && cout == 64) || (ks == 3 && stride == 1 && pad == 1 && cout == 32));
+}
+
+int stem_tc_kpad(int ks) { return ((3 * ks * ks + 63) / 64) * 64; }
+
+StemTcPlan* stem_tc_plan_create(const float* x_nchw, const __half* w_packed, const float* bias, __half* y, int B, int H,
+                                int W, int ks, int stride, int pad, int cout, int act) {
+  YB_REQUIRE(stem_tc_supported(ks, stride, pad, 3, cout), "stem_tc: unsupported stem shape");
+  auto* plan = new StemTcPlan();
+  StemParams& q = plan->prm;
+  memset(&q, 0, sizeof(q));
+  plan->ks = ks;
+  plan->stride = stride;
+  plan->pad = pad;
+  plan->cout = cout;
+  q.x = x_nchw;
+  q.bias = bias;
+  q.y = y;
+  q.B = B;
+  q.H = H;
+  q.W = W;
+  q.Ho = (H + 2 * pad - ks) / stride + 1;
+  q.Wo = (W + 2 * pad - ks) / stride + 1;
+  q.M = (long long)B * q.Ho * q.Wo;
+  q.act = act;
+  q.idesc = (1u << 4) | ((uint32_t)(cout >> 3) << 17) | ((uint32_t)(ST_M >> 4) << 24);
+  const int kpad = stem_tc_kpad(ks);
+  uint64_t dims[3] = {(uint64_t)kpad, (uint64_t)cout, 1};
+  uint64_t str[2] = {(uint64_t)kpad * 2, (uint64_t)kpad * cout * 2};
+  uint32_t box[3] = {64, (uint32_t)cout, 1};
+  encode_map_f16(&q.tmW, w_packed, 3, dims, str, box);
+  return plan;
+}
+
+void stem_tc_plan_destroy(StemTcPlan* plan) { delete plan; }
+
+void launch_stem_tc(const StemTcPlan* plan, cudaStream_t stream, LaunchCounter* lc) {
+  if (plan->ks == 7)
+    launch_variant<7, 2, 3, 64>(plan->prm, stream);
+  else
+    launch_variant<3, 1, 1, 32>(plan->prm, stream);
+  YB_CHECK_LAUNCH();
+  if (lc) lc->n++;
+}
+
+}  // namespace yb

@@ -18,11 +18,12 @@
 // Pipeline: warp 0 = TMA producer, warp 1 = TMEM alloc + single-thread tcgen05.mma issue,
 //   warps 2..5 = epilogue (tcgen05.ld -> +bias -> +residual -> activation -> 16-byte stores).
 //   `stages`-deep mbarrier ring (full/empty), tcgen05.commit releases shared memory slots.
-#include <cuda.h>  // CUtensorMap + enums only; the encode entry point is fetched at run time
 #include <vector>
-#include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace yb {
+
+using namespace tc;
 
 namespace {
 
@@ -59,129 +60,6 @@ struct alignas(64) TcParams {
   int vec_ok;
   int res_after_act;
 };
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar);
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(addr),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* desc, uint64_t* bar, int c0,
-                                            int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* desc, uint64_t* bar, int c0,
-                                            int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const void* desc, const void* smem_src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(desc)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-template <int NCOLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
-               "n"(NCOLS)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int NCOLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::f16 (fp16 in, fp32 accumulate)
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// 32 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
-        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
-        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 = 1024>>4
-//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 
 // ---------------------------------------------------------------------------------------------
 // kernel
@@ -455,11 +333,16 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+}  // namespace
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                     CUtensorMapFloatOOBfill);
 
+namespace {
 PFN_encodeTiled get_encode_fn() {
   static PFN_encodeTiled fn = nullptr;
   if (fn) return fn;
@@ -471,7 +354,9 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-void encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+}  // namespace
+
+void tc::encode_map_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                 const uint32_t* box) {
   cuuint64_t gdim[5];
   cuuint64_t gstr[5];
@@ -496,9 +381,6 @@ void encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* di
     throw Error(YB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
 }
 
-int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
-
-}  // namespace
 
 struct TcConvPlan {
   TcParams prm;
@@ -561,6 +443,17 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   q.a_box_bytes = q.tw * q.th * BLOCK_K * 2;
   const long long m_tiles = (long long)q.tiles_x * q.tiles_y * Bv;
 
+  // ---- epilogue mode: fp16 NHWC outputs with 16-byte aligned rows go through smem + TMA store
+  const int esz = p.y_f32 ? 4 : 2;
+  const int vec_elems = 16 / esz;
+  bool vec_ok = (p.y_pix_stride % vec_elems == 0) && (p.y_batch_stride % vec_elems == 0) &&
+                ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+  if (p.residual) vec_ok = vec_ok && (p.Cout % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+  q.vec_ok = vec_ok ? 1 : 0;
+  q.epi_tma = (!p.y_f32 && vec_ok && p.Cout % 8 == 0) ? 1 : 0;
+  // the staged epilogue moves 64-channel boxes: a CTA must own at least 64 output channels
+  const int bn_min = q.epi_tma ? 64 : 32;
+
   // ---- N tile: minimise waves * (BN + fixed cost)
   {
     const int cands[4] = {256, 128, 64, 32};
@@ -568,7 +461,8 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
     int bn_best = 32;
     for (int i = 0; i < 4; ++i) {
       int bn = cands[i];
-      if (bn > 32 && bn >= 2 * p.Cout) continue;  // more than half the tile would be padding
+      if (bn < bn_min) continue;
+      if (bn > bn_min && bn >= 2 * p.Cout) continue;  // more than half the tile would be padding
       long long ctas = m_tiles * ceil_div(p.Cout, bn);
       long long waves = (ctas + 147) / 148;
       double cost = (double)waves * (bn + 64);
@@ -578,18 +472,11 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
       }
     }
     plan->BN = bn_best;
-    if (bn_override == 32 || bn_override == 64 || bn_override == 128 || bn_override == 256) plan->BN = bn_override;
+    if (bn_override == 32 || bn_override == 64 || bn_override == 128 || bn_override == 256)
+      plan->BN = std::max(bn_override, bn_min);
   }
   const int BN = plan->BN;
   const int stage_bytes = A_STAGE_BYTES + BN * BLOCK_K * 2;
-  // ---- epilogue mode: fp16 NHWC outputs with 16-byte aligned rows go through smem + TMA store
-  const int esz = p.y_f32 ? 4 : 2;
-  const int vec_elems = 16 / esz;
-  bool vec_ok = (p.y_pix_stride % vec_elems == 0) && (p.y_batch_stride % vec_elems == 0) &&
-                ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
-  if (p.residual) vec_ok = vec_ok && (p.Cout % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
-  q.vec_ok = vec_ok ? 1 : 0;
-  q.epi_tma = (!p.y_f32 && vec_ok && p.Cout % 8 == 0) ? 1 : 0;
   const int res_bytes = (q.epi_tma && p.residual) ? 2 * A_STAGE_BYTES : 0;
   int stages = std::min(MAX_STAGES, (200 * 1024 - res_bytes) / stage_bytes);
   if (stages_override > 0) stages = std::min(stages, stages_override);
@@ -611,7 +498,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
     uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)Wov, 1, 1};
     uint64_t str[3] = {(uint64_t)p.Cin * 2, (uint64_t)Wov * p.Cin * 2, (uint64_t)Wov * p.Cin * 2};
     uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)q.tw, (uint32_t)q.th, 1};
-    encode_map(&q.tmA[0], x, 4, dims, str, box);
+    encode_map_f16(&q.tmA[0], x, 4, dims, str, box);
     q.tap_map[0] = 0;
     q.tap_dx[0] = 0;
     q.tap_dy[0] = 0;
@@ -637,7 +524,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
         uint64_t str[3] = {(uint64_t)s * p.Cin * 2, (uint64_t)s * p.W * p.Cin * 2,
                            (uint64_t)p.H * p.W * p.Cin * 2};
         uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)q.tw, (uint32_t)q.th, 1};
-        encode_map(&q.tmA[py * s + px], base, 4, dims, str, box);
+        encode_map_f16(&q.tmA[py * s + px], base, 4, dims, str, box);
       }
   }
   // ---- B tensor map: [tap][Cout][Cin]
@@ -645,7 +532,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
     uint64_t dims[3] = {(uint64_t)p.Cin, (uint64_t)p.Cout, (uint64_t)q.ntaps};
     uint64_t str[2] = {(uint64_t)p.Cin * 2, (uint64_t)p.Cout * p.Cin * 2};
     uint32_t box[3] = {(uint32_t)BLOCK_K, (uint32_t)BN, 1};
-    encode_map(&q.tmB, w_packed, 3, dims, str, box);
+    encode_map_f16(&q.tmB, w_packed, 3, dims, str, box);
   }
   // ---- epilogue
   q.y = p.y;
@@ -668,18 +555,18 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
     if (flat) {
       uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)Wov, 1, 1};
       uint64_t ystr[3] = {(uint64_t)p.y_pix_stride * 2, (uint64_t)Wov * p.y_pix_stride * 2, (uint64_t)Wov * p.y_pix_stride * 2};
-      encode_map(&q.tmY, p.y, 4, dims, ystr, box);
+      encode_map_f16(&q.tmY, p.y, 4, dims, ystr, box);
       if (p.residual) {
         uint64_t rstr[3] = {(uint64_t)p.Cout * 2, (uint64_t)Wov * p.Cout * 2, (uint64_t)Wov * p.Cout * 2};
-        encode_map(&q.tmR, p.residual, 4, dims, rstr, box);
+        encode_map_f16(&q.tmR, p.residual, 4, dims, rstr, box);
       }
     } else {
       uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.B};
       uint64_t ystr[3] = {(uint64_t)p.y_pix_stride * 2, (uint64_t)p.Wo * p.y_pix_stride * 2, (uint64_t)p.y_batch_stride * 2};
-      encode_map(&q.tmY, p.y, 4, dims, ystr, box);
+      encode_map_f16(&q.tmY, p.y, 4, dims, ystr, box);
       if (p.residual) {
         uint64_t rstr[3] = {(uint64_t)p.Cout * 2, (uint64_t)p.Wo * p.Cout * 2, (uint64_t)p.Ho * p.Wo * p.Cout * 2};
-        encode_map(&q.tmR, p.residual, 4, dims, rstr, box);
+        encode_map_f16(&q.tmR, p.residual, 4, dims, rstr, box);
       }
     }
   }

@@ -295,6 +295,27 @@ class Yolact(nn.Module):
         lib = _lib.load()
         return sum(int(lib.yb_launch_count(h)) for h in self._handles.values())
 
+    def profile_conv_stack(self, x):
+        """Per-op device times (ms) of one eager conv-stack pass: [(layer name, ms)], CUDA events."""
+        x = self._check_input(x)
+        lib = _lib.load()
+        h = self._handle_for(x.device)
+        B, _, H, W = x.shape
+        st = _lib.current_stream(x.device)
+        _lib.check(lib.yb_forward(h, _lib.ptr(x), B, H, W, None, None, None, None, st), "yb_forward")
+        _lib.check(lib.yb_set_profiling(h, 1), "yb_set_profiling")
+        try:
+            _lib.check(lib.yb_forward(h, _lib.ptr(x), B, H, W, None, None, None, None, st), "yb_forward")
+        finally:
+            lib.yb_set_profiling(h, 0)
+        buf = ctypes.create_string_buffer(1 << 20)
+        _lib.check(lib.yb_last_forward_profile(h, buf, len(buf)), "yb_last_forward_profile")
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, ms = line.rsplit(",", 1)
+            out.append((name, float(ms)))
+        return out
+
     def num_priors_for(self, h, w, device=None):
         lib = _lib.load()
         n = ctypes.c_int64()
