@@ -7,6 +7,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
+#include <set>
 
 namespace yb {
 
@@ -240,7 +242,9 @@ struct NetBuilder {
       YB_REQUIRE(tc_conv_supported(p), ("conv " + key + ": not supported by the tensor-core kernel").c_str());
       TcConvPlan* plan = autotune_tc(p, w.w_tc);
       ex->plans.push_back(plan);
-      op.name += " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) + " st=" + std::to_string(tc_conv_plan_stages(plan));
+      op.name += " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) + " st=" + std::to_string(tc_conv_plan_stages(plan)) +
+                 " g=" + std::to_string(tc_conv_plan_grid(plan));
+      tc_conv_plan_set_pdl(plan, h->pdl ? 1 : 0);
       op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
     } else {
       int types;
@@ -369,53 +373,54 @@ struct NetBuilder {
                              std::to_string(p.stride) + "," + std::to_string(p.pad) + "," + (p.residual ? "r" : "-") +
                              (p.y_f32 ? "f" : "h") + std::to_string(p.y_pix_stride) + "," + std::to_string((long long)p.y_batch_stride);
     auto it = h->tune_cache.find(tkey);
-    if (it != h->tune_cache.end()) return tc_conv_plan_create(p, w, it->second.first, it->second.second);
+    if (it != h->tune_cache.end()) return tc_conv_plan_create(p, w, it->second[0], it->second[1], it->second[2]);
     const int bns[4] = {256, 128, 64, 32};
     const int sts[3] = {0, 3, 2};
+    const int grids[3] = {148, 296, 1 << 30};
     TcConvPlan* best = nullptr;
     float best_ms = 1e30f;
+    std::set<std::string> seen;
     cudaEvent_t e0, e1;
     YB_CHECK_CUDA(cudaEventCreate(&e0));
     YB_CHECK_CUDA(cudaEventCreate(&e1));
-    for (int bi = 0; bi < 4; ++bi) {
-      const int bn = bns[bi];
-      if (bn > 32 && bn >= 2 * p.Cout) continue;
-      int last_stages = -1;
-      for (int si = 0; si < 3; ++si) {
-        TcConvPlan* cand = tc_conv_plan_create(p, w, bn, sts[si]);
-        if (tc_conv_plan_bn(cand) != bn || tc_conv_plan_stages(cand) == last_stages) {  // override had no effect
-          tc_conv_plan_destroy(cand);
-          continue;
+    for (int bi = 0; bi < 4; ++bi)
+      for (int si = 0; si < 3; ++si)
+        for (int gi = 0; gi < 3; ++gi) {
+          if (bns[bi] > 64 && bns[bi] >= 2 * p.Cout) continue;
+          TcConvPlan* cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi]);
+          const std::string ck = std::to_string(tc_conv_plan_bn(cand)) + "/" + std::to_string(tc_conv_plan_stages(cand)) +
+                                 "/" + std::to_string(tc_conv_plan_grid(cand));
+          if (!seen.insert(ck).second) {  // overrides were clamped to an already-timed configuration
+            tc_conv_plan_destroy(cand);
+            continue;
+          }
+          float ms = 1e30f;
+          try {
+            for (int i = 0; i < 3; ++i) launch_tc_conv(cand, 0, nullptr);
+            YB_CHECK_CUDA(cudaEventRecord(e0, 0));
+            for (int i = 0; i < 10; ++i) launch_tc_conv(cand, 0, nullptr);
+            YB_CHECK_CUDA(cudaEventRecord(e1, 0));
+            YB_CHECK_CUDA(cudaEventSynchronize(e1));
+            YB_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+          } catch (...) {
+            tc_conv_plan_destroy(cand);
+            if (best) tc_conv_plan_destroy(best);
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            throw;
+          }
+          if (ms < best_ms) {
+            if (best) tc_conv_plan_destroy(best);
+            best = cand;
+            best_ms = ms;
+          } else {
+            tc_conv_plan_destroy(cand);
+          }
         }
-        last_stages = tc_conv_plan_stages(cand);
-        float ms = 1e30f;
-        try {
-          for (int i = 0; i < 3; ++i) launch_tc_conv(cand, 0, nullptr);
-          YB_CHECK_CUDA(cudaEventRecord(e0, 0));
-          for (int i = 0; i < 10; ++i) launch_tc_conv(cand, 0, nullptr);
-          YB_CHECK_CUDA(cudaEventRecord(e1, 0));
-          YB_CHECK_CUDA(cudaEventSynchronize(e1));
-          YB_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        } catch (...) {
-          tc_conv_plan_destroy(cand);
-          if (best) tc_conv_plan_destroy(best);
-          cudaEventDestroy(e0);
-          cudaEventDestroy(e1);
-          throw;
-        }
-        if (ms < best_ms) {
-          if (best) tc_conv_plan_destroy(best);
-          best = cand;
-          best_ms = ms;
-        } else {
-          tc_conv_plan_destroy(cand);
-        }
-      }
-    }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     YB_REQUIRE(best != nullptr, "autotune: no candidate");
-    h->tune_cache[tkey] = std::make_pair(tc_conv_plan_bn(best), tc_conv_plan_stages(best));
+    h->tune_cache[tkey] = {tc_conv_plan_bn(best), tc_conv_plan_stages(best), tc_conv_plan_grid(best)};
     return best;
   }
 };

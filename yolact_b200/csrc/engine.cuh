@@ -1,6 +1,7 @@
 // Host-side engine: weight store (reference state_dict names), BatchNorm folding + repacking,
 // per-input-shape executors (activation buffers, kernel plans, CUDA graph), Detect workspaces.
 #pragma once
+#include <array>
 #include <functional>
 #include <map>
 #include <memory>
@@ -88,6 +89,7 @@ struct yb_handle {
   bool finalized = false;
   bool use_graphs = true;
   bool profiling = false;
+  bool pdl = false;         // YB_PDL=1: programmatic dependent launch between consecutive tcgen05 convs
   bool stem_on_tc = true;   // YB_STEM_TC=0 falls back to the SIMT stem
   bool autotune = true;     // YB_AUTOTUNE=0 disables plan-time autotuning of the tcgen05 tiles
   float last_total_ms = 0.f, last_conv_ms = 0.f;
@@ -96,7 +98,7 @@ struct yb_handle {
   std::map<std::string, yb::ConvW> convs;
   std::map<std::string, std::unique_ptr<yb::Executor>> execs;
   std::vector<void*> weight_allocs;
-  std::map<std::string, std::pair<int, int>> tune_cache;  // layer shape -> (BN, stages) picked by the autotuner
+  std::map<std::string, std::array<int, 3>> tune_cache;  // layer shape -> (BN, stages, grid) picked by the autotuner
   yb::Executor* last_exec = nullptr;
   // standalone op workspaces
   void* detect_ws = nullptr;

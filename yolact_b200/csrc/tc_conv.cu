@@ -41,7 +41,12 @@ struct alignas(64) TcParams {
   CUtensorMap tmY;      // output tile store  (epi_tma)
   CUtensorMap tmR;      // residual tile load (epi_tma && residual)
   int epi_tma;          // 1: fp16 NHWC output goes smem -> TMA store, residual comes in by TMA
+  int out_off;          // byte offset of the 2 x 16 KB epilogue staging tiles inside dynamic smem
   int res_off;          // byte offset of the residual staging buffers inside dynamic smem
+  int m_tiles, n_tiles; // tile = m_tile * n_tiles + n_tile
+  int acc_stages;       // TMEM accumulator buffers (2 when a CTA processes several tiles)
+  int tmem_cols;        // power of two >= acc_stages * BN
+  int pdl;              // launched with programmatic stream serialization
   int ntaps, kchunks, stages;
   int tap_map[MAX_TAPS], tap_dx[MAX_TAPS], tap_dy[MAX_TAPS];
   int tw, th, tiles_x, tiles_y;
@@ -64,6 +69,39 @@ struct alignas(64) TcParams {
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
+// Persistent: CTA c processes tiles c, c + gridDim.x, ...  (tile = m_tile * n_tiles + n_tile).
+// Three concurrent pipelines: smem ring (TMA producer <-> MMA), TMEM accumulator ring of
+// `acc_stages` buffers (MMA <-> epilogue), and the epilogue's own double-buffered staging tiles,
+// so the loads of tile i+1, the MMAs of tile i and the stores of tile i-1 overlap.
+__device__ __forceinline__ void tmem_alloc_dyn(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_dyn(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TileCoord {
+  int b, x0, y0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, int BN) {
+  TileCoord t;
+  const int nt = tile % p.n_tiles;
+  int m = tile / p.n_tiles;
+  const int tx = m % p.tiles_x;
+  m /= p.tiles_x;
+  const int ty = m % p.tiles_y;
+  t.b = m / p.tiles_y;
+  t.x0 = tx * p.tw;
+  t.y0 = ty * p.th;
+  t.n0 = nt * BN;
+  return t;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS)
 tc_conv_kernel(const __grid_constant__ TcParams p) {
@@ -73,260 +111,256 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_dyn[];
   __shared__ uint64_t full_bar[MAX_STAGES];
   __shared__ uint64_t empty_bar[MAX_STAGES];
-  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint64_t res_full_bar[2];
   __shared__ uint32_t s_tmem_base;
 
   // 1024-byte alignment required by SWIZZLE_128B (host adds 1024 bytes of slack)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint8_t* out_base = smem + p.out_off;   // 2 x 16 KB epilogue staging tiles
+  uint8_t* res_base = smem + p.res_off;   // 2 x 16 KB residual tiles (only when residual && epi_tma)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
   const int num_kb = p.ntaps * p.kchunks;
-
-  // tile coordinates
-  int t = blockIdx.x;
-  const int tx = t % p.tiles_x;
-  t /= p.tiles_x;
-  const int ty = t % p.tiles_y;
-  const int b = t / p.tiles_y;
-  const int x0 = tx * p.tw, y0 = ty * p.th;
-  const int n0 = blockIdx.y * BN;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int acc_stages = p.acc_stages;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
-    mbar_init(&res_full_bar[0], 1);
-    mbar_init(&res_full_bar[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 1);
+      mbar_init(&res_full_bar[i], 1);
+    }
     fence_barrier_init();
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmA[0]);
     if (p.epi_tma) tma_prefetch_desc(&p.tmY);
   }
-  if (warp == 1) tmem_alloc<BN>(&s_tmem_base);
+  if (warp == 1) tmem_alloc_dyn(&s_tmem_base, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  // Programmatic dependent launch: everything above overlaps the tail of the previous kernel in the
+  // stream; its output is only touched below this point.
+  if (p.pdl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)p.a_box_bytes + (uint32_t)B_STAGE_BYTES;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t it = (uint32_t)(kb / stages);
-        mbar_wait(&empty_bar[s], (it & 1u) ^ 1u);
-        const int tap = kb / p.kchunks;
-        const int kc = kb - tap * p.kchunks;
-        uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
-        uint8_t* sb = sa + A_STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], tx_bytes);
-        tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[s], kc * BLOCK_K, x0 + p.tap_dx[tap],
-                    y0 + p.tap_dy[tap], b);
-        tma_load_3d(sb, &p.tmB, &full_bar[s], kc * BLOCK_K, n0, tap);
+      uint32_t kbg = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord tc_ = decode_tile(p, tile, BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const uint32_t s = kbg % (uint32_t)stages;
+          const uint32_t it = kbg / (uint32_t)stages;
+          mbar_wait(&empty_bar[s], (it & 1u) ^ 1u);
+          const int tap = kb / p.kchunks;
+          const int kc = kb - tap * p.kchunks;
+          uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], tx_bytes);
+          tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[s], kc * BLOCK_K, tc_.x0 + p.tap_dx[tap],
+                      tc_.y0 + p.tap_dy[tap], tc_.b);
+          tma_load_3d(sb, &p.tmB, &full_bar[s], kc * BLOCK_K, tc_.n0, tap);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t it = (uint32_t)(kb / stages);
-        mbar_wait(&full_bar[s], it & 1u);
+      uint32_t kbg = 0, t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const uint32_t acc = t % (uint32_t)acc_stages;
+        const uint32_t use = t / (uint32_t)acc_stages;
+        mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        const uint32_t sb = sa + A_STAGE_BYTES;
-        const uint64_t da = make_sw128_desc(sa);
-        const uint64_t db = make_sw128_desc(sb);
+        const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const uint32_t s = kbg % (uint32_t)stages;
+          const uint32_t it = kbg / (uint32_t)stages;
+          mbar_wait(&full_bar[s], it & 1u);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint64_t da = make_sw128_desc(sa);
+          const uint64_t db = make_sw128_desc(sb);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 field
-          umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc,
-                   (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 field
+            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees this smem slot once the MMAs above have read it
         }
-        umma_commit(&empty_bar[s]);  // frees this smem slot once the MMAs above have read it
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       }
-      umma_commit(&tmem_full_bar);   // accumulator complete
     }
   } else {
     // ===================== epilogue (warps 2..5 -> TMEM lane quadrant warp%4) =====================
     const int quad = warp & 3;
     const int row = quad * 32 + lane;  // accumulator row == tile-local output pixel
     const int ly = row / p.tw, lx = row - ly * p.tw;
-    const int oy = y0 + ly, ox = x0 + lx;
-    const bool row_ok = (row < p.tw * p.th) && (oy < p.Ho) && (ox < p.Wo);
-    const long long pix = (long long)oy * p.Wo + ox;
-    if (p.epi_tma) {
-      // ---- staged epilogue: TMEM -> regs -> (+bias, +residual from smem, act) -> swizzled smem tile
-      //      -> one TMA store per 64-channel chunk (full 128-byte lines, OOB rows clipped by hardware)
-      const bool issuer = (warp == 2 && lane == 0);
-      const bool has_res = (p.residual != nullptr);
-      const int ncols = min(BN, p.Cout - n0);
-      const int nchunks = (ncols + 63) >> 6;
-      uint8_t* out_base = smem;                 // aliases the pipeline buffers: free once tmem_full fires
-      uint8_t* res_base = smem + p.res_off;     // dedicated, so the first two chunks prefetch during the mainloop
-      if (issuer && has_res) {
-        for (int c = 0; c < min(nchunks, 2); ++c) {
-          mbar_expect_tx(&res_full_bar[c], (uint32_t)p.a_box_bytes);
-          tma_load_4d(res_base + c * A_STAGE_BYTES, &p.tmR, &res_full_bar[c], n0 + c * 64, x0, y0, b);
-        }
+    const bool issuer = (warp == 2 && lane == 0);
+    const bool has_res = (p.residual != nullptr);
+    const uint32_t sw = (uint32_t)(row & 7);
+    const int nchunks_full = (min(BN, p.Cout) + 63) >> 6;
+
+    // residual chunk stream (epi_tma only): global chunk g lives in res buffer g&1; the issuer keeps it
+    // two chunks ahead of the consumer, across tile boundaries.  (pf_tile, pf_c) = next chunk to fetch.
+    int pf_tile = blockIdx.x, pf_c = 0;
+    uint32_t pf_g = 0;
+    auto prefetch_res = [&]() {
+      if (pf_tile >= num_tiles) return;
+      const TileCoord tcp = decode_tile(p, pf_tile, BN);
+      const int nch = (min(BN, p.Cout - tcp.n0) + 63) >> 6;
+      const uint32_t buf = pf_g & 1u;
+      mbar_expect_tx(&res_full_bar[buf], (uint32_t)p.a_box_bytes);
+      tma_load_4d(res_base + buf * A_STAGE_BYTES, &p.tmR, &res_full_bar[buf], tcp.n0 + pf_c * 64, tcp.x0, tcp.y0, tcp.b);
+      ++pf_g;
+      if (++pf_c >= nch) {
+        pf_c = 0;
+        pf_tile += gridDim.x;
       }
-      mbar_wait(&tmem_full_bar, 0);
+    };
+    if (p.epi_tma && has_res && issuer) {
+      prefetch_res();
+      prefetch_res();
+    }
+
+    uint32_t t = 0, g = 0;  // local tile counter, global staged-chunk counter
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const TileCoord tc_ = decode_tile(p, tile, BN);
+      const int x0 = tc_.x0, y0 = tc_.y0, b = tc_.b, n0 = tc_.n0;
+      const uint32_t acc = t % (uint32_t)acc_stages;
+      const uint32_t use = t / (uint32_t)acc_stages;
+      const uint32_t tmem_acc = tmem_base + acc * (uint32_t)BN + ((uint32_t)(quad * 32) << 16);
+      mbar_wait(&tmem_full_bar[acc], use & 1u);
       tc_fence_after();
-      const uint32_t sw = (uint32_t)(row & 7);
+
+      if (p.epi_tma) {
+        // ---- staged epilogue: TMEM -> regs -> (+bias, +residual from smem, act) -> swizzled smem tile
+        //      -> one TMA store per 64-channel chunk (full 128-byte lines, OOB rows clipped by hardware)
+        const int nchunks = (min(BN, p.Cout - n0) + 63) >> 6;
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
-        const int buf = c & 1;
-        uint8_t* out_tile = out_base + buf * A_STAGE_BYTES;
-        uint8_t* res_tile = res_base + buf * A_STAGE_BYTES;
-        if (c >= 2) {
-          if (issuer) bulk_wait_read<1>();  // the store that used this buffer two chunks ago has read it
-          epi_bar_sync();
-        }
-        uint32_t r0[32], r1[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 64), r0);
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 64 + 32), r1);
-        if (has_res) mbar_wait(&res_full_bar[buf], (uint32_t)((c >> 1) & 1));
-        const int nbase = n0 + c * 64;
-#pragma unroll
-        for (int j8 = 0; j8 < 8; ++j8) {   // 8 channels (16 bytes) at a time
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = j8 * 8 + j;
-            v[j] = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]);
-            if (p.bias && nbase + col < p.Cout) v[j] += __ldg(p.bias + nbase + col);
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          const uint32_t buf = g & 1u;
+          uint8_t* out_tile = out_base + buf * A_STAGE_BYTES;
+          uint8_t* res_tile = res_base + buf * A_STAGE_BYTES;
+          if (g >= 2) {
+            if (issuer) bulk_wait_read<1>();  // the store that used this buffer two chunks ago has read it
+            epi_bar_sync();
           }
-          if (p.res_after_act) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(tmem_acc + (uint32_t)(c * 64), r0);
+          tmem_ld32(tmem_acc + (uint32_t)(c * 64 + 32), r1);
+          if (has_res) mbar_wait(&res_full_bar[buf], (g >> 1) & 1u);
+          const int nbase = n0 + c * 64;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act);
-          }
-          const uint32_t off = (uint32_t)row * 128u + (((uint32_t)j8 ^ sw) << 4);
-          if (has_res) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(res_tile + off);
-            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+          for (int j8 = 0; j8 < 8; ++j8) {   // 8 channels (16 bytes) at a time
+            float v[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __half22float2(h2[j]);
-              v[2 * j] += f.x;
-              v[2 * j + 1] += f.y;
+            for (int j = 0; j < 8; ++j) {
+              const int col = j8 * 8 + j;
+              v[j] = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]);
+              if (p.bias && nbase + col < p.Cout) v[j] += __ldg(p.bias + nbase + col);
             }
-          }
-          if (!p.res_after_act) {
+            if (p.res_after_act) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act);
-          }
-          uint4 o;
-          __half2* o2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o2[j] = __halves2half2(from_f32<__half>(v[2 * j]), from_f32<__half>(v[2 * j + 1]));
-          *reinterpret_cast<uint4*>(out_tile + off) = o;
-        }
-        fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-        epi_bar_sync();
-        if (issuer) {
-          tma_store_4d(&p.tmY, out_tile, nbase, x0, y0, b);
-          bulk_commit();
-          if (has_res && c + 2 < nchunks) {   // everyone is done reading res_tile[buf]: refill it
-            mbar_expect_tx(&res_full_bar[buf], (uint32_t)p.a_box_bytes);
-            tma_load_4d(res_tile, &p.tmR, &res_full_bar[buf], n0 + (c + 2) * 64, x0, y0, b);
-          }
-        }
-      }
-      if (issuer) bulk_wait_read<0>();  // smem must outlive the bulk reads
-    } else {
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
-
-    float* yf = reinterpret_cast<float*>(p.y) + (long long)b * p.y_batch_stride + pix * p.y_pix_stride;
-    __half* yh = reinterpret_cast<__half*>(p.y) + (long long)b * p.y_batch_stride + pix * p.y_pix_stride;
-    const __half* res = p.residual ? p.residual + (long long)b * p.res_batch_stride + pix * p.Cout : nullptr;
-
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= p.Cout) break;  // warp-uniform
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
-      if (!row_ok) continue;
-      const int nbase = n0 + c0;
-      const int nvalid = min(32, p.Cout - nbase);
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nvalid) v[j] += __ldg(p.bias + nbase + j);
-      }
-      if (p.res_after_act) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-      }
-      if (res) {
-        if (p.vec_ok && nvalid == 32) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 raw = __ldg(reinterpret_cast<const uint4*>(res + nbase) + q);
-            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 f = __half22float2(h2[j]);
-              v[q * 8 + 2 * j] += f.x;
-              v[q * 8 + 2 * j + 1] += f.y;
+              for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act);
             }
-          }
-        } else {
+            const uint32_t off = (uint32_t)row * 128u + (((uint32_t)j8 ^ sw) << 4);
+            if (has_res) {
+              const uint4 raw = *reinterpret_cast<const uint4*>(res_tile + off);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) v[j] += __half2float(res[nbase + j]);
-        }
-      }
-      if (!p.res_after_act) {
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h2[j]);
+                v[2 * j] += f.x;
+                v[2 * j + 1] += f.y;
+              }
+            }
+            if (!p.res_after_act) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-      }
-
-      if (p.y_f32) {
-        if (p.vec_ok && nvalid == 32) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            reinterpret_cast<float4*>(yf + nbase)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) yf[nbase + j] = v[j];
-        }
-      } else {
-        if (p.vec_ok && nvalid == 32) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
+              for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act);
+            }
             uint4 o;
             __half2* o2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o2[j] = __halves2half2(from_f32<__half>(v[q * 8 + 2 * j]), from_f32<__half>(v[q * 8 + 2 * j + 1]));
-            reinterpret_cast<uint4*>(yh + nbase)[q] = o;
+            for (int j = 0; j < 4; ++j) o2[j] = __halves2half2(from_f32<__half>(v[2 * j]), from_f32<__half>(v[2 * j + 1]));
+            *reinterpret_cast<uint4*>(out_tile + off) = o;
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) yh[nbase + j] = from_f32<__half>(v[j]);
+          fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+          if (c == nchunks - 1) tc_fence_before();
+          epi_bar_sync();
+          if (issuer) {
+            if (c == nchunks - 1) mbar_arrive(&tmem_empty_bar[acc]);  // all 128 threads have read their rows
+            tma_store_4d(&p.tmY, out_tile, nbase, x0, y0, b);
+            bulk_commit();
+            if (has_res) prefetch_res();   // everyone is done reading res_tile[buf]: refill it two chunks ahead
+          }
         }
+      } else {
+        // ---- direct epilogue (fp32 / unaligned outputs: the head tensors): each warp transposes its
+        //      32 rows x 32 columns through shared memory so that a store instruction writes 32
+        //      consecutive channels of ONE pixel (coalesced), not one channel of 32 pixels.
+        float* tbuf = reinterpret_cast<float*>(out_base) + quad * (32 * 33);
+        const int ncols = min(BN, p.Cout - n0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_acc + (uint32_t)c0, r);
+          const int nbase = n0 + c0;
+          const int nvalid = min(32, p.Cout - nbase);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+          __syncwarp();
+          const float bias_l = (p.bias && lane < nvalid) ? __ldg(p.bias + nbase + lane) : 0.f;
+          for (int rr = 0; rr < 32; ++rr) {
+            const int trow = quad * 32 + rr;
+            const int ty_ = trow / p.tw, tx_ = trow - ty_ * p.tw;
+            const int oy = y0 + ty_, ox = x0 + tx_;
+            if (trow >= p.tw * p.th || oy >= p.Ho || ox >= p.Wo) continue;   // warp-uniform
+            if (lane >= nvalid) continue;
+            const long long pix = (long long)oy * p.Wo + ox;
+            float v = tbuf[rr * 33 + lane] + bias_l;
+            if (p.res_after_act) v = apply_act(v, p.act);
+            if (has_res) v += __half2float(p.residual[(long long)b * p.res_batch_stride + pix * p.Cout + nbase + lane]);
+            if (!p.res_after_act) v = apply_act(v, p.act);
+            const long long o = (long long)b * p.y_batch_stride + pix * p.y_pix_stride + nbase + lane;
+            if (p.y_f32)
+              reinterpret_cast<float*>(p.y)[o] = v;
+            else
+              reinterpret_cast<__half*>(p.y)[o] = from_f32<__half>(v);
+          }
+        }
+        tc_fence_before();
+        epi_bar_sync();
+        if (issuer) mbar_arrive(&tmem_empty_bar[acc]);
       }
     }
-    }  // direct-store epilogue
+    if (p.epi_tma && issuer) bulk_wait_read<0>();  // smem must outlive the bulk reads
+    (void)nchunks_full;
+    (void)ly;
+    (void)lx;
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_base);
+    tmem_dealloc_dyn(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -398,7 +432,8 @@ bool tc_conv_supported(const ConvProblem& p) {
   return true;
 }
 
-TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override, int stages_override) {
+TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override, int stages_override,
+                                int grid_override) {
   YB_REQUIRE(tc_conv_supported(p), "tc_conv: unsupported problem");
   YB_REQUIRE(p.Ho == (p.H + 2 * p.pad - p.KH) / p.stride + 1, "tc_conv: bad Ho");
   YB_REQUIRE(p.Wo == (p.W + 2 * p.pad - p.KW) / p.stride + 1, "tc_conv: bad Wo");
@@ -477,16 +512,26 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   }
   const int BN = plan->BN;
   const int stage_bytes = A_STAGE_BYTES + BN * BLOCK_K * 2;
+  // ---- persistent grid + shared-memory layout: [pipeline stages][2 x 16 KB out tiles][2 x 16 KB residual tiles]
+  q.m_tiles = (int)m_tiles;
+  q.n_tiles = ceil_div(p.Cout, BN);
+  const int num_tiles = q.m_tiles * q.n_tiles;
+  int grid = std::min(num_tiles, grid_override > 0 ? grid_override : 148);
+  q.acc_stages = (grid < num_tiles) ? 2 : 1;
+  int tmem_cols = 32;
+  while (tmem_cols < q.acc_stages * BN) tmem_cols *= 2;
+  q.tmem_cols = tmem_cols;
+  const int tiles_per_cta = ceil_div(num_tiles, grid);
+  const int out_bytes = 2 * A_STAGE_BYTES;
   const int res_bytes = (q.epi_tma && p.residual) ? 2 * A_STAGE_BYTES : 0;
-  int stages = std::min(MAX_STAGES, (200 * 1024 - res_bytes) / stage_bytes);
+  int stages = std::min(MAX_STAGES, (200 * 1024 - out_bytes - res_bytes) / stage_bytes);
   if (stages_override > 0) stages = std::min(stages, stages_override);
-  stages = std::max(1, std::min(stages, q.ntaps * q.kchunks));
+  stages = std::max(1, std::min(stages, q.ntaps * q.kchunks * tiles_per_cta));
   q.stages = stages;
-  size_t pipe_bytes = (size_t)stages * stage_bytes;
-  if (q.epi_tma) pipe_bytes = std::max(pipe_bytes, (size_t)2 * A_STAGE_BYTES);  // two output staging tiles alias it
-  q.res_off = (int)pipe_bytes;
-  plan->smem_bytes = pipe_bytes + res_bytes + 1024;
-  plan->grid = dim3((unsigned)m_tiles, (unsigned)ceil_div(p.Cout, BN));
+  q.out_off = stages * stage_bytes;
+  q.res_off = q.out_off + out_bytes;
+  plan->smem_bytes = (size_t)q.res_off + res_bytes + 1024;
+  plan->grid = dim3((unsigned)grid, 1, 1);
 
   // ---- instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major, N, M=128
   q.idesc = (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) |
@@ -574,8 +619,10 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
 }
 
 void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
+void tc_conv_plan_set_pdl(TcConvPlan* plan, int enable) { plan->prm.pdl = enable ? 1 : 0; }
 int tc_conv_plan_bn(const TcConvPlan* plan) { return plan->BN; }
 int tc_conv_plan_stages(const TcConvPlan* plan) { return plan->prm.stages; }
+int tc_conv_plan_grid(const TcConvPlan* plan) { return (int)plan->grid.x; }
 
 template <int BN>
 static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
@@ -587,7 +634,21 @@ static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
     attr_set = true;
     attr_bytes = 220 * 1024;
   }
-  tc_conv_kernel<BN><<<plan->grid, NUM_THREADS, plan->smem_bytes, stream>>>(plan->prm);
+  if (plan->prm.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = plan->grid;
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = plan->smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN>, plan->prm));
+  } else {
+    tc_conv_kernel<BN><<<plan->grid, NUM_THREADS, plan->smem_bytes, stream>>>(plan->prm);
+  }
 }
 
 void launch_tc_conv(const TcConvPlan* plan, cudaStream_t stream, LaunchCounter* lc) {
