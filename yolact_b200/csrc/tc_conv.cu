@@ -85,6 +85,76 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+
+// activation with a compile-time selector (the generic apply_act() is a runtime switch: far too
+// expensive inside the 64-element epilogue loops)
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+  if (ACT == ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == ACT_LEAKY) return v > 0.f ? v : 0.1f * v;
+  if (ACT == ACT_TANH) return tanhf(v);
+  return v;
+}
+__device__ __forceinline__ __half2 pack_sat(float a, float b) {
+  // saturate to the fp16 range instead of producing inf
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  return __floats2half2_rn(a, b);
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// One 64-channel chunk of one accumulator row: +bias (smem, broadcast), +residual (swizzled smem tile),
+// activation, fp16 pack, swizzled 16-byte stores into the output staging tile.
+template <int ACT, bool RES_AFTER>
+__device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1, const float* sbias,
+                                          const uint8_t* res_tile, uint8_t* out_tile, uint32_t row, uint32_t sw) {
+#pragma unroll
+  for (int j8 = 0; j8 < 8; ++j8) {
+    const float4 b0 = *reinterpret_cast<const float4*>(sbias + j8 * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(sbias + j8 * 8 + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = j8 * 8 + j;
+      v[j] = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + bb[j];
+      if (RES_AFTER) v[j] = act_t<ACT>(v[j]);
+    }
+    const uint32_t off = row * 128u + (((uint32_t)j8 ^ sw) << 4);
+    if (res_tile) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(res_tile + off);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        v[2 * j] += f.x;
+        v[2 * j + 1] += f.y;
+      }
+    }
+    if (!RES_AFTER) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = act_t<ACT>(v[j]);
+    }
+    uint4 o;
+    __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o2[j] = pack_sat(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(out_tile + off) = o;
+  }
+}
+
 struct TileCoord {
   int b, x0, y0, n0;
 };
@@ -115,6 +185,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint64_t res_full_bar[2];
   __shared__ uint32_t s_tmem_base;
+  __shared__ __align__(16) float sbias[BN];
 
   // 1024-byte alignment required by SWIZZLE_128B (host adds 1024 bytes of slack)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -245,8 +316,14 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       const uint32_t acc = t % (uint32_t)acc_stages;
       const uint32_t use = t / (uint32_t)acc_stages;
       const uint32_t tmem_acc = tmem_base + acc * (uint32_t)BN + ((uint32_t)(quad * 32) << 16);
+      // bias of this tile's BN output channels -> shared memory (read back as broadcast float4)
+      {
+        const int et = threadIdx.x - 64;   // 0..127 within the epilogue warps
+        for (int j = et; j < BN; j += 128) sbias[j] = (p.bias && n0 + j < p.Cout) ? __ldg(p.bias + n0 + j) : 0.f;
+      }
       mbar_wait(&tmem_full_bar[acc], use & 1u);
       tc_fence_after();
+      epi_bar_sync();   // sbias visible; also: the previous tile's readers of sbias are long done
 
       if (p.epi_tma) {
         // ---- staged epilogue: TMEM -> regs -> (+bias, +residual from smem, act) -> swizzled smem tile
@@ -262,43 +339,23 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             epi_bar_sync();
           }
           uint32_t r0[32], r1[32];
-          tmem_ld32(tmem_acc + (uint32_t)(c * 64), r0);
-          tmem_ld32(tmem_acc + (uint32_t)(c * 64 + 32), r1);
+          tmem_ld32_nowait(tmem_acc + (uint32_t)(c * 64), r0);
+          tmem_ld32_nowait(tmem_acc + (uint32_t)(c * 64 + 32), r1);
+          tmem_ld_wait();
           if (has_res) mbar_wait(&res_full_bar[buf], (g >> 1) & 1u);
           const int nbase = n0 + c * 64;
-#pragma unroll
-          for (int j8 = 0; j8 < 8; ++j8) {   // 8 channels (16 bytes) at a time
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int col = j8 * 8 + j;
-              v[j] = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]);
-              if (p.bias && nbase + col < p.Cout) v[j] += __ldg(p.bias + nbase + col);
-            }
-            if (p.res_after_act) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act);
-            }
-            const uint32_t off = (uint32_t)row * 128u + (((uint32_t)j8 ^ sw) << 4);
-            if (has_res) {
-              const uint4 raw = *reinterpret_cast<const uint4*>(res_tile + off);
-              const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h2[j]);
-                v[2 * j] += f.x;
-                v[2 * j + 1] += f.y;
-              }
-            }
-            if (!p.res_after_act) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act);
-            }
-            uint4 o;
-            __half2* o2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o2[j] = __halves2half2(from_f32<__half>(v[2 * j]), from_f32<__half>(v[2 * j + 1]));
-            *reinterpret_cast<uint4*>(out_tile + off) = o;
+          const float* sb = sbias + c * 64;
+          const uint8_t* rt = has_res ? res_tile : nullptr;
+          switch (p.act) {
+            case ACT_RELU: epi_chunk<ACT_RELU, false>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw); break;
+            case ACT_LEAKY:
+              if (p.res_after_act)
+                epi_chunk<ACT_LEAKY, true>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw);
+              else
+                epi_chunk<ACT_LEAKY, false>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw);
+              break;
+            case ACT_TANH: epi_chunk<ACT_TANH, false>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw); break;
+            default: epi_chunk<ACT_NONE, false>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw); break;
           }
           fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
           if (c == nchunks - 1) tc_fence_before();
@@ -326,7 +383,8 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
           __syncwarp();
-          const float bias_l = (p.bias && lane < nvalid) ? __ldg(p.bias + nbase + lane) : 0.f;
+          const float bias_l = sbias[c0 + lane];
+          const int act = p.act, raa = p.res_after_act;
           for (int rr = 0; rr < 32; ++rr) {
             const int trow = quad * 32 + rr;
             const int ty_ = trow / p.tw, tx_ = trow - ty_ * p.tw;
@@ -335,9 +393,10 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             if (lane >= nvalid) continue;
             const long long pix = (long long)oy * p.Wo + ox;
             float v = tbuf[rr * 33 + lane] + bias_l;
-            if (p.res_after_act) v = apply_act(v, p.act);
-            if (has_res) v += __half2float(p.residual[(long long)b * p.res_batch_stride + pix * p.Cout + nbase + lane]);
-            if (!p.res_after_act) v = apply_act(v, p.act);
+            const float rsd = has_res ? __half2float(p.residual[(long long)b * p.res_batch_stride + pix * p.Cout + nbase + lane]) : 0.f;
+            if (!raa) v += rsd;
+            v = (act == ACT_RELU) ? fmaxf(v, 0.f) : (act == ACT_TANH) ? tanhf(v) : (act == ACT_LEAKY) ? (v > 0.f ? v : 0.1f * v) : v;
+            if (raa) v += rsd;
             const long long o = (long long)b * p.y_batch_stride + pix * p.y_pix_stride + nbase + lane;
             if (p.y_f32)
               reinterpret_cast<float*>(p.y)[o] = v;
