@@ -128,6 +128,7 @@ int yb_create(const yb_config* cfg, int device, yb_handle** out) {
   if (const char* at = getenv("YB_AUTOTUNE")) h->autotune = (atoi(at) != 0);
   if (const char* st = getenv("YB_STEM_TC")) h->stem_on_tc = (atoi(st) != 0);
   if (const char* pd = getenv("YB_PDL")) h->pdl = (atoi(pd) != 0);
+  if (const char* fh = getenv("YB_FUSE_HEADS")) h->fuse_heads = (atoi(fh) != 0);
   if (!h->ops_only) {
     YB_REQUIRE(cfg->backbone == YB_BACKBONE_RESNET || cfg->backbone == YB_BACKBONE_DARKNET, "unknown backbone");
     YB_REQUIRE(cfg->num_stages >= 4 && cfg->num_stages <= 5, "num_stages must be 4 or 5");

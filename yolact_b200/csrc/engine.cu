@@ -362,6 +362,56 @@ struct NetBuilder {
     return out;
   }
 
+  void fused_head(const std::string& hn, const Act& in, float* loc, float* conf, float* coef, int64_t P, int A, int NC,
+                  int MD) {
+    ConvW& w = h->get_fused_head(hn);
+    const int c4 = A * 4, cc = A * NC, cm = A * MD;
+    YB_REQUIRE(w.Cout == c4 + cc + cm && w.Cin == in.C, "fused head: weight shape mismatch");
+    if (dry) return;
+    ConvProblem p;
+    p.B = in.B;
+    p.H = in.H;
+    p.W = in.W;
+    p.Cin = in.C;
+    p.KH = p.KW = 3;
+    p.stride = 1;
+    p.pad = 1;
+    p.Ho = in.H;
+    p.Wo = in.W;
+    p.Cout = w.Cout;
+    p.x = in.ptr;
+    p.y = loc;  // unused (segments)
+    p.y_f32 = 1;
+    p.y_batch_stride = P * 4;
+    p.y_pix_stride = c4;
+    p.bias = w.bias;
+    p.nseg = 3;
+    const int begins[4] = {0, c4, c4 + cc, c4 + cc + cm};
+    float* bases[3] = {loc, conf, coef};
+    const int64_t bs[3] = {P * 4, P * NC, P * MD};
+    const int ps[3] = {c4, cc, cm};
+    const int acts[3] = {ACT_NONE, ACT_NONE, ACT_TANH};  // mask_proto_coeff_activation = tanh (yolact.py:193)
+    for (int i = 0; i < 3; ++i) {
+      p.seg_begin[i] = begins[i];
+      p.seg_end[i] = begins[i + 1];
+      p.seg_y[i] = bases[i];
+      p.seg_bs[i] = bs[i];
+      p.seg_ps[i] = ps[i];
+      p.seg_act[i] = acts[i];
+    }
+    TcConvPlan* plan = autotune_tc(p, w.w_tc);
+    ex->plans.push_back(plan);
+    tc_conv_plan_set_pdl(plan, h->pdl ? 1 : 0);
+    LaunchCounter* lc = &h->lc;
+    Op op;
+    op.is_conv = true;
+    op.name = hn + ".bbox+conf+mask " + std::to_string(in.C) + "->" + std::to_string(w.Cout) + " k3s1 " +
+              std::to_string(in.H) + "x" + std::to_string(in.W) + " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) +
+              " st=" + std::to_string(tc_conv_plan_stages(plan)) + " g=" + std::to_string(tc_conv_plan_grid(plan));
+    op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
+    ex->ops.push_back(op);
+  }
+
   // Plan-time autotuning of the tcgen05 kernel's N tile and pipeline depth: each candidate is timed on the
   // layer's real buffers (contents irrelevant) with CUDA events; the fastest plan is kept.  Small layers
   // are launch/wave-quantisation bound and large-K ones L2-bandwidth bound, so no single rule fits.
@@ -371,7 +421,7 @@ struct NetBuilder {
     const std::string tkey = std::to_string(p.B) + "," + std::to_string(p.H) + "," + std::to_string(p.W) + "," +
                              std::to_string(p.Cin) + "," + std::to_string(p.Cout) + "," + std::to_string(p.KH) + "," +
                              std::to_string(p.stride) + "," + std::to_string(p.pad) + "," + (p.residual ? "r" : "-") +
-                             (p.y_f32 ? "f" : "h") + std::to_string(p.y_pix_stride) + "," + std::to_string((long long)p.y_batch_stride);
+                             (p.y_f32 ? "f" : "h") + std::to_string(p.nseg) + "," + std::to_string(p.y_pix_stride) + "," + std::to_string((long long)p.y_batch_stride);
     auto it = h->tune_cache.find(tkey);
     if (it != h->tune_cache.end()) return tc_conv_plan_create(p, w, it->second[0], it->second[1], it->second[2]);
     const int bns[4] = {256, 128, 64, 32};
@@ -540,6 +590,13 @@ void build_network(yb_handle* h, Executor* ex, bool dry) {
   for (int l = 0; l < 5; ++l) {
     const std::string hn = "prediction_layers.0";
     Act u = nb.conv(hn + ".upfeature.0", "", Pl[l], 3, 1, 1, ACT_RELU);
+    if (nb.f16 && h->fuse_heads) {
+      // bbox + conf + mask convs share their input: one tcgen05 launch with Cout = A*(4+C+k), the epilogue
+      // routes channel ranges to the three concatenated fp32 tensors (tanh on the mask coefficients)
+      nb.fused_head(hn, u, ex->loc ? ex->loc + level_off[l] * 4 : nullptr, ex->conf ? ex->conf + level_off[l] * NC : nullptr,
+                    ex->coef ? ex->coef + level_off[l] * MD : nullptr, ex->P, A, NC, MD);
+      continue;
+    }
     NetBuilder::OutSpec os;
     os.base = ex->loc ? ex->loc + level_off[l] * 4 : nullptr;
     os.batch_stride = ex->P * 4;
@@ -702,6 +759,43 @@ ConvW& yb_handle::get_conv(const std::string& conv_key, const std::string& bn_ke
     cw.bias = (float*)dmalloc(weight_allocs, (size_t)Co * 4);
     YB_CHECK_CUDA(cudaMemcpy(cw.bias, shift.data(), (size_t)Co * 4, cudaMemcpyHostToDevice));
   }
+  return cw;
+}
+
+ConvW& yb_handle::get_fused_head(const std::string& hn) {
+  ConvW& cw = convs[hn + ".fused"];
+  if (cw.w_tc) return cw;
+  const char* parts[3] = {".bbox_layer", ".conf_layer", ".mask_layer"};
+  int Ci = 0, Co = 0;
+  for (int i = 0; i < 3; ++i) {
+    const HostTensor& w = need(this, hn + parts[i] + ".weight");
+    YB_REQUIRE(w.shape.size() == 4 && w.shape[2] == 3 && w.shape[3] == 3, "fused head: 3x3 convs expected");
+    YB_REQUIRE(Ci == 0 || Ci == (int)w.shape[1], "fused head: Cin mismatch");
+    Ci = (int)w.shape[1];
+    Co += (int)w.shape[0];
+  }
+  std::vector<__half> pk((size_t)9 * Co * Ci);
+  std::vector<float> bias(Co, 0.f);
+  int o0 = 0;
+  for (int i = 0; i < 3; ++i) {
+    const HostTensor& w = need(this, hn + parts[i] + ".weight");
+    const int co = (int)w.shape[0];
+    for (int o = 0; o < co; ++o)
+      for (int c = 0; c < Ci; ++c)
+        for (int t = 0; t < 9; ++t)
+          pk[((size_t)t * Co + o0 + o) * Ci + c] = __float2half_rn(w.data[((size_t)o * Ci + c) * 9 + t]);
+    auto it = host.find(hn + parts[i] + ".bias");
+    if (it != host.end())
+      for (int o = 0; o < co; ++o) bias[o0 + o] = it->second.data[o];
+    o0 += co;
+  }
+  cw.Cin = Ci;
+  cw.Cout = Co;
+  cw.KH = cw.KW = 3;
+  cw.w_tc = (__half*)dmalloc(weight_allocs, pk.size() * 2);
+  YB_CHECK_CUDA(cudaMemcpy(cw.w_tc, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+  cw.bias = (float*)dmalloc(weight_allocs, (size_t)Co * 4);
+  YB_CHECK_CUDA(cudaMemcpy(cw.bias, bias.data(), (size_t)Co * 4, cudaMemcpyHostToDevice));
   return cw;
 }
 

@@ -89,6 +89,7 @@ struct yb_handle {
   bool finalized = false;
   bool use_graphs = true;
   bool profiling = false;
+  bool fuse_heads = true;   // YB_FUSE_HEADS=0: three separate head convs per level
   bool pdl = false;         // YB_PDL=1: programmatic dependent launch between consecutive tcgen05 convs
   bool stem_on_tc = true;   // YB_STEM_TC=0 falls back to the SIMT stem
   bool autotune = true;     // YB_AUTOTUNE=0 disables plan-time autotuning of the tcgen05 tiles
@@ -113,6 +114,7 @@ struct yb_handle {
   yb::ConvW& get_conv(const std::string& conv_key, const std::string& bn_key, bool want_tc, bool want_f32,
                       bool want_f16, int pack = 0);
   int peek_cout(const std::string& conv_key) const;
+  yb::ConvW& get_fused_head(const std::string& head_name);
   void finalize();
   // ---- executors
   yb::Executor* get_executor(int B, int H, int W);

@@ -25,6 +25,12 @@ struct ConvProblem {
   const float* bias = nullptr;     // [Cout] fp32 (BN folded), nullable
   const void* residual = nullptr;  // dense NHWC [B,Ho,Wo,Cout], activation dtype, nullable
   int res_after_act = 0;           // 1: y = act(conv) + residual (DarkNetBlock, backbone.py:246-247)
+  // fused prediction head (tcgen05 kernel only): output channels [seg_begin, seg_end) of segment i go to the
+  // fp32 tensor seg_y[i] with its own strides and activation; y / y_* are ignored when nseg > 0
+  int nseg = 0;
+  int seg_begin[3] = {0, 0, 0}, seg_end[3] = {0, 0, 0}, seg_ps[3] = {0, 0, 0}, seg_act[3] = {0, 0, 0};
+  int64_t seg_bs[3] = {0, 0, 0};
+  float* seg_y[3] = {nullptr, nullptr, nullptr};
 };
 
 enum SimtTypes : int {

@@ -45,6 +45,10 @@ struct alignas(64) TcParams {
   int res_off;          // byte offset of the residual staging buffers inside dynamic smem
   int m_tiles, n_tiles; // tile = m_tile * n_tiles + n_tile
   int acc_stages;       // TMEM accumulator buffers (2 when a CTA processes several tiles)
+  int nseg;             // > 0: output channels are split over several fp32 tensors (fused prediction head)
+  int seg_begin[3], seg_end[3], seg_ps[3], seg_act[3];
+  long long seg_bs[3];
+  float* seg_y[3];
   int tmem_cols;        // power of two >= acc_stages * BN
   int pdl;              // launched with programmatic stream serialization
   int ntaps, kchunks, stages;
@@ -384,7 +388,24 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
           __syncwarp();
           const float bias_l = sbias[c0 + lane];
-          const int act = p.act, raa = p.res_after_act;
+          int act = p.act;
+          const int raa = p.res_after_act;
+          // fused prediction head: this lane's channel belongs to one of up to 3 output tensors
+          float* seg_base = nullptr;
+          long long seg_bs = 0;
+          int seg_ps = 0, seg_c = 0;
+          if (p.nseg > 0) {
+            const int n = nbase + lane;
+#pragma unroll
+            for (int sg = 0; sg < 3; ++sg)
+              if (sg < p.nseg && n >= p.seg_begin[sg] && n < p.seg_end[sg]) {
+                seg_base = p.seg_y[sg];
+                seg_bs = p.seg_bs[sg];
+                seg_ps = p.seg_ps[sg];
+                seg_c = n - p.seg_begin[sg];
+                act = p.seg_act[sg];
+              }
+          }
           for (int rr = 0; rr < 32; ++rr) {
             const int trow = quad * 32 + rr;
             const int ty_ = trow / p.tw, tx_ = trow - ty_ * p.tw;
@@ -397,6 +418,10 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             if (!raa) v += rsd;
             v = (act == ACT_RELU) ? fmaxf(v, 0.f) : (act == ACT_TANH) ? tanhf(v) : (act == ACT_LEAKY) ? (v > 0.f ? v : 0.1f * v) : v;
             if (raa) v += rsd;
+            if (p.nseg > 0) {
+              if (seg_base) seg_base[(long long)b * seg_bs + pix * seg_ps + seg_c] = v;
+              continue;
+            }
             const long long o = (long long)b * p.y_batch_stride + pix * p.y_pix_stride + nbase + lane;
             if (p.y_f32)
               reinterpret_cast<float*>(p.y)[o] = v;
@@ -544,7 +569,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
                 ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
   if (p.residual) vec_ok = vec_ok && (p.Cout % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
   q.vec_ok = vec_ok ? 1 : 0;
-  q.epi_tma = (!p.y_f32 && vec_ok && p.Cout % 8 == 0) ? 1 : 0;
+  q.epi_tma = (!p.y_f32 && vec_ok && p.Cout % 8 == 0 && p.nseg == 0) ? 1 : 0;
   // the staged epilogue moves 64-channel boxes: a CTA must own at least 64 output channels
   const int bn_min = q.epi_tma ? 64 : 32;
 
@@ -645,6 +670,15 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   q.y_f32 = p.y_f32;
   q.act = p.act;
   q.res_after_act = p.res_after_act;
+  q.nseg = p.nseg;
+  for (int i = 0; i < p.nseg && i < 3; ++i) {
+    q.seg_begin[i] = p.seg_begin[i];
+    q.seg_end[i] = p.seg_end[i];
+    q.seg_ps[i] = p.seg_ps[i];
+    q.seg_act[i] = p.seg_act[i];
+    q.seg_bs[i] = p.seg_bs[i];
+    q.seg_y[i] = p.seg_y[i];
+  }
   q.y_pix_stride = p.y_pix_stride;
   if (flat) {
     q.y_batch_stride = 0;
