@@ -109,8 +109,21 @@ TC_CASES = [
 ]
 
 
+# kernel scheduling variants: default heuristic; few persistent CTAs (several tiles per CTA, TMEM double
+# buffering); CTA pairs with weight multicast (incl. an odd number of M tiles -> one dummy tile)
+TC_MODES = {
+    "default": {},
+    "persistent_grid3": {"YB_CONV2D_GRID": "3"},
+    "cluster2": {"YB_CONV2D_CLUSTER": "2"},
+    "cluster2_grid4_bn64": {"YB_CONV2D_CLUSTER": "2", "YB_CONV2D_GRID": "4", "YB_CONV2D_BN": "64"},
+}
+
+
+@pytest.mark.parametrize("mode", sorted(TC_MODES))
 @pytest.mark.parametrize("case", TC_CASES)
-def test_tcgen05_matches_simt_f16_and_torch(ops, case):
+def test_tcgen05_matches_simt_f16_and_torch(ops, case, mode, monkeypatch):
+    for k_, v_ in TC_MODES[mode].items():
+        monkeypatch.setenv(k_, v_)
     B, Ci, H, W, Co, k, s, p, act, wr = case
     x, w, bias, res = make(B, Ci, H, W, Co, k, s, p, True, wr, seed=1)
     y_tc, _ = run_conv(ops, x, w, bias, res, s, p, act, 1)

@@ -129,6 +129,8 @@ int yb_create(const yb_config* cfg, int device, yb_handle** out) {
   if (const char* st = getenv("YB_STEM_TC")) h->stem_on_tc = (atoi(st) != 0);
   if (const char* pd = getenv("YB_PDL")) h->pdl = (atoi(pd) != 0);
   if (const char* fh = getenv("YB_FUSE_HEADS")) h->fuse_heads = (atoi(fh) != 0);
+  if (const char* br = getenv("YB_BRANCHES")) h->multi_stream = (atoi(br) != 0);
+  if (const char* cl = getenv("YB_CLUSTERS")) h->clusters = (atoi(cl) != 0);
   if (!h->ops_only) {
     YB_REQUIRE(cfg->backbone == YB_BACKBONE_RESNET || cfg->backbone == YB_BACKBONE_DARKNET, "unknown backbone");
     YB_REQUIRE(cfg->num_stages >= 4 && cfg->num_stages <= 5, "num_stages must be 4 or 5");
@@ -503,7 +505,12 @@ int yb_conv2d(yb_handle* h, const float* d_x, const float* h_w, const float* h_b
           pk[((size_t)t * Co + o) * Ci + c] = __float2half_rn(h_w[((size_t)o * Ci + c) * taps + t]);
     __half* wd = (__half*)tp.get(pk.size() * 2);
     YB_CHECK_CUDA(cudaMemcpy(wd, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
-    plan = tc_conv_plan_create(p, wd);
+    {
+      const char* ce = getenv("YB_CONV2D_CLUSTER");
+      const char* be = getenv("YB_CONV2D_BN");
+      const char* ge = getenv("YB_CONV2D_GRID");
+      plan = tc_conv_plan_create(p, wd, be ? atoi(be) : 0, 0, ge ? atoi(ge) : 0, ce ? atoi(ce) : 0);
+    }
     run = [&]() { launch_tc_conv(plan, s, &h->lc); };
   } else if (precision == 2) {
     std::vector<__half> pk(K * Co);

@@ -153,6 +153,11 @@ struct NetBuilder {
   Executor* ex;
   bool dry;
   bool f16;
+  int lane = 0;
+  void push(Op& op) {
+    op.lane = lane;
+    push(op);
+  }
 
   size_t esize(const Act& a) const { return a.f32 ? 4 : (f16 ? 2 : 4); }
 
@@ -235,7 +240,7 @@ struct NetBuilder {
                                            stride, pad, w.Cout, act);
       ex->stem_plans.push_back(sp);
       op.fn = [sp, lc](cudaStream_t s) { launch_stem_tc(sp, s, lc); };
-      ex->ops.push_back(op);
+      push(op);
       return out;
     }
     if (tc) {
@@ -243,7 +248,7 @@ struct NetBuilder {
       TcConvPlan* plan = autotune_tc(p, w.w_tc);
       ex->plans.push_back(plan);
       op.name += " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) + " st=" + std::to_string(tc_conv_plan_stages(plan)) +
-                 " g=" + std::to_string(tc_conv_plan_grid(plan));
+                 " g=" + std::to_string(tc_conv_plan_grid(plan)) + " cl=" + std::to_string(tc_conv_plan_cluster(plan));
       tc_conv_plan_set_pdl(plan, h->pdl ? 1 : 0);
       op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
     } else {
@@ -258,7 +263,7 @@ struct NetBuilder {
       YB_REQUIRE(wp != nullptr, ("conv " + key + ": weights not packed for the SIMT kernel").c_str());
       op.fn = [p, wp, types, lc](cudaStream_t s) { launch_simt_conv(p, wp, types, s, lc); };
     }
-    ex->ops.push_back(op);
+    push(op);
     return out;
   }
 
@@ -276,7 +281,7 @@ struct NetBuilder {
       op.fn = [in, out, lc](cudaStream_t s) {
         launch_maxpool3x3s2<float>((const float*)in.ptr, (float*)out.ptr, in.B, in.H, in.W, in.C, out.H, out.W, s, lc);
       };
-    ex->ops.push_back(op);
+    push(op);
     return out;
   }
 
@@ -298,7 +303,7 @@ struct NetBuilder {
         launch_upsample_bilinear<float>((const float*)in.ptr, (const float*)addp, (float*)out.ptr, in.B, in.H, in.W,
                                         in.C, out.H, out.W, sh, sw, relu, s, lc);
       };
-    ex->ops.push_back(op);
+    push(op);
     return out;
   }
 
@@ -322,7 +327,7 @@ struct NetBuilder {
         launch_dcn_simt<float>((const float*)in.ptr, (const float*)om.ptr, wp, bias, (float*)out.ptr, in.B, in.H, in.W,
                                in.C, out.H, out.W, Cout, stride, 1, 1, ACT_RELU, 1, s, lc);
       };
-      ex->ops.push_back(op);
+      push(op);
     } else {
       // gather -> fp16 columns [B,Ho,Wo,9C]; contraction = 1x1 conv with K = 9C on tcgen05
       Act cols = alloc_act(in.B, Ho, Wo, 9 * in.C);
@@ -333,7 +338,7 @@ struct NetBuilder {
         launch_dcn_gather_f16((const __half*)in.ptr, (const float*)om.ptr, (__half*)cols.ptr, in.B, in.H, in.W, in.C,
                               cols.H, cols.W, stride, 1, 1, 1, s, lc);
       };
-      ex->ops.push_back(g);
+      push(g);
       ConvProblem p;
       p.B = in.B;
       p.H = Ho;
@@ -357,7 +362,7 @@ struct NetBuilder {
       op.is_conv = true;
       op.name = key + " dcn_contract K=" + std::to_string(p.Cin);
       op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
-      ex->ops.push_back(op);
+      push(op);
     }
     return out;
   }
@@ -407,9 +412,10 @@ struct NetBuilder {
     op.is_conv = true;
     op.name = hn + ".bbox+conf+mask " + std::to_string(in.C) + "->" + std::to_string(w.Cout) + " k3s1 " +
               std::to_string(in.H) + "x" + std::to_string(in.W) + " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) +
-              " st=" + std::to_string(tc_conv_plan_stages(plan)) + " g=" + std::to_string(tc_conv_plan_grid(plan));
+              " st=" + std::to_string(tc_conv_plan_stages(plan)) + " g=" + std::to_string(tc_conv_plan_grid(plan)) +
+              " cl=" + std::to_string(tc_conv_plan_cluster(plan));
     op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
-    ex->ops.push_back(op);
+    push(op);
   }
 
   // Plan-time autotuning of the tcgen05 kernel's N tile and pipeline depth: each candidate is timed on the
@@ -423,7 +429,8 @@ struct NetBuilder {
                              std::to_string(p.stride) + "," + std::to_string(p.pad) + "," + (p.residual ? "r" : "-") +
                              (p.y_f32 ? "f" : "h") + std::to_string(p.nseg) + "," + std::to_string(p.y_pix_stride) + "," + std::to_string((long long)p.y_batch_stride);
     auto it = h->tune_cache.find(tkey);
-    if (it != h->tune_cache.end()) return tc_conv_plan_create(p, w, it->second[0], it->second[1], it->second[2]);
+    if (it != h->tune_cache.end())
+      return tc_conv_plan_create(p, w, it->second[0], it->second[1], it->second[2], it->second[3]);
     const int bns[4] = {256, 128, 64, 32};
     const int sts[3] = {0, 3, 2};
     const int grids[3] = {148, 296, 1 << 30};
@@ -435,11 +442,13 @@ struct NetBuilder {
     YB_CHECK_CUDA(cudaEventCreate(&e1));
     for (int bi = 0; bi < 4; ++bi)
       for (int si = 0; si < 3; ++si)
-        for (int gi = 0; gi < 3; ++gi) {
+        for (int gi = 0; gi < 6; ++gi) {
           if (bns[bi] > 64 && bns[bi] >= 2 * p.Cout) continue;
-          TcConvPlan* cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi]);
+          const int clus = (gi >= 3 && h->clusters) ? 2 : 1;   // second half of the sweep: CTA pairs with weight multicast
+          if (gi >= 3 && !h->clusters) continue;
+          TcConvPlan* cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi % 3], clus);
           const std::string ck = std::to_string(tc_conv_plan_bn(cand)) + "/" + std::to_string(tc_conv_plan_stages(cand)) +
-                                 "/" + std::to_string(tc_conv_plan_grid(cand));
+                                 "/" + std::to_string(tc_conv_plan_grid(cand)) + "/" + std::to_string(tc_conv_plan_cluster(cand));
           if (!seen.insert(ck).second) {  // overrides were clamped to an already-timed configuration
             tc_conv_plan_destroy(cand);
             continue;
@@ -470,7 +479,8 @@ struct NetBuilder {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     YB_REQUIRE(best != nullptr, "autotune: no candidate");
-    h->tune_cache[tkey] = {tc_conv_plan_bn(best), tc_conv_plan_stages(best), tc_conv_plan_grid(best)};
+    h->tune_cache[tkey] = {tc_conv_plan_bn(best), tc_conv_plan_stages(best), tc_conv_plan_grid(best),
+                           tc_conv_plan_cluster(best)};
     return best;
   }
 };
@@ -572,6 +582,7 @@ void build_network(yb_handle* h, Executor* ex, bool dry) {
   Pl[3] = nb.conv("fpn.downsample_layers.0", "", Pl[2], 3, 2, 1, ACT_NONE);
   Pl[4] = nb.conv("fpn.downsample_layers.1", "", Pl[3], 3, 2, 1, ACT_NONE);
   for (int l = 0; l < 5; ++l) ex->feats[4 + l] = Pl[l];
+  ex->fork_index = ex->ops.size();   // protonet (lane 0) and the 5 head levels (lanes 1..5) are independent
 
   // ---------------- protonet on P3 (config.py:691, utils/functions.py:163-213, yolact.py:588-599) ----
   {
@@ -588,6 +599,7 @@ void build_network(yb_handle* h, Executor* ex, bool dry) {
 
   // ---------------- shared prediction head over the 5 levels (yolact.py:133-212, 616-634) -----------
   for (int l = 0; l < 5; ++l) {
+    nb.lane = 1 + l;
     const std::string hn = "prediction_layers.0";
     Act u = nb.conv(hn + ".upfeature.0", "", Pl[l], 3, 1, 1, ACT_RELU);
     if (nb.f16 && h->fuse_heads) {
@@ -626,6 +638,11 @@ yb_handle::~yb_handle() {
   if (detect_ws) cudaFree(detect_ws);
   if (scratch) cudaFree(scratch);
   if (cap_stream) cudaStreamDestroy(cap_stream);
+  for (auto s : lane_streams)
+    if (s) cudaStreamDestroy(s);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  for (auto e : ev_join)
+    if (e) cudaEventDestroy(e);
 }
 
 cudaStream_t yb_handle::capture_stream() {
@@ -835,8 +852,36 @@ Executor* yb_handle::get_executor(int B, int H, int W) {
   return raw;
 }
 
-static void run_ops(yb_handle* h, Executor* ex, cudaStream_t stream) {
-  for (auto& op : ex->ops) op.fn(stream);
+static void run_ops(yb_handle* h, Executor* ex, cudaStream_t stream, bool branches = false) {
+  if (!branches || ex->fork_index == 0 || ex->fork_index >= ex->ops.size()) {
+    for (auto& op : ex->ops) op.fn(stream);
+    return;
+  }
+  // trunk, then fork: each lane gets its own stream so that the captured graph has parallel branches
+  // (small latency-bound head convs fill the gaps of the large protonet convs)
+  for (size_t i = 0; i < ex->fork_index; ++i) ex->ops[i].fn(stream);
+  if (!h->ev_fork) YB_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  YB_CHECK_CUDA(cudaEventRecord(h->ev_fork, stream));
+  bool used[8] = {false, false, false, false, false, false, false, false};
+  for (size_t i = ex->fork_index; i < ex->ops.size(); ++i) {
+    const int lane = ex->ops[i].lane & 7;
+    cudaStream_t s = stream;
+    if (lane > 0) {
+      if (!h->lane_streams[lane]) YB_CHECK_CUDA(cudaStreamCreateWithFlags(&h->lane_streams[lane], cudaStreamNonBlocking));
+      s = h->lane_streams[lane];
+      if (!used[lane]) {
+        YB_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_fork, 0));
+        used[lane] = true;
+      }
+    }
+    ex->ops[i].fn(s);
+  }
+  for (int lane = 1; lane < 8; ++lane) {
+    if (!used[lane]) continue;
+    if (!h->ev_join[lane]) YB_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_join[lane], cudaEventDisableTiming));
+    YB_CHECK_CUDA(cudaEventRecord(h->ev_join[lane], h->lane_streams[lane]));
+    YB_CHECK_CUDA(cudaStreamWaitEvent(stream, h->ev_join[lane], 0));
+  }
 }
 
 static void run_ops_profiled(yb_handle* h, Executor* ex, cudaStream_t stream) {
@@ -880,7 +925,7 @@ void yb_handle::forward(const float* d_x, int B, int H, int W, float* d_loc, flo
       cudaStream_t cs = capture_stream();
       YB_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
       try {
-        run_ops(this, ex, cs);
+        run_ops(this, ex, cs, multi_stream);
       } catch (...) {
         cudaStreamEndCapture(cs, &g);
         if (g) cudaGraphDestroy(g);
@@ -938,15 +983,15 @@ void yb_handle::infer(const float* d_x, int B, int H, int W, int cross_class, in
     ex->det_max_out = max_out;
     ex->det_cross_class = cross_class;
   }
-  auto run_all = [&](cudaStream_t s) {
-    run_ops(this, ex, s);
+  auto run_all = [&](cudaStream_t s, bool branches) {
+    run_ops(this, ex, s, branches);
     launch_detect(dp, ex->loc, ex->conf, ex->coef, ex->priors, ex->dws, ex->det_box, ex->det_coef, ex->det_cls,
                   ex->det_score, ex->det_count, s, &lc);
   };
   YB_CHECK_CUDA(cudaMemcpyAsync(ex->d_in, d_x, (size_t)B * 3 * H * W * 4, cudaMemcpyDeviceToDevice, stream));
   last_exec = ex;
   if (!use_graphs || ex->infer_calls == 0) {
-    run_all(stream);
+    run_all(stream, false);
   } else {
     if (!ex->graph_infer) {
       cudaGraph_t g = nullptr;
@@ -954,7 +999,7 @@ void yb_handle::infer(const float* d_x, int B, int H, int W, int cross_class, in
       cudaStream_t cs = capture_stream();
       YB_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
       try {
-        run_all(cs);
+        run_all(cs, multi_stream);
       } catch (...) {
         cudaStreamEndCapture(cs, &g);
         if (g) cudaGraphDestroy(g);

@@ -44,6 +44,7 @@ struct Op {
   std::function<void(cudaStream_t)> fn;
   bool is_conv = false;
   std::string name;   // layer key, for yb_last_forward_profile
+  int lane = 0;       // graph branch: 0 = trunk (+ protonet); 1..5 = prediction head of FPN level lane-1
   float last_ms = 0.f;
 };
 
@@ -53,6 +54,7 @@ struct Executor {
   std::vector<TcConvPlan*> plans;
   std::vector<StemTcPlan*> stem_plans;
   std::vector<Op> ops;           // the conv stack (yb_forward)
+  size_t fork_index = 0;         // ops[fork_index..] may run on their lanes concurrently (0 = no fork)
   float* d_in = nullptr;         // NCHW fp32 copy of the input (stable address for graph replay)
   float* loc = nullptr;          // [B,P,4]
   float* conf = nullptr;         // [B,P,C] logits
@@ -89,6 +91,7 @@ struct yb_handle {
   bool finalized = false;
   bool use_graphs = true;
   bool profiling = false;
+  bool clusters = true;     // YB_CLUSTERS=0: never use CTA pairs with weight multicast
   bool fuse_heads = true;   // YB_FUSE_HEADS=0: three separate head convs per level
   bool pdl = false;         // YB_PDL=1: programmatic dependent launch between consecutive tcgen05 convs
   bool stem_on_tc = true;   // YB_STEM_TC=0 falls back to the SIMT stem
@@ -99,7 +102,7 @@ struct yb_handle {
   std::map<std::string, yb::ConvW> convs;
   std::map<std::string, std::unique_ptr<yb::Executor>> execs;
   std::vector<void*> weight_allocs;
-  std::map<std::string, std::array<int, 3>> tune_cache;  // layer shape -> (BN, stages, grid) picked by the autotuner
+  std::map<std::string, std::array<int, 4>> tune_cache;  // layer shape -> (BN, stages, grid, cluster) from the autotuner
   yb::Executor* last_exec = nullptr;
   // standalone op workspaces
   void* detect_ws = nullptr;
@@ -107,6 +110,9 @@ struct yb_handle {
   void* scratch = nullptr;   // maskiou / dcn / conv2d temporaries
   size_t scratch_bytes = 0;
   cudaStream_t cap_stream = nullptr;  // private stream used only for CUDA-graph capture
+  cudaStream_t lane_streams[8] = {};  // branch streams joined into the capture (parallel graph branches)
+  cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
+  bool multi_stream = true;           // YB_BRANCHES=0: capture a linear graph
   cudaStream_t capture_stream();
   ~yb_handle();
 

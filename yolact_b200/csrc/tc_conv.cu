@@ -45,6 +45,8 @@ struct alignas(64) TcParams {
   int res_off;          // byte offset of the residual staging buffers inside dynamic smem
   int m_tiles, n_tiles; // tile = m_tile * n_tiles + n_tile
   int acc_stages;       // TMEM accumulator buffers (2 when a CTA processes several tiles)
+  int cluster;          // 1, or 2: CTA pairs (adjacent M tiles, same N tile) share each weight tile via TMA multicast
+  int nbatch;           // batch extent of the tile space (1 when flattened)
   int nseg;             // > 0: output channels are split over several fp32 tensors (fused prediction head)
   int seg_begin[3], seg_end[3], seg_ps[3], seg_act[3];
   long long seg_bs[3];
@@ -159,13 +161,42 @@ __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1
   }
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// weight tile half -> the same shared-memory offset of BOTH CTAs of the pair, completing tx on both full barriers
+__device__ __forceinline__ void tma_load_3d_mcast(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2,
+                                                  uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in every CTA of `mask` once the preceding MMAs are done
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 struct TileCoord {
   int b, x0, y0, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, int BN) {
+// pt indexes (M-tile group, N tile); a cluster of `p.cluster` CTAs takes the group's consecutive M tiles.
+// An M tile past the end (odd tile count) decodes to batch index >= nbatch: every TMA access is then out of
+// bounds (zero-filled loads, clipped stores), so the CTA still takes part in the multicast protocol.
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int pt, int BN, int rank) {
   TileCoord t;
-  const int nt = tile % p.n_tiles;
-  int m = tile / p.n_tiles;
+  const int nt = pt % p.n_tiles;
+  int m = (pt / p.n_tiles) * p.cluster + rank;
   const int tx = m % p.tiles_x;
   m /= p.tiles_x;
   const int ty = m % p.tiles_y;
@@ -200,13 +231,16 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
   const int num_kb = p.ntaps * p.kchunks;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int cl = p.cluster;
+  const int rank = (cl > 1) ? (int)cluster_ctarank() : 0;
+  const int num_tiles = ((p.m_tiles + cl - 1) / cl) * p.n_tiles;   // tile groups x N tiles
+  const int tile0 = (int)blockIdx.x / cl, tile_step = (int)gridDim.x / cl;
   const int acc_stages = p.acc_stages;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], (uint32_t)cl);   // every CTA of the pair must have consumed the slot
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
@@ -222,6 +256,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (cl > 1) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   const uint32_t tmem_base = s_tmem_base;
   // Programmatic dependent launch: everything above overlaps the tail of the previous kernel in the
   // stream; its output is only touched below this point.
@@ -235,8 +270,8 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)p.a_box_bytes + (uint32_t)B_STAGE_BYTES;
       uint32_t kbg = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord tc_ = decode_tile(p, tile, BN);
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const TileCoord tc_ = decode_tile(p, tile, BN, rank);
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)stages;
           const uint32_t it = kbg / (uint32_t)stages;
@@ -248,7 +283,13 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           mbar_expect_tx(&full_bar[s], tx_bytes);
           tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[s], kc * BLOCK_K, tc_.x0 + p.tap_dx[tap],
                       tc_.y0 + p.tap_dy[tap], tc_.b);
-          tma_load_3d(sb, &p.tmB, &full_bar[s], kc * BLOCK_K, tc_.n0, tap);
+          if (cl > 1) {
+            // this CTA fetches its half of the weight tile and multicasts it to the pair
+            tma_load_3d_mcast(sb + rank * (B_STAGE_BYTES / 2), &p.tmB, &full_bar[s], kc * BLOCK_K,
+                              tc_.n0 + rank * (BN / 2), tap, (uint16_t)0x3);
+          } else {
+            tma_load_3d(sb, &p.tmB, &full_bar[s], kc * BLOCK_K, tc_.n0, tap);
+          }
         }
       }
     }
@@ -256,7 +297,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       uint32_t kbg = 0, t = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++t) {
         const uint32_t acc = t % (uint32_t)acc_stages;
         const uint32_t use = t / (uint32_t)acc_stages;
         mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
@@ -276,7 +317,10 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 field
             umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);  // frees this smem slot once the MMAs above have read it
+          if (cl > 1)
+            umma_commit_mcast(&empty_bar[s], (uint16_t)0x3);   // ... in both CTAs of the pair
+          else
+            umma_commit(&empty_bar[s]);  // frees this smem slot once the MMAs above have read it
         }
         umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       }
@@ -293,11 +337,11 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 
     // residual chunk stream (epi_tma only): global chunk g lives in res buffer g&1; the issuer keeps it
     // two chunks ahead of the consumer, across tile boundaries.  (pf_tile, pf_c) = next chunk to fetch.
-    int pf_tile = blockIdx.x, pf_c = 0;
+    int pf_tile = tile0, pf_c = 0;
     uint32_t pf_g = 0;
     auto prefetch_res = [&]() {
       if (pf_tile >= num_tiles) return;
-      const TileCoord tcp = decode_tile(p, pf_tile, BN);
+      const TileCoord tcp = decode_tile(p, pf_tile, BN, rank);
       const int nch = (min(BN, p.Cout - tcp.n0) + 63) >> 6;
       const uint32_t buf = pf_g & 1u;
       mbar_expect_tx(&res_full_bar[buf], (uint32_t)p.a_box_bytes);
@@ -305,7 +349,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       ++pf_g;
       if (++pf_c >= nch) {
         pf_c = 0;
-        pf_tile += gridDim.x;
+        pf_tile += tile_step;
       }
     };
     if (p.epi_tma && has_res && issuer) {
@@ -314,8 +358,8 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
     }
 
     uint32_t t = 0, g = 0;  // local tile counter, global staged-chunk counter
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-      const TileCoord tc_ = decode_tile(p, tile, BN);
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++t) {
+      const TileCoord tc_ = decode_tile(p, tile, BN, rank);
       const int x0 = tc_.x0, y0 = tc_.y0, b = tc_.b, n0 = tc_.n0;
       const uint32_t acc = t % (uint32_t)acc_stages;
       const uint32_t use = t / (uint32_t)acc_stages;
@@ -410,7 +454,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             const int trow = quad * 32 + rr;
             const int ty_ = trow / p.tw, tx_ = trow - ty_ * p.tw;
             const int oy = y0 + ty_, ox = x0 + tx_;
-            if (trow >= p.tw * p.th || oy >= p.Ho || ox >= p.Wo) continue;   // warp-uniform
+            if (trow >= p.tw * p.th || oy >= p.Ho || ox >= p.Wo || b >= p.nbatch) continue;   // warp-uniform
             if (lane >= nvalid) continue;
             const long long pix = (long long)oy * p.Wo + ox;
             float v = tbuf[rr * 33 + lane] + bias_l;
@@ -442,6 +486,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (cl > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_dyn(tmem_base, (uint32_t)p.tmem_cols);
@@ -517,7 +562,7 @@ bool tc_conv_supported(const ConvProblem& p) {
 }
 
 TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override, int stages_override,
-                                int grid_override) {
+                                int grid_override, int cluster_override) {
   YB_REQUIRE(tc_conv_supported(p), "tc_conv: unsupported problem");
   YB_REQUIRE(p.Ho == (p.H + 2 * p.pad - p.KH) / p.stride + 1, "tc_conv: bad Ho");
   YB_REQUIRE(p.Wo == (p.W + 2 * p.pad - p.KW) / p.stride + 1, "tc_conv: bad Wo");
@@ -599,13 +644,16 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   // ---- persistent grid + shared-memory layout: [pipeline stages][2 x 16 KB out tiles][2 x 16 KB residual tiles]
   q.m_tiles = (int)m_tiles;
   q.n_tiles = ceil_div(p.Cout, BN);
-  const int num_tiles = q.m_tiles * q.n_tiles;
-  int grid = std::min(num_tiles, grid_override > 0 ? grid_override : 148);
-  q.acc_stages = (grid < num_tiles) ? 2 : 1;
+  q.nbatch = Bv;
+  q.cluster = (cluster_override == 2 && q.m_tiles >= 2) ? 2 : 1;
+  const int cl = q.cluster;
+  const int num_tiles = ceil_div(q.m_tiles, cl) * q.n_tiles;   // tile groups x N tiles
+  int grid = std::min(num_tiles, std::max(1, (grid_override > 0 ? grid_override : 148) / cl)) * cl;
+  q.acc_stages = (grid < num_tiles * cl) ? 2 : 1;
   int tmem_cols = 32;
   while (tmem_cols < q.acc_stages * BN) tmem_cols *= 2;
   q.tmem_cols = tmem_cols;
-  const int tiles_per_cta = ceil_div(num_tiles, grid);
+  const int tiles_per_cta = ceil_div(num_tiles * cl, grid);
   const int out_bytes = 2 * A_STAGE_BYTES;
   const int res_bytes = (q.epi_tma && p.residual) ? 2 * A_STAGE_BYTES : 0;
   int stages = std::min(MAX_STAGES, (200 * 1024 - out_bytes - res_bytes) / stage_bytes);
@@ -660,7 +708,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   {
     uint64_t dims[3] = {(uint64_t)p.Cin, (uint64_t)p.Cout, (uint64_t)q.ntaps};
     uint64_t str[2] = {(uint64_t)p.Cin * 2, (uint64_t)p.Cout * p.Cin * 2};
-    uint32_t box[3] = {(uint32_t)BLOCK_K, (uint32_t)BN, 1};
+    uint32_t box[3] = {(uint32_t)BLOCK_K, (uint32_t)(BN / q.cluster), 1};   // a pair loads half a tile per CTA
     encode_map_f16(&q.tmB, w_packed, 3, dims, str, box);
   }
   // ---- epilogue
@@ -716,6 +764,7 @@ void tc_conv_plan_set_pdl(TcConvPlan* plan, int enable) { plan->prm.pdl = enable
 int tc_conv_plan_bn(const TcConvPlan* plan) { return plan->BN; }
 int tc_conv_plan_stages(const TcConvPlan* plan) { return plan->prm.stages; }
 int tc_conv_plan_grid(const TcConvPlan* plan) { return (int)plan->grid.x; }
+int tc_conv_plan_cluster(const TcConvPlan* plan) { return plan->prm.cluster; }
 
 template <int BN>
 static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
@@ -727,17 +776,28 @@ static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
     attr_set = true;
     attr_bytes = 220 * 1024;
   }
-  if (plan->prm.pdl) {
+  if (plan->prm.pdl || plan->prm.cluster > 1) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = plan->grid;
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = plan->smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (plan->prm.pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    if (plan->prm.cluster > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = (unsigned)plan->prm.cluster;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN>, plan->prm));
   } else {
     tc_conv_kernel<BN><<<plan->grid, NUM_THREADS, plan->smem_bytes, stream>>>(plan->prm);
