@@ -239,7 +239,7 @@ def main():
     # ------------------------------------------------------------------ B200 arm
     import torch.distributed as dist
     import yolact_b200
-    from yolact_b200.output_utils import assemble_masks
+    from yolact_b200.output_utils import assemble_masks_batch
     from yolact_b200 import output_utils
     from yolact_b200.parallel import gather_detections
 
@@ -263,12 +263,8 @@ def main():
 
     def step_device(i, fmt="f32", out=None):
         box, coef, cls, score, count, proto = net.infer_padded(xs[i % n_rot])
-        res = []
-        for b in range(B):
-            # all M padded rows are assembled (no host sync on the count); with these weights count == M
-            m, bpx, _ = assemble_masks(proto[b], coef[b], box[b], size, size, True, fmt,
-                                       masks_out=(out[b] if out is not None else None))
-            res.append((m, bpx))
+        # all M padded rows are assembled (no host sync on the count); with these weights count == M
+        res = assemble_masks_batch(proto, coef, box, size, size, True, fmt, masks_out=out)
         if world > 1:
             gather_detections(box, coef, cls, score, count, per_rank_batch=B)
         return box, coef, cls, score, count, res
@@ -341,9 +337,7 @@ def main():
         if i >= 2:
             s_main.wait_event(ev_d2h[k])             # d_masks[k] / d_boxes[k] were last read by step i-2's D2H
         box, coef, cls, score, count, proto = net.infer_padded(dx[k])
-        for b in range(B):
-            _, bpx, _ = assemble_masks(proto[b], coef[b], box[b], size, size, True, "bits", masks_out=d_masks[k][b])
-            d_boxes[k][b].copy_(bpx)
+        assemble_masks_batch(proto, coef, box, size, size, True, "bits", masks_out=d_masks[k], boxes_out=d_boxes[k])
         ev_comp[k].record(s_main)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_comp[k])

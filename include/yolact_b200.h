@@ -166,6 +166,13 @@ YB_API int yb_postprocess(yb_handle* h, const float* d_proto, int ph, int pw, in
                    int crop_masks, int mask_format, void* d_masks, int64_t* d_boxes_px,
                    float* d_proto_masks, void* stream);
 
+/* Same for a whole batch in ONE launch (throughput extension; the reference API is per image):
+ * proto [B,ph,pw,k], coef [B,n,k], box [B,n,4] (n padded rows per image, e.g. yb_infer's max_out),
+ * masks [B,n,...], boxes_px [B,n,4]. */
+YB_API int yb_postprocess_batch(yb_handle* h, const float* d_proto, int ph, int pw, int k, const float* d_coef,
+                                const float* d_box, int n, int batch, int out_h, int out_w, int crop_masks,
+                                int mask_format, void* d_masks, int64_t* d_boxes_px, void* stream);
+
 /* maskiou_net on [n,1,ph,pw] fp32 masks -> d_maskiou [n] = net(mask)[i, cls[i]];
  * d_cls == NULL: d_maskiou [n, num_classes-1] = net(mask) (FastMaskIoUNet.forward itself). */
 YB_API int yb_maskiou(yb_handle* h, const float* d_proto_masks, int n, int ph, int pw,

@@ -166,3 +166,19 @@ def test_postprocess_full_size_properties():
     assert np.array_equal(ob, bx[:8])
     assert (om != m[:8]).mean() < 1e-4
     np.testing.assert_allclose(pm.cpu().numpy()[:8], O.proto_masks(proto, coef[:8], box[:8]), atol=2e-6)
+
+
+def test_postprocess_batch_equals_per_image():
+    from yolact_b200.output_utils import assemble_masks_batch
+    r = np.random.RandomState(11)
+    B, n = 3, 17
+    proto = np.maximum(r.standard_normal((B, 40, 44, 32)), 0).astype(np.float32)
+    coef = np.tanh(r.standard_normal((B, n, 32))).astype(np.float32)
+    c, wh = r.uniform(0.2, 0.8, (B, n, 2)), r.uniform(0.05, 0.6, (B, n, 2))
+    box = np.concatenate([c - wh / 2, c + wh / 2], 2).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).cuda()
+    for fmt in ("f32", "u8", "bits"):
+        mb, bb = assemble_masks_batch(t(proto), t(coef), t(box), 101, 135, True, fmt)
+        for b in range(B):
+            m1, b1, _ = assemble_masks(t(proto[b]), t(coef[b]), t(box[b]), 101, 135, True, fmt)
+            assert torch.equal(mb[b], m1) and torch.equal(bb[b], b1), (fmt, b)

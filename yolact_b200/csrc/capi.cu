@@ -312,6 +312,18 @@ int yb_postprocess(yb_handle* h, const float* d_proto, int ph, int pw, int k, co
   YB_API_END
 }
 
+int yb_postprocess_batch(yb_handle* h, const float* d_proto, int ph, int pw, int k, const float* d_coef,
+                         const float* d_box, int n, int batch, int out_h, int out_w, int crop_masks, int mask_format,
+                         void* d_masks, int64_t* d_boxes_px, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && d_proto && d_coef && d_box, "yb_postprocess_batch: null argument");
+  YB_REQUIRE(n >= 0 && batch >= 0, "yb_postprocess_batch: negative count");
+  DeviceGuard g(h->device);
+  launch_mask_assembly(d_proto, ph, pw, k, d_coef, d_box, n, out_h, out_w, crop_masks, mask_format, d_masks,
+                       d_boxes_px, nullptr, (cudaStream_t)stream, &h->lc, batch);
+  YB_API_END
+}
+
 int yb_maskiou(yb_handle* h, const float* d_proto_masks, int n, int ph, int pw, const int64_t* d_cls,
                float* d_maskiou, void* stream) {
   YB_API_BEGIN

@@ -129,7 +129,7 @@ void launch_detect(const DetectParams& dp, const float* loc, const float* conf, 
 void launch_mask_assembly(const float* proto, int ph, int pw, int k, const float* coef,
                           const float* box, int n, int out_h, int out_w, int crop, int mask_format,
                           void* masks, int64_t* boxes_px, float* proto_masks, cudaStream_t stream,
-                          LaunchCounter* lc);
+                          LaunchCounter* lc, int batch = 1);
 // global max over HxW per (n, c) then gather channel cls[n] (yolact.py:373, output_utils.py:83)
 void launch_maxpool_gather(const float* x_nhwc, int n, int H, int W, int C, const int64_t* cls,
                            float* out, cudaStream_t stream, LaunchCounter* lc);

@@ -51,7 +51,12 @@ __global__ void __launch_bounds__(MT)
 mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
                      const float* __restrict__ coef, const float* __restrict__ box, int n, int out_h,
                      int out_w, int crop, int band, int group, int max_rows, float scale_h,
-                     float scale_w, void* __restrict__ masks_v) {
+                     float scale_w, void* __restrict__ masks_v, long long mask_img_stride_bytes) {
+  // blockIdx.z = image of the batch (yb_postprocess_batch); every per-image tensor is dense
+  proto += (size_t)blockIdx.z * ph * pw * k;
+  coef += (size_t)blockIdx.z * n * k;
+  box += (size_t)blockIdx.z * n * 4;
+  masks_v = reinterpret_cast<unsigned char*>(masks_v) + (size_t)blockIdx.z * mask_img_stride_bytes;
   extern __shared__ unsigned char smem_raw[];
   ColTab* coltab = reinterpret_cast<ColTab*>(smem_raw);                 // [out_w]
   float* mrows = reinterpret_cast<float*>(coltab + out_w);               // [max_rows][pw]
@@ -203,7 +208,7 @@ mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
 // boxes: sanitize_coordinates(cast=False) for x with w, y with h, then .long() (output_utils.py:97-99)
 __global__ void boxes_px_kernel(const float* __restrict__ box, int n, int out_h, int out_w,
                                 int64_t* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;   // n = total boxes over the batch
   if (i >= n) return;
   float x1, x2, y1, y2;
   sanitize(box[i * 4 + 0], box[i * 4 + 2], out_w, 0, &x1, &x2);
@@ -275,14 +280,15 @@ __global__ void maxpool_gather_kernel(const float* __restrict__ x, int HW, int C
 void launch_mask_assembly(const float* proto, int ph, int pw, int k, const float* coef,
                           const float* box, int n, int out_h, int out_w, int crop, int mask_format,
                           void* masks, int64_t* boxes_px, float* proto_masks, cudaStream_t stream,
-                          LaunchCounter* lc) {
-  if (n <= 0) return;
+                          LaunchCounter* lc, int batch) {
+  if (n <= 0 || batch <= 0) return;
+  YB_REQUIRE(batch == 1 || proto_masks == nullptr, "mask_assembly: proto_masks output is per image");
   YB_REQUIRE(k % 4 == 0 && k <= 128, "mask_assembly: mask_dim must be a multiple of 4 and <= 128");
   YB_REQUIRE(out_h > 0 && out_w > 0 && ph > 0 && pw > 0, "mask_assembly: bad sizes");
   const float scale_h = (float)ph / (float)out_h;
   const float scale_w = (float)pw / (float)out_w;
   if (boxes_px) {
-    boxes_px_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(box, n, out_h, out_w, boxes_px);
+    boxes_px_kernel<<<ceil_div(n * batch, 128), 128, 0, stream>>>(box, n * batch, out_h, out_w, boxes_px);
     YB_CHECK_LAUNCH();
     if (lc) lc->n++;
   }
@@ -306,8 +312,12 @@ void launch_mask_assembly(const float* proto, int ph, int pw, int k, const float
     const int bands = ceil_div(out_h, band);
     // enough CTAs for >= 2 waves of 148 SMs, but keep groups large for prototype reuse in L1
     int group = n;
-    while (group > 1 && (int64_t)bands * ceil_div(n, group) < 2 * 148) group = (group + 1) / 2;
-    dim3 grid(bands, ceil_div(n, group));
+    while (group > 1 && (int64_t)bands * ceil_div(n, group) * batch < 2 * 148) group = (group + 1) / 2;
+    dim3 grid(bands, ceil_div(n, group), batch);
+    const size_t plane = (size_t)out_h * out_w;
+    const long long img_stride = (long long)n * (mask_format == YB_MASK_F32 ? plane * 4
+                                                : mask_format == YB_MASK_U8 ? plane
+                                                                            : (size_t)out_h * ((out_w + 31) / 32) * 4);
 #define YB_LAUNCH_MASK(FMT)                                                                       \
   do {                                                                                            \
     if (smem > 48 * 1024)                                                                         \
@@ -315,7 +325,7 @@ void launch_mask_assembly(const float* proto, int ph, int pw, int k, const float
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     mask_assembly_kernel<FMT><<<grid, MT, smem, stream>>>(proto, ph, pw, k, coef, box, n, out_h,  \
                                                          out_w, crop, band, group, max_rows,     \
-                                                         scale_h, scale_w, masks);               \
+                                                         scale_h, scale_w, masks, img_stride);   \
   } while (0)
     switch (mask_format) {
       case YB_MASK_F32: YB_LAUNCH_MASK(YB_MASK_F32); break;

@@ -80,6 +80,34 @@ def assemble_masks(proto, coef, boxes, h, w, crop_masks=True, mask_format="f32",
     return masks, boxes_px, pm
 
 
+def assemble_masks_batch(proto, coef, boxes, h, w, crop_masks=True, mask_format="f32", masks_out=None,
+                         boxes_out=None):
+    """Whole batch in one launch: proto [B,ph,pw,k], coef [B,n,k], boxes [B,n,4] (padded rows, e.g.
+    Yolact.infer_padded's outputs) -> (masks [B,n,...], boxes_px int64 [B,n,4]).  No host sync."""
+    if not proto.is_cuda:
+        raise _lib.YbError("yolact_b200.postprocess runs on CUDA (B200) only; there is no CPU path.")
+    lib = _lib.load()
+    dev = proto.device
+    B, ph, pw, k = (int(s) for s in proto.shape)
+    n = int(coef.shape[1])
+    proto, coef, boxes = proto.contiguous().float(), coef.contiguous().float(), boxes.contiguous().float()
+    fmt = _FORMATS[mask_format]
+    if masks_out is not None:
+        masks = masks_out
+    elif fmt == _lib.YB_MASK_F32:
+        masks = torch.empty(B, n, h, w, dtype=torch.float32, device=dev)
+    elif fmt == _lib.YB_MASK_U8:
+        masks = torch.empty(B, n, h, w, dtype=torch.uint8, device=dev)
+    else:
+        masks = torch.empty(B, n, h, (w + 31) // 32, dtype=torch.int32, device=dev)
+    boxes_px = boxes_out if boxes_out is not None else torch.empty(B, n, 4, dtype=torch.int64, device=dev)
+    if n > 0 and B > 0:
+        _lib.check(lib.yb_postprocess_batch(_ops_handle(dev, k), _lib.ptr(proto), ph, pw, k, _lib.ptr(coef),
+                                            _lib.ptr(boxes), n, B, h, w, 1 if crop_masks else 0, fmt, _lib.ptr(masks),
+                                            _lib.ptr(boxes_px), _lib.current_stream(dev)), "yb_postprocess_batch")
+    return masks, boxes_px
+
+
 def postprocess(det_output, w, h, batch_idx=0, interpolation_mode='bilinear', visualize_lincomb=False,
                 crop_masks=True, score_threshold=0, mask_format="f32"):
     cfg = _config.cfg
