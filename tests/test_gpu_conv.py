@@ -110,12 +110,11 @@ TC_CASES = [
 
 
 # kernel scheduling variants: default heuristic; few persistent CTAs (several tiles per CTA, TMEM double
-# buffering); CTA pairs with weight multicast (incl. an odd number of M tiles -> one dummy tile)
+# buffering) with the default and with a narrow N tile
 TC_MODES = {
     "default": {},
     "persistent_grid3": {"YB_CONV2D_GRID": "3"},
-    "cluster2": {"YB_CONV2D_CLUSTER": "2"},
-    "cluster2_grid4_bn64": {"YB_CONV2D_CLUSTER": "2", "YB_CONV2D_GRID": "4", "YB_CONV2D_BN": "64"},
+    "persistent_grid5_bn64": {"YB_CONV2D_GRID": "5", "YB_CONV2D_BN": "64"},
 }
 
 

@@ -91,7 +91,7 @@ struct yb_handle {
   bool finalized = false;
   bool use_graphs = true;
   bool profiling = false;
-  bool clusters = true;     // YB_CLUSTERS=0: never use CTA pairs with weight multicast
+  bool clusters = false;    // YB_CLUSTERS=1: let the autotuner try CTA pairs with weight multicast (experimental)
   bool fuse_heads = true;   // YB_FUSE_HEADS=0: three separate head convs per level
   bool pdl = false;         // YB_PDL=1: programmatic dependent launch between consecutive tcgen05 convs
   bool stem_on_tc = true;   // YB_STEM_TC=0 falls back to the SIMT stem
