@@ -45,6 +45,8 @@ struct alignas(64) TcParams {
   int res_off;          // byte offset of the residual staging buffers inside dynamic smem
   int m_tiles, n_tiles; // tile = m_tile * n_tiles + n_tile
   int acc_stages;       // TMEM accumulator buffers (2 when a CTA processes several tiles)
+  int mrep;             // 1, or 2: each work unit is TWO adjacent M tiles sharing every weight tile in shared memory
+                        // (halves the B-operand bytes an SM must ingest per MMA cycle; 2 TMEM accumulators)
   int cluster;          // 1, or 2: CTA pairs (adjacent M tiles, same N tile) share each weight tile via TMA multicast
   int nbatch;           // batch extent of the tile space (1 when flattened)
   int nseg;             // > 0: output channels are split over several fp32 tensors (fused prediction head)
@@ -193,10 +195,10 @@ struct TileCoord {
 // pt indexes (M-tile group, N tile); a cluster of `p.cluster` CTAs takes the group's consecutive M tiles.
 // An M tile past the end (odd tile count) decodes to batch index >= nbatch: every TMA access is then out of
 // bounds (zero-filled loads, clipped stores), so the CTA still takes part in the multicast protocol.
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int pt, int BN, int rank) {
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int pt, int BN, int rank) {   // rank: index inside the group
   TileCoord t;
   const int nt = pt % p.n_tiles;
-  int m = (pt / p.n_tiles) * p.cluster + rank;
+  int m = (pt / p.n_tiles) * (p.cluster * p.mrep) + rank;
   const int tx = m % p.tiles_x;
   m /= p.tiles_x;
   const int ty = m % p.tiles_y;
@@ -211,7 +213,6 @@ template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS)
 tc_conv_kernel(const __grid_constant__ TcParams p) {
   constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 
   extern __shared__ uint8_t smem_dyn[];
   __shared__ uint64_t full_bar[MAX_STAGES];
@@ -232,8 +233,11 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   const int stages = p.stages;
   const int num_kb = p.ntaps * p.kchunks;
   const int cl = p.cluster;
+  const int mrep = p.mrep;                 // M tiles per work unit (cl > 1 implies mrep == 1)
+  const int grp = cl * mrep;
   const int rank = (cl > 1) ? (int)cluster_ctarank() : 0;
-  const int num_tiles = ((p.m_tiles + cl - 1) / cl) * p.n_tiles;   // tile groups x N tiles
+  const int num_tiles = ((p.m_tiles + grp - 1) / grp) * p.n_tiles;   // tile groups x N tiles
+  const int STAGE_BYTES = mrep * A_STAGE_BYTES + B_STAGE_BYTES;
   const int tile0 = (int)blockIdx.x / cl, tile_step = (int)gridDim.x / cl;
   const int acc_stages = p.acc_stages;
 
@@ -268,10 +272,11 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)p.a_box_bytes + (uint32_t)B_STAGE_BYTES;
+      const uint32_t tx_bytes = (uint32_t)(mrep * p.a_box_bytes) + (uint32_t)B_STAGE_BYTES;
       uint32_t kbg = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const TileCoord tc_ = decode_tile(p, tile, BN, rank);
+        const TileCoord tc1 = decode_tile(p, tile, BN, mrep > 1 ? 1 : rank);   // second M tile of the unit
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)stages;
           const uint32_t it = kbg / (uint32_t)stages;
@@ -279,10 +284,13 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           const int tap = kb / p.kchunks;
           const int kc = kb - tap * p.kchunks;
           uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
-          uint8_t* sb = sa + A_STAGE_BYTES;
+          uint8_t* sb = sa + mrep * A_STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], tx_bytes);
           tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[s], kc * BLOCK_K, tc_.x0 + p.tap_dx[tap],
                       tc_.y0 + p.tap_dy[tap], tc_.b);
+          if (mrep > 1)
+            tma_load_4d(sa + A_STAGE_BYTES, &p.tmA[p.tap_map[tap]], &full_bar[s], kc * BLOCK_K, tc1.x0 + p.tap_dx[tap],
+                        tc1.y0 + p.tap_dy[tap], tc1.b);
           if (cl > 1) {
             // this CTA fetches its half of the weight tile and multicasts it to the pair
             tma_load_3d_mcast(sb + rank * (B_STAGE_BYTES / 2), &p.tmB, &full_bar[s], kc * BLOCK_K,
@@ -302,20 +310,23 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
         const uint32_t use = t / (uint32_t)acc_stages;
         mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
+        const uint32_t tmem_d = tmem_base + acc * (uint32_t)(mrep * BN);
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)stages;
           const uint32_t it = kbg / (uint32_t)stages;
           mbar_wait(&full_bar[s], it & 1u);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
-          const uint64_t da = make_sw128_desc(sa);
+          const uint32_t sb = sa + (uint32_t)(mrep * A_STAGE_BYTES);
           const uint64_t db = make_sw128_desc(sb);
+          for (int hh = 0; hh < mrep; ++hh) {   // both M tiles of the unit consume the same weight tile
+            const uint64_t da = make_sw128_desc(sa + (uint32_t)(hh * A_STAGE_BYTES));
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 field
-            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 field
+              umma_f16(tmem_d + (uint32_t)(hh * BN), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc,
+                       (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
           if (cl > 1)
             umma_commit_mcast(&empty_bar[s], (uint16_t)0x3);   // ... in both CTAs of the pair
@@ -337,11 +348,11 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 
     // residual chunk stream (epi_tma only): global chunk g lives in res buffer g&1; the issuer keeps it
     // two chunks ahead of the consumer, across tile boundaries.  (pf_tile, pf_c) = next chunk to fetch.
-    int pf_tile = tile0, pf_c = 0;
+    int pf_tile = tile0, pf_c = 0, pf_h = 0;
     uint32_t pf_g = 0;
     auto prefetch_res = [&]() {
       if (pf_tile >= num_tiles) return;
-      const TileCoord tcp = decode_tile(p, pf_tile, BN, rank);
+      const TileCoord tcp = decode_tile(p, pf_tile, BN, mrep > 1 ? pf_h : rank);
       const int nch = (min(BN, p.Cout - tcp.n0) + 63) >> 6;
       const uint32_t buf = pf_g & 1u;
       mbar_expect_tx(&res_full_bar[buf], (uint32_t)p.a_box_bytes);
@@ -349,7 +360,10 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       ++pf_g;
       if (++pf_c >= nch) {
         pf_c = 0;
-        pf_tile += tile_step;
+        if (++pf_h >= mrep) {
+          pf_h = 0;
+          pf_tile += tile_step;
+        }
       }
     };
     if (p.epi_tma && has_res && issuer) {
@@ -359,19 +373,23 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 
     uint32_t t = 0, g = 0;  // local tile counter, global staged-chunk counter
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++t) {
-      const TileCoord tc_ = decode_tile(p, tile, BN, rank);
-      const int x0 = tc_.x0, y0 = tc_.y0, b = tc_.b, n0 = tc_.n0;
       const uint32_t acc = t % (uint32_t)acc_stages;
       const uint32_t use = t / (uint32_t)acc_stages;
-      const uint32_t tmem_acc = tmem_base + acc * (uint32_t)BN + ((uint32_t)(quad * 32) << 16);
-      // bias of this tile's BN output channels -> shared memory (read back as broadcast float4)
+      // bias of this unit's BN output channels -> shared memory (read back as broadcast float4)
       {
+        const int n0u = decode_tile(p, tile, BN, rank).n0;
         const int et = threadIdx.x - 64;   // 0..127 within the epilogue warps
-        for (int j = et; j < BN; j += 128) sbias[j] = (p.bias && n0 + j < p.Cout) ? __ldg(p.bias + n0 + j) : 0.f;
+        for (int j = et; j < BN; j += 128) sbias[j] = (p.bias && n0u + j < p.Cout) ? __ldg(p.bias + n0u + j) : 0.f;
       }
       mbar_wait(&tmem_full_bar[acc], use & 1u);
       tc_fence_after();
       epi_bar_sync();   // sbias visible; also: the previous tile's readers of sbias are long done
+
+      for (int hh = 0; hh < mrep; ++hh) {   // the unit's M tiles, one TMEM accumulator each
+      const bool last_h = (hh == mrep - 1);
+      const TileCoord tc_ = decode_tile(p, tile, BN, mrep > 1 ? hh : rank);
+      const int x0 = tc_.x0, y0 = tc_.y0, b = tc_.b, n0 = tc_.n0;
+      const uint32_t tmem_acc = tmem_base + (acc * (uint32_t)mrep + (uint32_t)hh) * (uint32_t)BN + ((uint32_t)(quad * 32) << 16);
 
       if (p.epi_tma) {
         // ---- staged epilogue: TMEM -> regs -> (+bias, +residual from smem, act) -> swizzled smem tile
@@ -406,10 +424,10 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             default: epi_chunk<ACT_NONE, false>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw); break;
           }
           fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-          if (c == nchunks - 1) tc_fence_before();
+          if (c == nchunks - 1 && last_h) tc_fence_before();
           epi_bar_sync();
           if (issuer) {
-            if (c == nchunks - 1) mbar_arrive(&tmem_empty_bar[acc]);  // all 128 threads have read their rows
+            if (c == nchunks - 1 && last_h) mbar_arrive(&tmem_empty_bar[acc]);  // all 128 threads have read their rows
             tma_store_4d(&p.tmY, out_tile, nbase, x0, y0, b);
             bulk_commit();
             if (has_res) prefetch_res();   // everyone is done reading res_tile[buf]: refill it two chunks ahead
@@ -475,8 +493,9 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
         }
         tc_fence_before();
         epi_bar_sync();
-        if (issuer) mbar_arrive(&tmem_empty_bar[acc]);
+        if (issuer && last_h) mbar_arrive(&tmem_empty_bar[acc]);
       }
+      }   // hh
     }
     if (p.epi_tma && issuer) bulk_wait_read<0>();  // smem must outlive the bulk reads
     (void)nchunks_full;
@@ -562,7 +581,7 @@ bool tc_conv_supported(const ConvProblem& p) {
 }
 
 TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override, int stages_override,
-                                int grid_override, int cluster_override) {
+                                int grid_override, int cluster_override, int mrep_override) {
   YB_REQUIRE(tc_conv_supported(p), "tc_conv: unsupported problem");
   YB_REQUIRE(p.Ho == (p.H + 2 * p.pad - p.KH) / p.stride + 1, "tc_conv: bad Ho");
   YB_REQUIRE(p.Wo == (p.W + 2 * p.pad - p.KW) / p.stride + 1, "tc_conv: bad Wo");
@@ -640,20 +659,22 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
       plan->BN = std::max(bn_override, bn_min);
   }
   const int BN = plan->BN;
-  const int stage_bytes = A_STAGE_BYTES + BN * BLOCK_K * 2;
+  int stage_bytes = A_STAGE_BYTES + BN * BLOCK_K * 2;
   // ---- persistent grid + shared-memory layout: [pipeline stages][2 x 16 KB out tiles][2 x 16 KB residual tiles]
   q.m_tiles = (int)m_tiles;
   q.n_tiles = ceil_div(p.Cout, BN);
   q.nbatch = Bv;
   q.cluster = (cluster_override == 2 && q.m_tiles >= 2) ? 2 : 1;
+  q.mrep = (mrep_override == 2 && q.cluster == 1 && q.m_tiles >= 2) ? 2 : 1;
   const int cl = q.cluster;
-  const int num_tiles = ceil_div(q.m_tiles, cl) * q.n_tiles;   // tile groups x N tiles
+  const int num_tiles = ceil_div(q.m_tiles, cl * q.mrep) * q.n_tiles;   // tile groups x N tiles
   int grid = std::min(num_tiles, std::max(1, (grid_override > 0 ? grid_override : 148) / cl)) * cl;
-  q.acc_stages = (grid < num_tiles * cl) ? 2 : 1;
+  q.acc_stages = (grid < num_tiles * cl && q.mrep * BN * 2 <= 512) ? 2 : 1;
   int tmem_cols = 32;
-  while (tmem_cols < q.acc_stages * BN) tmem_cols *= 2;
+  while (tmem_cols < q.acc_stages * q.mrep * BN) tmem_cols *= 2;
   q.tmem_cols = tmem_cols;
   const int tiles_per_cta = ceil_div(num_tiles * cl, grid);
+  stage_bytes = q.mrep * A_STAGE_BYTES + BN * BLOCK_K * 2;
   const int out_bytes = 2 * A_STAGE_BYTES;
   const int res_bytes = (q.epi_tma && p.residual) ? 2 * A_STAGE_BYTES : 0;
   int stages = std::min(MAX_STAGES, (200 * 1024 - out_bytes - res_bytes) / stage_bytes);
@@ -765,6 +786,7 @@ int tc_conv_plan_bn(const TcConvPlan* plan) { return plan->BN; }
 int tc_conv_plan_stages(const TcConvPlan* plan) { return plan->prm.stages; }
 int tc_conv_plan_grid(const TcConvPlan* plan) { return (int)plan->grid.x; }
 int tc_conv_plan_cluster(const TcConvPlan* plan) { return plan->prm.cluster; }
+int tc_conv_plan_mrep(const TcConvPlan* plan) { return plan->prm.mrep; }
 
 template <int BN>
 static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
