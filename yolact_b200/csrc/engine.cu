@@ -4,6 +4,7 @@
 #include "engine.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -156,7 +157,7 @@ struct NetBuilder {
   int lane = 0;
   void push(Op& op) {
     op.lane = lane;
-    push(op);
+    ex->ops.push_back(op);
   }
 
   size_t esize(const Act& a) const { return a.f32 ? 4 : (f16 ? 2 : 4); }
@@ -857,6 +858,18 @@ Executor* yb_handle::get_executor(int B, int H, int W) {
 }
 
 static void run_ops(yb_handle* h, Executor* ex, cudaStream_t stream, bool branches = false) {
+  static const bool trace = getenv("YB_TRACE") != nullptr;   // debug: name every op and sync after it
+  if (trace) {
+    for (auto& op : ex->ops) {
+      fprintf(stderr, "[yb] %s ...", op.name.c_str());
+      fflush(stderr);
+      op.fn(stream);
+      cudaError_t e = cudaStreamSynchronize(stream);
+      fprintf(stderr, " %s\n", e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+      fflush(stderr);
+    }
+    return;
+  }
   if (!branches || ex->fork_index == 0 || ex->fork_index >= ex->ops.size()) {
     for (auto& op : ex->ops) op.fn(stream);
     return;

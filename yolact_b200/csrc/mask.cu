@@ -146,7 +146,10 @@ mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
       // (16-byte stores for fp32, 4-byte for uint8); quads may straddle a row boundary.
       const size_t band_off = (size_t)d * plane + (size_t)y0 * out_w;
       const int L = (y1 - y0) * out_w;
-      const int lead = (int)(band_off & 3);
+      // elements to the previous 4-element boundary of the ACTUAL address (the per-image offset of a
+      // batched call need not be 16-byte aligned)
+      const size_t esz = (FORMAT == YB_MASK_F32) ? 4 : 1;
+      const int lead = (int)(((reinterpret_cast<uintptr_t>(masks_v) / esz) + band_off) & 3);
       const int nq = (L + lead + 3) >> 2;
       for (int q = tid; q < nq; q += MT) {
         const int i0 = 4 * q - lead;
