@@ -115,8 +115,6 @@ TC_MODES = {
     "default": {},
     "persistent_grid3": {"YB_CONV2D_GRID": "3"},
     "persistent_grid5_bn64": {"YB_CONV2D_GRID": "5", "YB_CONV2D_BN": "64"},
-    "mrep2": {"YB_CONV2D_MREP": "2"},
-    "mrep2_grid3_bn128": {"YB_CONV2D_MREP": "2", "YB_CONV2D_GRID": "3", "YB_CONV2D_BN": "128"},
 }
 
 

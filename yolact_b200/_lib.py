@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libyolact_b200.so")
+LIB_PATH = os.environ.get("YB_LIB") or os.path.join(_HERE, "libyolact_b200.so")
 
 
 class YbConfig(ctypes.Structure):

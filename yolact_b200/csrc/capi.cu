@@ -130,8 +130,6 @@ int yb_create(const yb_config* cfg, int device, yb_handle** out) {
   if (const char* pd = getenv("YB_PDL")) h->pdl = (atoi(pd) != 0);
   if (const char* fh = getenv("YB_FUSE_HEADS")) h->fuse_heads = (atoi(fh) != 0);
   if (const char* br = getenv("YB_BRANCHES")) h->multi_stream = (atoi(br) != 0);
-  if (const char* cl = getenv("YB_CLUSTERS")) h->clusters = (atoi(cl) != 0);
-  if (const char* mr = getenv("YB_MREP2")) h->mrep2 = (atoi(mr) != 0);
   if (!h->ops_only) {
     YB_REQUIRE(cfg->backbone == YB_BACKBONE_RESNET || cfg->backbone == YB_BACKBONE_DARKNET, "unknown backbone");
     YB_REQUIRE(cfg->num_stages >= 4 && cfg->num_stages <= 5, "num_stages must be 4 or 5");
@@ -519,11 +517,9 @@ int yb_conv2d(yb_handle* h, const float* d_x, const float* h_w, const float* h_b
     __half* wd = (__half*)tp.get(pk.size() * 2);
     YB_CHECK_CUDA(cudaMemcpy(wd, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
     {
-      const char* ce = getenv("YB_CONV2D_CLUSTER");
       const char* be = getenv("YB_CONV2D_BN");
       const char* ge = getenv("YB_CONV2D_GRID");
-      const char* me = getenv("YB_CONV2D_MREP");
-      plan = tc_conv_plan_create(p, wd, be ? atoi(be) : 0, 0, ge ? atoi(ge) : 0, ce ? atoi(ce) : 0, me ? atoi(me) : 0);
+      plan = tc_conv_plan_create(p, wd, be ? atoi(be) : 0, 0, ge ? atoi(ge) : 0);
     }
     run = [&]() { launch_tc_conv(plan, s, &h->lc); };
   } else if (precision == 2) {

@@ -249,7 +249,7 @@ struct NetBuilder {
       TcConvPlan* plan = autotune_tc(p, w.w_tc);
       ex->plans.push_back(plan);
       op.name += " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) + " st=" + std::to_string(tc_conv_plan_stages(plan)) +
-                 " g=" + std::to_string(tc_conv_plan_grid(plan)) + " cl=" + std::to_string(tc_conv_plan_cluster(plan)) + " m=" + std::to_string(tc_conv_plan_mrep(plan));
+                 " g=" + std::to_string(tc_conv_plan_grid(plan));
       tc_conv_plan_set_pdl(plan, h->pdl ? 1 : 0);
       op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
     } else {
@@ -413,8 +413,7 @@ struct NetBuilder {
     op.is_conv = true;
     op.name = hn + ".bbox+conf+mask " + std::to_string(in.C) + "->" + std::to_string(w.Cout) + " k3s1 " +
               std::to_string(in.H) + "x" + std::to_string(in.W) + " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) +
-              " st=" + std::to_string(tc_conv_plan_stages(plan)) + " g=" + std::to_string(tc_conv_plan_grid(plan)) +
-              " cl=" + std::to_string(tc_conv_plan_cluster(plan)) + " m=" + std::to_string(tc_conv_plan_mrep(plan));
+              " st=" + std::to_string(tc_conv_plan_stages(plan)) + " g=" + std::to_string(tc_conv_plan_grid(plan));
     op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
     push(op);
   }
@@ -431,7 +430,7 @@ struct NetBuilder {
                              (p.y_f32 ? "f" : "h") + std::to_string(p.nseg) + "," + std::to_string(p.y_pix_stride) + "," + std::to_string((long long)p.y_batch_stride);
     auto it = h->tune_cache.find(tkey);
     if (it != h->tune_cache.end())
-      return tc_conv_plan_create(p, w, it->second[0], it->second[1], it->second[2], it->second[3], it->second[4]);
+      return tc_conv_plan_create(p, w, it->second[0], it->second[1], it->second[2]);
     const int bns[4] = {256, 128, 64, 32};
     const int sts[3] = {0, 3, 2};
     const int grids[3] = {148, 296, 1 << 30};
@@ -443,17 +442,11 @@ struct NetBuilder {
     YB_CHECK_CUDA(cudaEventCreate(&e1));
     for (int bi = 0; bi < 4; ++bi)
       for (int si = 0; si < 3; ++si)
-        for (int gi = 0; gi < 9; ++gi) {
+        for (int gi = 0; gi < 3; ++gi) {
           if (bns[bi] > 64 && bns[bi] >= 2 * p.Cout) continue;
-          // variants: plain | two M tiles per unit sharing the weight tile | CTA pairs with weight multicast
-          const int variant = gi / 3;
-          if (variant == 1 && !h->mrep2) continue;
-          if (variant == 2 && !h->clusters) continue;
-          TcConvPlan* cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi % 3], variant == 2 ? 2 : 1,
-                                                 variant == 1 ? 2 : 1);
+          TcConvPlan* cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi]);
           const std::string ck = std::to_string(tc_conv_plan_bn(cand)) + "/" + std::to_string(tc_conv_plan_stages(cand)) +
-                                 "/" + std::to_string(tc_conv_plan_grid(cand)) + "/" + std::to_string(tc_conv_plan_cluster(cand)) +
-                                 "/" + std::to_string(tc_conv_plan_mrep(cand));
+                                 "/" + std::to_string(tc_conv_plan_grid(cand));
           if (!seen.insert(ck).second) {  // overrides were clamped to an already-timed configuration
             tc_conv_plan_destroy(cand);
             continue;
@@ -484,8 +477,7 @@ struct NetBuilder {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     YB_REQUIRE(best != nullptr, "autotune: no candidate");
-    h->tune_cache[tkey] = {tc_conv_plan_bn(best), tc_conv_plan_stages(best), tc_conv_plan_grid(best),
-                           tc_conv_plan_cluster(best), tc_conv_plan_mrep(best)};
+    h->tune_cache[tkey] = {tc_conv_plan_bn(best), tc_conv_plan_stages(best), tc_conv_plan_grid(best)};
     return best;
   }
 };

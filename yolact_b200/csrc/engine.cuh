@@ -91,8 +91,6 @@ struct yb_handle {
   bool finalized = false;
   bool use_graphs = true;
   bool profiling = false;
-  bool mrep2 = true;        // YB_MREP2=0: never pair M tiles on one weight tile
-  bool clusters = false;    // YB_CLUSTERS=1: let the autotuner try CTA pairs with weight multicast (experimental)
   bool fuse_heads = true;   // YB_FUSE_HEADS=0: three separate head convs per level
   bool pdl = false;         // YB_PDL=1: programmatic dependent launch between consecutive tcgen05 convs
   bool stem_on_tc = true;   // YB_STEM_TC=0 falls back to the SIMT stem
@@ -103,7 +101,7 @@ struct yb_handle {
   std::map<std::string, yb::ConvW> convs;
   std::map<std::string, std::unique_ptr<yb::Executor>> execs;
   std::vector<void*> weight_allocs;
-  std::map<std::string, std::array<int, 5>> tune_cache;  // layer shape -> (BN, stages, grid, cluster, mrep) from the autotuner
+  std::map<std::string, std::array<int, 3>> tune_cache;  // layer shape -> (BN, stages, grid) from the autotuner
   yb::Executor* last_exec = nullptr;
   // standalone op workspaces
   void* detect_ws = nullptr;

@@ -46,15 +46,10 @@ void launch_simt_conv(const ConvProblem& p, const void* w, int types, cudaStream
 // ---- tcgen05 implicit-GEMM convolution (fp16 in, fp32 accumulate) ----------------------------
 struct TcConvPlan;  // opaque: tensor maps + tiling; built once per (layer, shape, pointers)
 // w_packed: device half [KH*KW][CoutPad][Cin], CoutPad = round_up(Cout,16). Requires Cin % 64 == 0.
-// bn_override in {32,64,128,256} / stages_override > 0 pin the N tile / pipeline depth (autotuner); 0 = heuristic
+// bn_override in {32,64,128,256} / stages_override > 0 pin the N tile / pipeline depth (autotuner); 0 = heuristic.
 // grid_override > 0 caps the number of (persistent) CTAs; default 148 = one per SM.
-// mrep_override == 2: a work unit is two adjacent M tiles sharing each weight tile in shared memory.
-// cluster_override == 2 (experimental): CTA pairs share each weight tile through TMA multicast (halves the L2 traffic of B)
 TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override = 0,
-                                int stages_override = 0, int grid_override = 0, int cluster_override = 0,
-                                int mrep_override = 0);
-int tc_conv_plan_cluster(const TcConvPlan* plan);
-int tc_conv_plan_mrep(const TcConvPlan* plan);
+                                int stages_override = 0, int grid_override = 0);
 int tc_conv_plan_grid(const TcConvPlan* plan);
 void tc_conv_plan_set_pdl(TcConvPlan* plan, int enable);   // programmatic dependent launch (prologue overlap)
 int tc_conv_plan_bn(const TcConvPlan* plan);

@@ -45,10 +45,6 @@ struct alignas(64) TcParams {
   int res_off;          // byte offset of the residual staging buffers inside dynamic smem
   int m_tiles, n_tiles; // tile = m_tile * n_tiles + n_tile
   int acc_stages;       // TMEM accumulator buffers (2 when a CTA processes several tiles)
-  int mrep;             // 1, or 2: each work unit is TWO adjacent M tiles sharing every weight tile in shared memory
-                        // (halves the B-operand bytes an SM must ingest per MMA cycle; 2 TMEM accumulators)
-  int cluster;          // 1, or 2: CTA pairs (adjacent M tiles, same N tile) share each weight tile via TMA multicast
-  int nbatch;           // batch extent of the tile space (1 when flattened)
   int nseg;             // > 0: output channels are split over several fp32 tensors (fused prediction head)
   int seg_begin[3], seg_end[3], seg_ps[3], seg_act[3];
   long long seg_bs[3];
@@ -163,42 +159,13 @@ __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1
   }
 }
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// weight tile half -> the same shared-memory offset of BOTH CTAs of the pair, completing tx on both full barriers
-__device__ __forceinline__ void tma_load_3d_mcast(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2,
-                                                  uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
-      : "memory");
-}
-// arrive on the barrier at this shared-memory offset in every CTA of `mask` once the preceding MMAs are done
-__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
-
 struct TileCoord {
   int b, x0, y0, n0;
 };
-// pt indexes (M-tile group, N tile); a cluster of `p.cluster` CTAs takes the group's consecutive M tiles.
-// An M tile past the end (odd tile count) decodes to batch index >= nbatch: every TMA access is then out of
-// bounds (zero-filled loads, clipped stores), so the CTA still takes part in the multicast protocol.
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int pt, int BN, int rank) {   // rank: index inside the group
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, int BN) {
   TileCoord t;
-  const int nt = pt % p.n_tiles;
-  int m = (pt / p.n_tiles) * (p.cluster * p.mrep) + rank;
+  const int nt = tile % p.n_tiles;
+  int m = tile / p.n_tiles;
   const int tx = m % p.tiles_x;
   m /= p.tiles_x;
   const int ty = m % p.tiles_y;
@@ -213,6 +180,7 @@ template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS)
 tc_conv_kernel(const __grid_constant__ TcParams p) {
   constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 
   extern __shared__ uint8_t smem_dyn[];
   __shared__ uint64_t full_bar[MAX_STAGES];
@@ -232,19 +200,13 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
   const int num_kb = p.ntaps * p.kchunks;
-  const int cl = p.cluster;
-  const int mrep = p.mrep;                 // M tiles per work unit (cl > 1 implies mrep == 1)
-  const int grp = cl * mrep;
-  const int rank = (cl > 1) ? (int)cluster_ctarank() : 0;
-  const int num_tiles = ((p.m_tiles + grp - 1) / grp) * p.n_tiles;   // tile groups x N tiles
-  const int STAGE_BYTES = mrep * A_STAGE_BYTES + B_STAGE_BYTES;
-  const int tile0 = (int)blockIdx.x / cl, tile_step = (int)gridDim.x / cl;
+  const int num_tiles = p.m_tiles * p.n_tiles;
   const int acc_stages = p.acc_stages;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], (uint32_t)cl);   // every CTA of the pair must have consumed the slot
+      mbar_init(&empty_bar[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
@@ -260,7 +222,6 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (cl > 1) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   const uint32_t tmem_base = s_tmem_base;
   // Programmatic dependent launch: everything above overlaps the tail of the previous kernel in the
   // stream; its output is only touched below this point.
@@ -272,11 +233,10 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)(mrep * p.a_box_bytes) + (uint32_t)B_STAGE_BYTES;
+      const uint32_t tx_bytes = (uint32_t)p.a_box_bytes + (uint32_t)B_STAGE_BYTES;
       uint32_t kbg = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const TileCoord tc_ = decode_tile(p, tile, BN, rank);
-        const TileCoord tc1 = decode_tile(p, tile, BN, mrep > 1 ? 1 : rank);   // second M tile of the unit
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord tc_ = decode_tile(p, tile, BN);
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)stages;
           const uint32_t it = kbg / (uint32_t)stages;
@@ -284,20 +244,11 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           const int tap = kb / p.kchunks;
           const int kc = kb - tap * p.kchunks;
           uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
-          uint8_t* sb = sa + mrep * A_STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], tx_bytes);
           tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[s], kc * BLOCK_K, tc_.x0 + p.tap_dx[tap],
                       tc_.y0 + p.tap_dy[tap], tc_.b);
-          if (mrep > 1)
-            tma_load_4d(sa + A_STAGE_BYTES, &p.tmA[p.tap_map[tap]], &full_bar[s], kc * BLOCK_K, tc1.x0 + p.tap_dx[tap],
-                        tc1.y0 + p.tap_dy[tap], tc1.b);
-          if (cl > 1) {
-            // this CTA fetches its half of the weight tile and multicasts it to the pair
-            tma_load_3d_mcast(sb + rank * (B_STAGE_BYTES / 2), &p.tmB, &full_bar[s], kc * BLOCK_K,
-                              tc_.n0 + rank * (BN / 2), tap, (uint16_t)0x3);
-          } else {
-            tma_load_3d(sb, &p.tmB, &full_bar[s], kc * BLOCK_K, tc_.n0, tap);
-          }
+          tma_load_3d(sb, &p.tmB, &full_bar[s], kc * BLOCK_K, tc_.n0, tap);
         }
       }
     }
@@ -305,33 +256,27 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       uint32_t kbg = 0, t = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++t) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
         const uint32_t acc = t % (uint32_t)acc_stages;
         const uint32_t use = t / (uint32_t)acc_stages;
         mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * (uint32_t)(mrep * BN);
+        const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)stages;
           const uint32_t it = kbg / (uint32_t)stages;
           mbar_wait(&full_bar[s], it & 1u);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint32_t sb = sa + (uint32_t)(mrep * A_STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint64_t da = make_sw128_desc(sa);
           const uint64_t db = make_sw128_desc(sb);
-          for (int hh = 0; hh < mrep; ++hh) {   // both M tiles of the unit consume the same weight tile
-            const uint64_t da = make_sw128_desc(sa + (uint32_t)(hh * A_STAGE_BYTES));
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 field
-              umma_f16(tmem_d + (uint32_t)(hh * BN), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc,
-                       (kb > 0 || k > 0) ? 1u : 0u);
-            }
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 field
+            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          if (cl > 1)
-            umma_commit_mcast(&empty_bar[s], (uint16_t)0x3);   // ... in both CTAs of the pair
-          else
-            umma_commit(&empty_bar[s]);  // frees this smem slot once the MMAs above have read it
+          umma_commit(&empty_bar[s]);  // frees this smem slot once the MMAs above have read it
         }
         umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       }
@@ -348,11 +293,11 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 
     // residual chunk stream (epi_tma only): global chunk g lives in res buffer g&1; the issuer keeps it
     // two chunks ahead of the consumer, across tile boundaries.  (pf_tile, pf_c) = next chunk to fetch.
-    int pf_tile = tile0, pf_c = 0, pf_h = 0;
+    int pf_tile = blockIdx.x, pf_c = 0;
     uint32_t pf_g = 0;
     auto prefetch_res = [&]() {
       if (pf_tile >= num_tiles) return;
-      const TileCoord tcp = decode_tile(p, pf_tile, BN, mrep > 1 ? pf_h : rank);
+      const TileCoord tcp = decode_tile(p, pf_tile, BN);
       const int nch = (min(BN, p.Cout - tcp.n0) + 63) >> 6;
       const uint32_t buf = pf_g & 1u;
       mbar_expect_tx(&res_full_bar[buf], (uint32_t)p.a_box_bytes);
@@ -360,10 +305,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       ++pf_g;
       if (++pf_c >= nch) {
         pf_c = 0;
-        if (++pf_h >= mrep) {
-          pf_h = 0;
-          pf_tile += tile_step;
-        }
+        pf_tile += gridDim.x;
       }
     };
     if (p.epi_tma && has_res && issuer) {
@@ -372,24 +314,20 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
     }
 
     uint32_t t = 0, g = 0;  // local tile counter, global staged-chunk counter
-    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++t) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const TileCoord tc_ = decode_tile(p, tile, BN);
+      const int x0 = tc_.x0, y0 = tc_.y0, b = tc_.b, n0 = tc_.n0;
       const uint32_t acc = t % (uint32_t)acc_stages;
       const uint32_t use = t / (uint32_t)acc_stages;
-      // bias of this unit's BN output channels -> shared memory (read back as broadcast float4)
+      const uint32_t tmem_acc = tmem_base + acc * (uint32_t)BN + ((uint32_t)(quad * 32) << 16);
+      // bias of this tile's BN output channels -> shared memory (read back as broadcast float4)
       {
-        const int n0u = decode_tile(p, tile, BN, rank).n0;
         const int et = threadIdx.x - 64;   // 0..127 within the epilogue warps
-        for (int j = et; j < BN; j += 128) sbias[j] = (p.bias && n0u + j < p.Cout) ? __ldg(p.bias + n0u + j) : 0.f;
+        for (int j = et; j < BN; j += 128) sbias[j] = (p.bias && n0 + j < p.Cout) ? __ldg(p.bias + n0 + j) : 0.f;
       }
       mbar_wait(&tmem_full_bar[acc], use & 1u);
       tc_fence_after();
       epi_bar_sync();   // sbias visible; also: the previous tile's readers of sbias are long done
-
-      for (int hh = 0; hh < mrep; ++hh) {   // the unit's M tiles, one TMEM accumulator each
-      const bool last_h = (hh == mrep - 1);
-      const TileCoord tc_ = decode_tile(p, tile, BN, mrep > 1 ? hh : rank);
-      const int x0 = tc_.x0, y0 = tc_.y0, b = tc_.b, n0 = tc_.n0;
-      const uint32_t tmem_acc = tmem_base + (acc * (uint32_t)mrep + (uint32_t)hh) * (uint32_t)BN + ((uint32_t)(quad * 32) << 16);
 
       if (p.epi_tma) {
         // ---- staged epilogue: TMEM -> regs -> (+bias, +residual from smem, act) -> swizzled smem tile
@@ -424,10 +362,10 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             default: epi_chunk<ACT_NONE, false>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw); break;
           }
           fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-          if (c == nchunks - 1 && last_h) tc_fence_before();
+          if (c == nchunks - 1) tc_fence_before();
           epi_bar_sync();
           if (issuer) {
-            if (c == nchunks - 1 && last_h) mbar_arrive(&tmem_empty_bar[acc]);  // all 128 threads have read their rows
+            if (c == nchunks - 1) mbar_arrive(&tmem_empty_bar[acc]);  // all 128 threads have read their rows
             tma_store_4d(&p.tmY, out_tile, nbase, x0, y0, b);
             bulk_commit();
             if (has_res) prefetch_res();   // everyone is done reading res_tile[buf]: refill it two chunks ahead
@@ -472,7 +410,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             const int trow = quad * 32 + rr;
             const int ty_ = trow / p.tw, tx_ = trow - ty_ * p.tw;
             const int oy = y0 + ty_, ox = x0 + tx_;
-            if (trow >= p.tw * p.th || oy >= p.Ho || ox >= p.Wo || b >= p.nbatch) continue;   // warp-uniform
+            if (trow >= p.tw * p.th || oy >= p.Ho || ox >= p.Wo) continue;   // warp-uniform
             if (lane >= nvalid) continue;
             const long long pix = (long long)oy * p.Wo + ox;
             float v = tbuf[rr * 33 + lane] + bias_l;
@@ -493,9 +431,8 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
         }
         tc_fence_before();
         epi_bar_sync();
-        if (issuer && last_h) mbar_arrive(&tmem_empty_bar[acc]);
+        if (issuer) mbar_arrive(&tmem_empty_bar[acc]);
       }
-      }   // hh
     }
     if (p.epi_tma && issuer) bulk_wait_read<0>();  // smem must outlive the bulk reads
     (void)nchunks_full;
@@ -505,7 +442,6 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (cl > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_dyn(tmem_base, (uint32_t)p.tmem_cols);
@@ -581,7 +517,7 @@ bool tc_conv_supported(const ConvProblem& p) {
 }
 
 TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override, int stages_override,
-                                int grid_override, int cluster_override, int mrep_override) {
+                                int grid_override) {
   YB_REQUIRE(tc_conv_supported(p), "tc_conv: unsupported problem");
   YB_REQUIRE(p.Ho == (p.H + 2 * p.pad - p.KH) / p.stride + 1, "tc_conv: bad Ho");
   YB_REQUIRE(p.Wo == (p.W + 2 * p.pad - p.KW) / p.stride + 1, "tc_conv: bad Wo");
@@ -659,22 +595,17 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
       plan->BN = std::max(bn_override, bn_min);
   }
   const int BN = plan->BN;
-  int stage_bytes = A_STAGE_BYTES + BN * BLOCK_K * 2;
+  const int stage_bytes = A_STAGE_BYTES + BN * BLOCK_K * 2;
   // ---- persistent grid + shared-memory layout: [pipeline stages][2 x 16 KB out tiles][2 x 16 KB residual tiles]
   q.m_tiles = (int)m_tiles;
   q.n_tiles = ceil_div(p.Cout, BN);
-  q.nbatch = Bv;
-  q.cluster = (cluster_override == 2 && q.m_tiles >= 2) ? 2 : 1;
-  q.mrep = (mrep_override == 2 && q.cluster == 1 && q.m_tiles >= 2) ? 2 : 1;
-  const int cl = q.cluster;
-  const int num_tiles = ceil_div(q.m_tiles, cl * q.mrep) * q.n_tiles;   // tile groups x N tiles
-  int grid = std::min(num_tiles, std::max(1, (grid_override > 0 ? grid_override : 148) / cl)) * cl;
-  q.acc_stages = (grid < num_tiles * cl && q.mrep * BN * 2 <= 512) ? 2 : 1;
+  const int num_tiles = q.m_tiles * q.n_tiles;
+  int grid = std::min(num_tiles, grid_override > 0 ? grid_override : 148);
+  q.acc_stages = (grid < num_tiles) ? 2 : 1;
   int tmem_cols = 32;
-  while (tmem_cols < q.acc_stages * q.mrep * BN) tmem_cols *= 2;
+  while (tmem_cols < q.acc_stages * BN) tmem_cols *= 2;
   q.tmem_cols = tmem_cols;
-  const int tiles_per_cta = ceil_div(num_tiles * cl, grid);
-  stage_bytes = q.mrep * A_STAGE_BYTES + BN * BLOCK_K * 2;
+  const int tiles_per_cta = ceil_div(num_tiles, grid);
   const int out_bytes = 2 * A_STAGE_BYTES;
   const int res_bytes = (q.epi_tma && p.residual) ? 2 * A_STAGE_BYTES : 0;
   int stages = std::min(MAX_STAGES, (200 * 1024 - out_bytes - res_bytes) / stage_bytes);
@@ -729,7 +660,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   {
     uint64_t dims[3] = {(uint64_t)p.Cin, (uint64_t)p.Cout, (uint64_t)q.ntaps};
     uint64_t str[2] = {(uint64_t)p.Cin * 2, (uint64_t)p.Cout * p.Cin * 2};
-    uint32_t box[3] = {(uint32_t)BLOCK_K, (uint32_t)(BN / q.cluster), 1};   // a pair loads half a tile per CTA
+    uint32_t box[3] = {(uint32_t)BLOCK_K, (uint32_t)BN, 1};
     encode_map_f16(&q.tmB, w_packed, 3, dims, str, box);
   }
   // ---- epilogue
@@ -785,8 +716,6 @@ void tc_conv_plan_set_pdl(TcConvPlan* plan, int enable) { plan->prm.pdl = enable
 int tc_conv_plan_bn(const TcConvPlan* plan) { return plan->BN; }
 int tc_conv_plan_stages(const TcConvPlan* plan) { return plan->prm.stages; }
 int tc_conv_plan_grid(const TcConvPlan* plan) { return (int)plan->grid.x; }
-int tc_conv_plan_cluster(const TcConvPlan* plan) { return plan->prm.cluster; }
-int tc_conv_plan_mrep(const TcConvPlan* plan) { return plan->prm.mrep; }
 
 template <int BN>
 static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
@@ -798,28 +727,17 @@ static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
     attr_set = true;
     attr_bytes = 220 * 1024;
   }
-  if (plan->prm.pdl || plan->prm.cluster > 1) {
+  if (plan->prm.pdl) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = plan->grid;
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = plan->smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    int na = 0;
-    if (plan->prm.pdl) {
-      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[na].val.programmaticStreamSerializationAllowed = 1;
-      ++na;
-    }
-    if (plan->prm.cluster > 1) {
-      attr[na].id = cudaLaunchAttributeClusterDimension;
-      attr[na].val.clusterDim.x = (unsigned)plan->prm.cluster;
-      attr[na].val.clusterDim.y = 1;
-      attr[na].val.clusterDim.z = 1;
-      ++na;
-    }
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = na;
+    cfg.numAttrs = 1;
     YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN>, plan->prm));
   } else {
     tc_conv_kernel<BN><<<plan->grid, NUM_THREADS, plan->smem_bytes, stream>>>(plan->prm);
