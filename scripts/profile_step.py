@@ -9,7 +9,7 @@ import torch
 import yolact_b200
 from oracle.weights import deterministic_state_dict, deterministic_input
 from yolact_b200.config import CONFIGS
-from yolact_b200.output_utils import assemble_masks
+from yolact_b200.output_utils import assemble_masks_batch
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="yolact_base_config")
@@ -33,8 +33,7 @@ def step():
         net.forward_conv_only(x)
         return
     box, coef, cls, score, count, proto = net.infer_padded(x)
-    for b in range(args.batch):
-        assemble_masks(proto[b], coef[b], box[b], size, size, True, "f32", masks_out=masks[b])
+    assemble_masks_batch(proto, coef, box, size, size, True, "f32", masks_out=masks)
 
 
 for _ in range(3):

@@ -313,9 +313,10 @@ void launch_mask_assembly(const float* proto, int ph, int pw, int k, const float
     }
     YB_REQUIRE(smem <= 200 * 1024, "mask_assembly: output too wide for the shared-memory tables");
     const int bands = ceil_div(out_h, band);
-    // enough CTAs for >= 2 waves of 148 SMs, but keep groups large for prototype reuse in L1
+    // ~12 resident CTAs per SM keep enough stores in flight to approach the HBM write rate; groups stay
+    // >= 8 detections so the band's prototype rows are reused from L1
     int group = n;
-    while (group > 1 && (int64_t)bands * ceil_div(n, group) * batch < 2 * 148) group = (group + 1) / 2;
+    while (group > 8 && (int64_t)bands * ceil_div(n, group) * batch < 12 * 148) group = (group + 1) / 2;
     dim3 grid(bands, ceil_div(n, group), batch);
     const size_t plane = (size_t)out_h * out_w;
     const long long img_stride = (long long)n * (mask_format == YB_MASK_F32 ? plane * 4
