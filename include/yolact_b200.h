@@ -27,6 +27,11 @@
  *   yb_postprocess     <- postprocess lincomb path (layers/output_utils.py:15-99), crop and
  *                         sanitize_coordinates (layers/box_utils.py:327-373), F.interpolate bilinear
  *   yb_maskiou         <- FastMaskIoUNet.forward (yolact.py:363-375) + gather (output_utils.py:79-83)
+ *   yb_fast_base_transform <- FastBaseTransform.forward (utils/augmentations.py:616-658)
+ *   yb_mask_iou / yb_box_iou <- mask_iou / jaccard (layers/box_utils.py:98-113, :54-79) as used by
+ *                         eval.py:435-445 (_mask_iou, _bbox_iou)
+ *   yb_mask_rle        <- pycocotools.mask.encode in Detections.add_mask (eval.py:320-330)
+ *   yb_display_blend   <- the GPU mask blend of prep_display (eval.py:186-209,226)
  *   yb_dcn_forward     <- dcn_v2_forward (external/DCNv2/src/dcn_v2.h:9-39,
  *                         src/cuda/dcn_v2_cuda.cu:42-172, src/cuda/dcn_v2_im2col_cuda.cu:125-195)
  *   yb_conv2d          <- nn.Conv2d + folded BatchNorm2d + activation (+ residual), op-level test hook
@@ -63,6 +68,20 @@ typedef enum { YB_BACKBONE_NONE = -1, YB_BACKBONE_RESNET = 0, YB_BACKBONE_DARKNE
  *   YB_PREC_F32  : fp32 activations, fp32 FMA on CUDA cores (parity mode; bit-for-bit class ids)
  *   YB_PREC_F16TC: fp16 activations/weights, fp32 accumulation on tcgen05 tensor cores (production) */
 typedef enum { YB_PREC_F32 = 0, YB_PREC_F16TC = 1 } yb_precision;
+
+/* Detect's NMS variant (the `cross_class` argument of yb_detect / yb_infer):
+ *   YB_NMS_FAST        : fast_nms          (detection.py:137-180; eval.py default)
+ *   YB_NMS_CROSS_CLASS : cc_fast_nms       (detection.py:111-135; --cross_class_nms)
+ *   YB_NMS_TRADITIONAL : traditional_nms   (detection.py:182-228 + utils/cython_nms.pyx; --fast_nms=False) */
+typedef enum { YB_NMS_FAST = 0, YB_NMS_CROSS_CLASS = 1, YB_NMS_TRADITIONAL = 2 } yb_nms_mode;
+
+/* cfg.backbone.transform of FastBaseTransform (utils/augmentations.py:645-650) */
+typedef enum {
+  YB_XFORM_NORMALIZE = 0,       /* (x - mean) / std   (all published configs except darknet53) */
+  YB_XFORM_SUBTRACT_MEANS = 1,  /* x - mean                                                     */
+  YB_XFORM_TO_FLOAT = 2,        /* x / 255            (yolact_darknet53)                        */
+  YB_XFORM_NONE = 3
+} yb_transform_mode;
 
 /* Output formats of yb_postprocess masks. */
 typedef enum {
@@ -139,7 +158,8 @@ YB_API int yb_softmax(yb_handle* h, const float* d_in, float* d_out, int64_t row
 /* ---- Detect ---------------------------------------------------------------------------------- */
 /* conf_is_logits: 1 -> softmax is fused into candidate selection (conf untouched);
  *                 0 -> conf already softmaxed (what the reference Detect receives).
- * cross_class: 0 -> fast_nms (per class), 1 -> cc_fast_nms.
+ * cross_class: a yb_nms_mode: 0 -> fast_nms (per class), 1 -> cc_fast_nms, 2 -> traditional_nms (greedy per-class
+ * NMS on boxes scaled by cfg.max_size with the +1 pixel convention; needs max_num_detections <= nms_top_k).
  * Outputs per image, padded to max_out rows (max_out >= max_num_detections, or >= nms_top_k when
  * cross_class): box [B,max_out,4] relative x1y1x2y2, coef [B,max_out,mask_dim], cls int64
  * [B,max_out] in [0,num_classes-1), score [B,max_out] descending, count int32 [B] (0 == the
@@ -177,6 +197,44 @@ YB_API int yb_postprocess_batch(yb_handle* h, const float* d_proto, int ph, int 
  * d_cls == NULL: d_maskiou [n, num_classes-1] = net(mask) (FastMaskIoUNet.forward itself). */
 YB_API int yb_maskiou(yb_handle* h, const float* d_proto_masks, int n, int ph, int pw,
                const int64_t* d_cls, float* d_maskiou, void* stream);
+
+/* ---- either side of the path: frame preparation and eval.py's result consumers ---------------------- */
+/* FastBaseTransform.forward: d_img [B,H,W,3] BGR (uint8 when img_is_u8, else fp32 0..255, the
+ * reference's `.float()` frame) -> bilinear resize to [out_h,out_w] (align_corners=False) -> transform
+ * `mode` with h_mean_bgr / h_std_bgr (3 host floats each; NULL = MEANS / STD of data/config.py:28-29)
+ * -> RGB -> d_out [B,3,out_h,out_w] fp32, i.e. exactly yb_forward's input. */
+YB_API int yb_fast_base_transform(yb_handle* h, const void* d_img, int img_is_u8, int B, int H, int W,
+                                  int out_h, int out_w, int mode, const float* h_mean_bgr,
+                                  const float* h_std_bgr, float* d_out, void* stream);
+
+/* 0/1 masks [rows, w] (YB_MASK_F32 or YB_MASK_U8; value > 0.5 -> 1) -> YB_MASK_BITS rows of
+ * ceil(w/32) words (padding bits zero).  For ground-truth masks that arrive from the host. */
+YB_API int yb_pack_mask_bits(yb_handle* h, const void* d_in, int in_format, int64_t rows, int w,
+                             uint32_t* d_bits, void* stream);
+
+/* mask_iou on bit-packed masks: a [n, words], b [m, words] (words = h * ceil(w/32), padding bits
+ * zero) -> d_iou [n, m] = |a&b| / (|a| + |b| - |a&b|), or |a&b| / |a| when iscrowd (box_utils.py:113;
+ * 0/0 = NaN like the reference). */
+YB_API int yb_mask_iou(yb_handle* h, const uint32_t* d_a, int n, const uint32_t* d_b, int m, int64_t words,
+                       int iscrowd, float* d_iou, void* stream);
+
+/* jaccard: a [n,4], b [m,4] x1y1x2y2 -> d_iou [n,m] (box_utils.py:54-79). */
+YB_API int yb_box_iou(yb_handle* h, const float* d_a, int n, const float* d_b, int m, int iscrowd,
+                      float* d_iou, void* stream);
+
+/* COCO run-length encoding of n masks [n,h,w] in `mask_format`: runs in column-major order, alternating
+ * 0-runs / 1-runs starting with zeros (counts[0] == 0 when the first pixel is set) -- the `cnts` array
+ * of pycocotools' rleEncode.  d_counts [n, cap] uint32, d_nruns [n]: number of runs, or -(needed) when
+ * cap was too small for that mask (its counts are then undefined). */
+YB_API int yb_mask_rle(yb_handle* h, const void* d_masks, int mask_format, int n, int mask_h, int mask_w,
+                       uint32_t* d_counts, int64_t cap, int32_t* d_nruns, void* stream);
+
+/* prep_display's mask blend: d_img [h,w,3] fp32 (0..255 when img_is_255, else 0..1), n masks in
+ * `mask_format` in drawing order, d_colors [n,3] fp32 0..1, alpha = mask_alpha ->
+ * d_out [h,w,3] uint8 = (blend * 255).byte()  (eval.py:186-209,226). */
+YB_API int yb_display_blend(yb_handle* h, const float* d_img, int img_is_255, const void* d_masks,
+                            int mask_format, int n, int img_h, int img_w, const float* d_colors, float alpha,
+                            uint8_t* d_out, void* stream);
 
 /* ---- op-level entry points --------------------------------------------------------------------- */
 /* Mirrors dcn_v2_forward's argument list (src/dcn_v2.h:9-23); all tensors NCHW fp32 contiguous.

@@ -60,6 +60,39 @@ def install_shims():
         sys.path.insert(0, REF)
 
 
+def install_cython_nms():
+    """utils/cython_nms.pyx does not compile with Cython 3 / numpy 2 (`np.int_t`, `np.int` are gone).  Build it
+    from a temporary copy with exactly those two aliases renamed (np.int_t -> np.intp_t, np.int -> np.intp; the
+    algorithm is untouched) and register it as utils.cython_nms so Detect.traditional_nms imports it."""
+    import importlib.util
+    import shutil
+    import subprocess
+    import sysconfig
+    import tempfile
+    if "utils.cython_nms" in sys.modules:
+        return
+    src = open(os.path.join(REF, "utils", "cython_nms.pyx")).read()
+    src = src.replace("np.int_t", "np.intp_t").replace("dtype=np.int)", "dtype=np.intp)")
+    d = tempfile.mkdtemp(prefix="yb_cnms_")
+    try:
+        pyx = os.path.join(d, "cython_nms.pyx")
+        open(pyx, "w").write(src)
+        subprocess.run([sys.executable, "-m", "cython", "-3", pyx], check=True, capture_output=True)
+        so = os.path.join(d, "cython_nms" + sysconfig.get_config_var("EXT_SUFFIX"))
+        subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"], "-I", np.get_include(),
+                        os.path.join(d, "cython_nms.c"), "-o", so], check=True, capture_output=True)
+        spec = importlib.util.spec_from_file_location("utils.cython_nms", so)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    import utils as ref_utils
+    sys.modules["utils.cython_nms"] = mod
+    ref_utils.cython_nms = mod
+    import pyximport
+    pyximport.install = lambda *a, **k: None     # traditional_nms calls it before the import above resolves
+
+
 def npz_save(name, **arrs):
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, name + ".npz")
@@ -167,6 +200,21 @@ def gen_detect_unit(seed=3):
             for k in ("box", "mask", "class", "score"):
                 out["%s%d_%s" % (tag, b, k)] = to_np(det[k])
             print("detect_unit", tag, b, "n =", det["score"].shape[0])
+    # --fast_nms=False: Detect.traditional_nms (detection.py:182-228) with the reference's cython_nms
+    install_cython_nms()
+    for ms in (550, 138):
+        cfg.max_size = ms
+        d = Detect(C, bkg_label=0, top_k=200, conf_thresh=0.05, nms_thresh=0.5)
+        d.use_fast_nms = False
+        d.use_cross_class_nms = False
+        res = d({"loc": torch.from_numpy(loc), "conf": conf, "mask": torch.from_numpy(mask),
+                 "priors": torch.from_numpy(priors)}, None)
+        for b in range(B):
+            det = res[b]["detection"]
+            for k in ("box", "mask", "class", "score"):
+                out["trad%d_%d_%s" % (ms, b, k)] = to_np(det[k])
+            print("detect_unit traditional max_size", ms, b, "n =", det["score"].shape[0])
+    cfg.max_size = 550
     npz_save("detect_unit", **out)
 
 
@@ -238,6 +286,109 @@ def gen_dcn_unit(seed=7):
     npz_save("dcn_unit", **out)
 
 
+def gen_eval_unit(seed=11):
+    """Rows either side of the path: FastBaseTransform, mask_iou / jaccard, prep_display -- all from the real
+    reference.  Shims: Tensor.cuda() -> identity (FastBaseTransform.__init__ moves its constants to the GPU);
+    for prep_display a Tensor subclass whose `.device.index` is 0 plus Tensor.to(int) -> identity, because the
+    reference only takes its GPU colour path when the image reports a CUDA device (eval.py:171-183,193)."""
+    from data.config import cfg, set_cfg
+    from utils.augmentations import FastBaseTransform
+    from layers.box_utils import mask_iou, jaccard
+    r = np.random.RandomState(seed)
+    out = {}
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        cases = {"up": ("yolact_base_config", (2, 37, 53), 96, False),
+                 "down": ("yolact_base_config", (1, 300, 211), 96, False),
+                 "same": ("yolact_base_config", (1, 64, 64), 64, False),
+                 "ar": ("yolact_base_config", (1, 120, 200), 80, True),
+                 "dark": ("yolact_darknet53_config", (1, 50, 70), 96, False)}
+        for tag, (cname, (B, H, W), S, ar) in cases.items():
+            set_cfg(cname)
+            cfg.max_size = S
+            cfg.preserve_aspect_ratio = ar
+            img = r.randint(0, 256, size=(B, H, W, 3)).astype(np.uint8)
+            y = FastBaseTransform()(torch.from_numpy(img).float())
+            out["xf_%s_img" % tag] = img
+            out["xf_%s_out" % tag] = to_np(y)
+            out["xf_%s_cfg" % tag] = np.array([S, int(ar), int(cfg.backbone.transform.normalize),
+                                              int(cfg.backbone.transform.subtract_means), int(cfg.backbone.transform.to_float)])
+            print("eval_unit transform", tag, tuple(y.shape), "absmax %.3f" % float(y.abs().max()))
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    set_cfg("yolact_base_config")
+    cfg.mask_proto_debug = False
+
+    # ---- mask_iou / jaccard
+    def blobs(n, h, w):
+        m = np.zeros((n, h, w), np.float32)
+        for i in range(n):
+            for _ in range(r.randint(1, 4)):
+                y0, x0 = r.randint(0, h - 4), r.randint(0, w - 4)
+                m[i, y0:y0 + r.randint(2, h // 2), x0:x0 + r.randint(2, w // 2)] = 1
+        return m
+    ma, mb = blobs(7, 45, 70), blobs(5, 45, 70)
+    mb[4] = 0                       # empty mask: 0/0 -> NaN for non-crowd (kept: parity includes it)
+    ba = np.sort(r.uniform(0, 300, (7, 2, 2)), axis=1).reshape(7, 4)[:, [0, 1, 2, 3]].astype(np.float32)
+    bb = np.sort(r.uniform(0, 300, (5, 2, 2)), axis=1).reshape(5, 4).astype(np.float32)
+    ba = ba[:, [0, 1, 2, 3]]
+    out.update({"iou_masks_a": ma.astype(np.uint8), "iou_masks_b": mb.astype(np.uint8), "iou_boxes_a": ba, "iou_boxes_b": bb})
+    for crowd in (False, True):
+        t = "crowd" if crowd else "plain"
+        out["iou_mask_" + t] = to_np(mask_iou(torch.from_numpy(ma), torch.from_numpy(mb), crowd))
+        out["iou_box_" + t] = to_np(jaccard(torch.from_numpy(ba), torch.from_numpy(bb), crowd))
+    print("eval_unit iou mask", out["iou_mask_plain"][0], "box", out["iou_box_plain"][0])
+
+    # ---- prep_display (eval.py:135-262), production call form: undo_transform=False, img = BGR frame 0..255
+    import eval as ref_eval
+
+    class _OnGpu0(torch.Tensor):
+        @property
+        def device(self):
+            return types.SimpleNamespace(index=0)
+
+    orig_to = torch.Tensor.to
+
+    def to_shim(self, *a, **k):
+        if a and isinstance(a[0], int):
+            return self
+        return orig_to(self, *a, **k)
+
+    n, ph, pw, K = 12, 69, 69, 32
+    proto = np.maximum(r.standard_normal((ph, pw, K)), 0).astype(np.float32)
+    proto = (proto + np.roll(proto, 1, 0) + np.roll(proto, 1, 1) + np.roll(proto, (2, 3), (0, 1))) / 4
+    coef = np.tanh(r.standard_normal((n, K))).astype(np.float32)
+    c = r.uniform(0.2, 0.8, (n, 2))
+    wh = r.uniform(0.1, 0.6, (n, 2))
+    box = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    score = np.sort(r.uniform(0.05, 0.99, n).astype(np.float32))[::-1].copy()
+    cls = r.randint(0, 80, n).astype(np.int64)
+    H, W = 203, 277
+    frame = r.randint(0, 256, size=(H, W, 3)).astype(np.float32)
+    out.update({"disp_proto": proto, "disp_coef": coef, "disp_box": box, "disp_score": score, "disp_cls": cls,
+                "disp_frame": frame.astype(np.uint8)})
+    torch.Tensor.to = to_shim
+    try:
+        for tag, argv, kw in (("masks", ["--top_k=8", "--score_threshold=0.15", "--display_text=False", "--display_bboxes=False"], {}),
+                              ("classcolor", ["--top_k=15", "--score_threshold=0.3", "--display_text=False", "--display_bboxes=False"],
+                               {"class_color": True}),
+                              ("full", ["--top_k=5", "--score_threshold=0.15"], {})):
+            ref_eval.parse_args(argv)
+            ref_eval.color_cache.clear()
+            det = {"box": torch.from_numpy(box.copy()), "mask": torch.from_numpy(coef), "class": torch.from_numpy(cls),
+                   "score": torch.from_numpy(score), "proto": torch.from_numpy(proto)}
+            img = torch.from_numpy(frame).as_subclass(_OnGpu0)
+            with torch.no_grad():
+                res = ref_eval.prep_display([{"detection": det, "net": None}], img, None, None, undo_transform=False, **kw)
+            out["disp_" + tag] = np.asarray(res)
+            print("eval_unit prep_display", tag, res.shape, res.dtype, "mean %.2f" % res.mean())
+    finally:
+        torch.Tensor.to = orig_to
+    out["coco_classes"] = np.array(list(cfg.dataset.class_names))
+    npz_save("eval_unit", **out)
+
+
 def gen_state_keys():
     """state_dict key -> shape for every published config."""
     import json
@@ -266,6 +417,8 @@ if __name__ == "__main__":
         gen_detect_unit()
         gen_postprocess_unit()
         gen_dcn_unit()
+    if "units" in which or "eval" in which:
+        gen_eval_unit()
     if "nets" in which:
         gen_network_case("net_resnet50_160", "yolact_resnet50_config", 1, 160, 160, (120, 150))
         gen_network_case("net_base_192x160_b2", "yolact_base_config", 2, 192, 160, (100, 100))

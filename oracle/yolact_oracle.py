@@ -268,10 +268,65 @@ def _stable_desc_order(scores):
     return np.lexsort((np.arange(scores.shape[-1]), -scores.astype(np.float64)))
 
 
+def cython_nms(dets, thresh):
+    """utils/cython_nms.pyx:24-74 restated: dets [n,5] float32 (x1,y1,x2,y2,score) in PIXELS, greedy NMS with
+    the +1 area convention; returns the kept indices in ascending index order (np.where).
+    Ties in score: lower index first (the pyx uses argsort()[::-1], whose tie order is unspecified)."""
+    dets = np.asarray(dets, np.float32)
+    x1, y1, x2, y2, sc = dets[:, 0], dets[:, 1], dets[:, 2], dets[:, 3], dets[:, 4]
+    one = np.float32(1)
+    areas = ((x2 - x1 + one) * (y2 - y1 + one)).astype(np.float32)
+    order = _stable_desc_order(sc)
+    n = dets.shape[0]
+    suppressed = np.zeros(n, bool)
+    for _i in range(n):
+        i = order[_i]
+        if suppressed[i]:
+            continue
+        rest = order[_i + 1:]
+        rest = rest[~suppressed[rest]]
+        if rest.size == 0:
+            continue
+        xx1 = np.maximum(x1[i], x1[rest])
+        yy1 = np.maximum(y1[i], y1[rest])
+        xx2 = np.minimum(x2[i], x2[rest])
+        yy2 = np.minimum(y2[i], y2[rest])
+        w = np.maximum(np.float32(0), (xx2 - xx1 + one).astype(np.float32))
+        h = np.maximum(np.float32(0), (yy2 - yy1 + one).astype(np.float32))
+        inter = (w * h).astype(np.float32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ovr = (inter / ((areas[i] + areas[rest]).astype(np.float32) - inter).astype(np.float32)).astype(np.float32)
+        suppressed[rest[ovr >= np.float32(thresh)]] = True
+    return np.where(~suppressed)[0]
+
+
+def traditional_nms(boxes, masks, scores, iou_threshold, conf_thresh, max_size, max_dets):
+    """Detect.traditional_nms (detection.py:182-228).  boxes [n,4] relative, scores [C-1,n]."""
+    boxes = (np.asarray(boxes, np.float32) * np.float32(max_size)).astype(np.float32)    # :194
+    idx_lst, cls_lst, scr_lst = [], [], []
+    for c in range(scores.shape[0]):
+        cls_scores = scores[c]
+        conf_mask = cls_scores > np.float32(conf_thresh)                                 # :198
+        idx = np.arange(cls_scores.shape[0])[conf_mask]
+        cs = cls_scores[conf_mask]
+        if cs.shape[0] == 0:
+            continue
+        keep = cython_nms(np.concatenate([boxes[conf_mask], cs[:, None]], 1), iou_threshold)
+        idx_lst.append(idx[keep])
+        cls_lst.append(np.full(keep.shape[0], c, np.int64))
+        scr_lst.append(cs[keep])
+    idx = np.concatenate(idx_lst)
+    classes = np.concatenate(cls_lst)
+    s = np.concatenate(scr_lst)
+    o = _stable_desc_order(s)[:max_dets]                                                 # :219-221
+    idx, classes, s = idx[o], classes[o], s[o]
+    return (boxes[idx] / np.float32(max_size)).astype(np.float32), masks[idx], classes, s   # :228
+
+
 def detect_one(loc, conf, mask, priors, conf_thresh=0.05, nms_thresh=0.5, top_k=200, max_dets=100,
-               cross_class=False):
+               cross_class=False, traditional=False, max_size=550):
     """One image.  conf [P,C] softmaxed.  Returns dict(box, mask, class, score) or None
-    (Detect.detect + fast_nms / cc_fast_nms, detection.py:81-180)."""
+    (Detect.detect + fast_nms / cc_fast_nms / traditional_nms, detection.py:81-228)."""
     conf = np.asarray(conf, np.float32)
     boxes = decode(loc, priors)
     cur = conf[:, 1:].T                                   # [C-1, P]   (detection.py:83)
@@ -282,6 +337,9 @@ def detect_one(loc, conf, mask, priors, conf_thresh=0.05, nms_thresh=0.5, top_k=
     masks = np.asarray(mask, np.float32)[keep]
     if scores.shape[1] == 0:
         return None                                       # :94-95
+    if traditional:
+        b, m, c, s = traditional_nms(boxes, masks, scores, nms_thresh, conf_thresh, max_size, max_dets)
+        return {"box": b, "mask": m, "class": c.astype(np.int64), "score": s}
     if cross_class:
         # cc_fast_nms, detection.py:111-135
         classes = scores.argmax(axis=0)

@@ -41,6 +41,8 @@ class YbConfig(ctypes.Structure):
 YB_BACKBONE_NONE, YB_BACKBONE_RESNET, YB_BACKBONE_DARKNET = -1, 0, 1
 YB_PREC_F32, YB_PREC_F16TC = 0, 1
 YB_MASK_F32, YB_MASK_U8, YB_MASK_BITS = 0, 1, 2
+YB_NMS_FAST, YB_NMS_CROSS_CLASS, YB_NMS_TRADITIONAL = 0, 1, 2
+YB_XFORM_NORMALIZE, YB_XFORM_SUBTRACT_MEANS, YB_XFORM_TO_FLOAT, YB_XFORM_NONE = 0, 1, 2, 3
 
 # name -> (restype, argtypes); kept in one table so tests can check that every symbol the header
 # declares is exported by the library.
@@ -67,6 +69,14 @@ SIGNATURES = {
     "yb_postprocess_batch": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                      c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "yb_maskiou": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "yb_fast_base_transform": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       POINTER(c_float), POINTER(c_float), c_void_p, c_void_p]),
+    "yb_pack_mask_bits": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    "yb_mask_iou": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    "yb_box_iou": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "yb_mask_rle": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "yb_display_blend": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_float,
+                                 c_void_p, c_void_p]),
     "yb_dcn_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 14 +
                        [c_void_p]),
     "yb_conv2d": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 12 +

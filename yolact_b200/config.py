@@ -14,6 +14,10 @@ import copy
 # ImageNet statistics used by BaseTransform / FastBaseTransform (data/config.py:28-29), BGR order
 MEANS = (103.94, 116.78, 123.68)
 STD = (57.38, 57.12, 58.4)
+# Display palette of prep_display (data/config.py:6-24), RGB
+COLORS = ((244, 67, 54), (233, 30, 99), (156, 39, 176), (103, 58, 183), (63, 81, 181), (33, 150, 243), (3, 169, 244),
+          (0, 188, 212), (0, 150, 136), (76, 175, 80), (139, 195, 74), (205, 220, 57), (255, 235, 59), (255, 193, 7),
+          (255, 152, 0), (255, 87, 34), (121, 85, 72), (158, 158, 158), (96, 125, 139))
 
 
 class Config(object):
@@ -53,7 +57,8 @@ _base = Config(dict(
     use_maskiou=False, rescore_mask=False, rescore_bbox=False,
     nms_top_k=200, nms_conf_thresh=0.05, nms_thresh=0.5, max_num_detections=100,
     eval_mask_branch=True, mask_proto_debug=False,
-    normalize=True, to_float=False,     # backbone.transform (config.py:181-202)
+    normalize=True, to_float=False, subtract_means=False, channel_order="RGB",   # backbone.transform (config.py:181-202)
+    preserve_aspect_ratio=False,        # config.py:655 (FastBaseTransform / Resize)
 ))
 
 CONFIGS = {
@@ -134,4 +139,7 @@ def from_reference_cfg(rcfg):
         eval_mask_branch=bool(getattr(rcfg, "eval_mask_branch", True)),
         mask_proto_debug=bool(getattr(rcfg, "mask_proto_debug", False)),
         normalize=bool(b.transform.normalize), to_float=bool(b.transform.to_float),
+        subtract_means=bool(getattr(b.transform, "subtract_means", False)),
+        channel_order=str(getattr(b.transform, "channel_order", "RGB")),
+        preserve_aspect_ratio=bool(getattr(rcfg, "preserve_aspect_ratio", False)),
     ))

@@ -289,6 +289,7 @@ int yb_detect(yb_handle* h, const float* d_loc, const float* d_conf, const float
   dp.max_dets = h->cfg.max_num_detections;
   dp.conf_is_logits = conf_is_logits;
   dp.cross_class = cross_class;
+  dp.max_size = (float)h->cfg.max_size;
   dp.max_out = max_out;
   YB_REQUIRE(dp.nms_thresh > 0.f, "nms_threshold must be non negative.");  // detection.py:25-26
   void* ws = h->get_detect_ws(detect_workspace_bytes(B, P, dp.num_classes, dp.top_k));
@@ -379,6 +380,71 @@ int yb_maskiou(yb_handle* h, const float* d_proto_masks, int n, int ph, int pw, 
     C = cw.Cout;
   }
   launch_maxpool_gather(cur, n, H, W, C, d_cls, d_maskiou, s, &h->lc);
+  YB_API_END
+}
+
+// ---- frame preparation / eval.py consumers -----------------------------------------------------------
+int yb_fast_base_transform(yb_handle* h, const void* d_img, int img_is_u8, int B, int H, int W, int out_h, int out_w,
+                           int mode, const float* h_mean_bgr, const float* h_std_bgr, float* d_out, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && d_img && d_out, "yb_fast_base_transform: null argument");
+  YB_REQUIRE(mode >= YB_XFORM_NORMALIZE && mode <= YB_XFORM_NONE, "yb_fast_base_transform: unknown transform mode");
+  // data/config.py:28-29 (BGR order)
+  static const float kMeans[3] = {103.94f, 116.78f, 123.68f};
+  static const float kStd[3] = {57.38f, 57.12f, 58.40f};
+  DeviceGuard g(h->device);
+  launch_fast_base_transform(d_img, img_is_u8, B, H, W, out_h, out_w, mode, h_mean_bgr ? h_mean_bgr : kMeans,
+                             h_std_bgr ? h_std_bgr : kStd, d_out, (cudaStream_t)stream, &h->lc);
+  YB_API_END
+}
+
+int yb_pack_mask_bits(yb_handle* h, const void* d_in, int in_format, int64_t rows, int w, uint32_t* d_bits,
+                      void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && rows >= 0 && w > 0 && (rows == 0 || (d_in && d_bits)), "yb_pack_mask_bits: bad argument");
+  DeviceGuard g(h->device);
+  launch_pack_mask_bits(d_in, in_format, rows, w, d_bits, (cudaStream_t)stream, &h->lc);
+  YB_API_END
+}
+
+int yb_mask_iou(yb_handle* h, const uint32_t* d_a, int n, const uint32_t* d_b, int m, int64_t words, int iscrowd,
+                float* d_iou, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && n >= 0 && m >= 0 && words >= 0, "yb_mask_iou: bad argument");
+  YB_REQUIRE(n == 0 || m == 0 || (d_a && d_b && d_iou), "yb_mask_iou: null argument");
+  DeviceGuard g(h->device);
+  launch_mask_iou_bits(d_a, n, d_b, m, words, iscrowd, d_iou, (cudaStream_t)stream, &h->lc);
+  YB_API_END
+}
+
+int yb_box_iou(yb_handle* h, const float* d_a, int n, const float* d_b, int m, int iscrowd, float* d_iou,
+               void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && n >= 0 && m >= 0, "yb_box_iou: bad argument");
+  YB_REQUIRE(n == 0 || m == 0 || (d_a && d_b && d_iou), "yb_box_iou: null argument");
+  DeviceGuard g(h->device);
+  launch_box_iou(d_a, n, d_b, m, iscrowd, d_iou, (cudaStream_t)stream, &h->lc);
+  YB_API_END
+}
+
+int yb_mask_rle(yb_handle* h, const void* d_masks, int mask_format, int n, int mask_h, int mask_w, uint32_t* d_counts,
+                int64_t cap, int32_t* d_nruns, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && n >= 0, "yb_mask_rle: bad argument");
+  YB_REQUIRE(n == 0 || (d_masks && d_counts && d_nruns), "yb_mask_rle: null argument");
+  DeviceGuard g(h->device);
+  launch_mask_rle(d_masks, mask_format, n, mask_h, mask_w, d_counts, cap, d_nruns, (cudaStream_t)stream, &h->lc);
+  YB_API_END
+}
+
+int yb_display_blend(yb_handle* h, const float* d_img, int img_is_255, const void* d_masks, int mask_format, int n,
+                     int img_h, int img_w, const float* d_colors, float alpha, uint8_t* d_out, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && d_img && d_out, "yb_display_blend: null argument");
+  YB_REQUIRE(n == 0 || (d_masks && d_colors), "yb_display_blend: null masks / colors");
+  DeviceGuard g(h->device);
+  launch_display_blend(d_img, img_is_255, d_masks, mask_format, n, img_h, img_w, d_colors, alpha, d_out,
+                       (cudaStream_t)stream, &h->lc);
   YB_API_END
 }
 

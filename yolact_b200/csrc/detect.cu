@@ -1,4 +1,5 @@
-// Detect: softmax -> score threshold -> per-class top-k -> decode -> Fast NMS -> global top-k.
+// Detect: softmax -> score threshold -> per-class top-k -> decode -> Fast NMS -> global top-k
+// (plus the --fast_nms=False variant: greedy per-class NMS, trad_nms_kernel).
 //
 // Reference: Detect.__call__/detect/fast_nms/cc_fast_nms (layers/functions/detection.py:32-180),
 // decode (layers/box_utils.py:267-312, non-yolo branch), jaccard/intersect (box_utils.py:32-80),
@@ -348,6 +349,119 @@ class_nms_kernel(const float* __restrict__ scoresT, const int32_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// K2 (traditional): per (class, image) greedy NMS -- Detect.traditional_nms (detection.py:182-228)
+// with utils/cython_nms.pyx:24-74 as the inner routine.
+//   * candidates of class c: score > conf_thresh (detection.py:198); NO top-k cut;
+//   * boxes are multiplied by cfg.max_size and areas / intersections use the +1 pixel convention
+//     (cython_nms.pyx:31,60-66); box j is suppressed by a kept, higher scoring box i when
+//     inter / (area_i + area_j - inter) >= thresh;
+//   * the returned box is (box * max_size) / max_size (detection.py:194,228).
+// The CTA walks the candidates in descending score order, 256 at a time (exact radix select below
+// the previous chunk's smallest key + bitonic sort): each chunk is first tested against the boxes
+// kept so far, then resolved sequentially inside the chunk.  Only the first max_keep kept boxes of
+// a class can reach the image's top max_keep (they outscore everything later in this class), so
+// the walk stops there -- the result is the reference's, without an O(n^2) matrix.
+// Ties in score: lower prior index first (the reference's argsort order is unspecified for ties).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float trad_overlap(const float4& a, float area_a, const float4& b, float area_b) {
+  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  const float w = fmaxf(0.f, __fadd_rn(__fsub_rn(xx2, xx1), 1.f));
+  const float h = fmaxf(0.f, __fadd_rn(__fsub_rn(yy2, yy1), 1.f));
+  const float inter = __fmul_rn(w, h);
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+}
+
+__global__ void __launch_bounds__(NT2)
+trad_nms_kernel(const float* __restrict__ scoresT, const int32_t* __restrict__ cand_prior,
+                const int32_t* __restrict__ cand_count, const float* __restrict__ loc,
+                const float* __restrict__ priors, int64_t P, int C, int top_k, float conf_thresh,
+                float nms_thresh, float max_size, int max_keep, float* __restrict__ pool_score,
+                int32_t* __restrict__ pool_prior, float* __restrict__ pool_box,
+                int32_t* __restrict__ pool_n) {
+  __shared__ unsigned long long sel[SORT_N];
+  __shared__ SelectScratch sc;
+  __shared__ float4 sbox[SORT_N];     // current chunk, scaled by max_size
+  __shared__ float sarea[SORT_N];
+  __shared__ int s_alive[SORT_N];
+  __shared__ float4 kbox[SORT_N];     // kept so far (scaled)
+  __shared__ float karea[SORT_N];
+  __shared__ int s_warp[NT2 / 32];
+
+  const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int M = cand_count[b];
+  const float* sc_row = scoresT + ((int64_t)b * (C - 1) + c) * P;
+  const int32_t* cp = cand_prior + (int64_t)b * P;
+  const int64_t base = ((int64_t)b * (C - 1) + c) * top_k;
+
+  int mine = 0;
+  for (int i = tid; i < M; i += NT2) mine += (sc_row[i] > conf_thresh) ? 1 : 0;
+  int n_c;
+  block_excl_scan(mine, s_warp, &n_c);
+
+  unsigned long long last_key = ~0ull;   // keys of processed candidates are >= last_key
+  int kept = 0, processed = 0;
+  while (processed < n_c && kept < max_keep) {
+    const int K = min(SORT_N, n_c - processed);
+    const unsigned long long lk = last_key;
+    auto keyfn = [&](int i) -> unsigned long long {
+      const float s = sc_row[i];
+      if (!(s > conf_thresh)) return 0ull;
+      const unsigned long long k =
+          ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)cp[i]);
+      return k < lk ? k : 0ull;
+    };
+    block_select_topk(keyfn, M, K, sel, &sc);
+    block_sort_desc(sel);
+
+    const unsigned long long mykey = sel[tid];
+    const bool valid = tid < K;
+    const int prior = valid ? (int)(0xFFFFFFFFu - (unsigned)(mykey & 0xFFFFFFFFull)) : 0;
+    const float score = __uint_as_float((unsigned)(mykey >> 32));
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float area = 0.f;
+    if (valid) {
+      const float4 d = decode_box(loc + ((int64_t)b * P + prior) * 4, priors + (int64_t)prior * 4);
+      bx = make_float4(__fmul_rn(d.x, max_size), __fmul_rn(d.y, max_size), __fmul_rn(d.z, max_size),
+                       __fmul_rn(d.w, max_size));
+      area = __fmul_rn(__fadd_rn(__fsub_rn(bx.z, bx.x), 1.f), __fadd_rn(__fsub_rn(bx.w, bx.y), 1.f));
+    }
+    bool alive = valid;
+    for (int k = 0; k < kept && alive; ++k)
+      if (trad_overlap(kbox[k], karea[k], bx, area) >= nms_thresh) alive = false;
+    sbox[tid] = bx;
+    sarea[tid] = area;
+    s_alive[tid] = alive ? 1 : 0;
+    __syncthreads();
+    for (int i = 0; i < K; ++i) {
+      if (s_alive[i]) {   // uniform: written before the previous barrier
+        if (tid > i && alive && trad_overlap(sbox[i], sarea[i], bx, area) >= nms_thresh) {
+          alive = false;
+          s_alive[tid] = 0;
+        }
+      }
+      __syncthreads();
+    }
+    int total;
+    const int pos = kept + block_excl_scan(alive ? 1 : 0, s_warp, &total);
+    if (alive && pos < max_keep) {
+      kbox[pos] = bx;
+      karea[pos] = area;
+      pool_score[base + pos] = score;
+      pool_prior[base + pos] = prior;
+      reinterpret_cast<float4*>(pool_box)[base + pos] =
+          make_float4(__fdiv_rn(bx.x, max_size), __fdiv_rn(bx.y, max_size), __fdiv_rn(bx.z, max_size),
+                      __fdiv_rn(bx.w, max_size));
+    }
+    kept = min(kept + total, max_keep);
+    processed += K;
+    last_key = sel[K - 1];
+    __syncthreads();   // kbox / sel are rewritten by the next round
+  }
+  if (tid == 0) pool_n[b * (C - 1) + c] = kept;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K3: final top max_dets over all (class, rank) pool entries of one image
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT2)
@@ -454,7 +568,8 @@ void launch_detect(const DetectParams& dp, const float* loc, const float* conf, 
   YB_REQUIRE(dp.top_k >= 1 && dp.top_k <= SORT_N, "detect: nms_top_k must be in [1,256]");
   YB_REQUIRE(dp.num_classes >= 2 && dp.num_classes - 1 <= 128, "detect: num_classes out of range");
   YB_REQUIRE(dp.max_out <= SORT_N, "detect: max_out must be <= 256");
-  YB_REQUIRE(dp.cross_class ? dp.max_out >= 1 : dp.max_out >= dp.max_dets,
+  YB_REQUIRE(dp.cross_class >= YB_NMS_FAST && dp.cross_class <= YB_NMS_TRADITIONAL, "detect: unknown nms mode");
+  YB_REQUIRE(dp.cross_class == YB_NMS_CROSS_CLASS ? dp.max_out >= 1 : dp.max_out >= dp.max_dets,
              "detect: max_out too small");
   YB_REQUIRE(dp.P < (1ll << 31), "detect: too many priors");
   const int B = dp.B, C = dp.num_classes;
@@ -464,12 +579,13 @@ void launch_detect(const DetectParams& dp, const float* loc, const float* conf, 
     size_t smem = (size_t)K1_ROWS * C * sizeof(float);
     YB_REQUIRE(smem <= 48 * 1024, "detect: num_classes too large for the K1 tile");
     detect_candidates_kernel<<<grid, K1_ROWS, smem, stream>>>(
-        conf, dp.P, C, dp.conf_is_logits, dp.conf_thresh, dp.cross_class, ws.scoresT, ws.cand_prior,
+        conf, dp.P, C, dp.conf_is_logits, dp.conf_thresh, dp.cross_class == YB_NMS_CROSS_CLASS ? 1 : 0, ws.scoresT,
+        ws.cand_prior,
         ws.cand_cls, ws.cand_count);
     YB_CHECK_LAUNCH();
     if (lc) lc->n++;
   }
-  if (dp.cross_class) {
+  if (dp.cross_class == YB_NMS_CROSS_CLASS) {
     dim3 grid(1, B);
     class_nms_kernel<true><<<grid, NT2, 0, stream>>>(
         ws.scoresT, ws.cand_prior, ws.cand_cls, ws.cand_count, loc, priors, coef, dp.P, C,
@@ -479,10 +595,18 @@ void launch_detect(const DetectParams& dp, const float* loc, const float* conf, 
     if (lc) lc->n++;
   } else {
     dim3 grid(C - 1, B);
-    class_nms_kernel<false><<<grid, NT2, 0, stream>>>(
-        ws.scoresT, ws.cand_prior, ws.cand_cls, ws.cand_count, loc, priors, coef, dp.P, C,
-        dp.mask_dim, dp.top_k, dp.nms_thresh, ws.pool_score, ws.pool_prior, ws.pool_box, ws.pool_n,
-        dp.max_out, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (dp.cross_class == YB_NMS_TRADITIONAL) {
+      YB_REQUIRE(dp.max_dets <= dp.top_k, "detect: traditional NMS needs max_num_detections <= nms_top_k");
+      YB_REQUIRE(dp.max_size > 0.f, "detect: traditional NMS needs cfg.max_size");
+      trad_nms_kernel<<<grid, NT2, 0, stream>>>(ws.scoresT, ws.cand_prior, ws.cand_count, loc, priors, dp.P, C,
+                                                dp.top_k, dp.conf_thresh, dp.nms_thresh, dp.max_size, dp.max_dets,
+                                                ws.pool_score, ws.pool_prior, ws.pool_box, ws.pool_n);
+    } else {
+      class_nms_kernel<false><<<grid, NT2, 0, stream>>>(
+          ws.scoresT, ws.cand_prior, ws.cand_cls, ws.cand_count, loc, priors, coef, dp.P, C,
+          dp.mask_dim, dp.top_k, dp.nms_thresh, ws.pool_score, ws.pool_prior, ws.pool_box, ws.pool_n,
+          dp.max_out, nullptr, nullptr, nullptr, nullptr, nullptr);
+    }
     YB_CHECK_LAUNCH();
     if (lc) lc->n++;
     final_select_kernel<<<B, NT2, 0, stream>>>(ws.pool_score, ws.pool_prior, ws.pool_box, ws.pool_n,

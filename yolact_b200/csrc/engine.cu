@@ -971,6 +971,7 @@ void yb_handle::infer(const float* d_x, int B, int H, int W, int cross_class, in
   dp.max_dets = cfg.max_num_detections;
   dp.conf_is_logits = 1;
   dp.cross_class = cross_class;
+  dp.max_size = (float)cfg.max_size;
   dp.max_out = max_out;
   if (!ex->det_ws || ex->det_max_out != max_out || ex->det_cross_class != cross_class) {
     // (re)build the fused-detect buffers; invalidates the captured graph
@@ -1020,7 +1021,7 @@ void yb_handle::infer(const float* d_x, int B, int H, int W, int cross_class, in
       cudaGraphDestroy(g);
     }
     YB_CHECK_CUDA(cudaGraphLaunch(ex->graph_infer, stream));
-    lc.n += (int64_t)ex->ops.size() + (cross_class ? 2 : 3);
+    lc.n += (int64_t)ex->ops.size() + (cross_class == YB_NMS_CROSS_CLASS ? 2 : 3);
   }
   ex->infer_calls++;
   const void* src[6] = {ex->det_box, ex->det_coef, ex->det_cls, ex->det_score, ex->det_count, ex->proto};

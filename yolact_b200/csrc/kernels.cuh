@@ -115,7 +115,8 @@ struct DetectParams {
   float nms_thresh = 0.5f;
   int max_dets = 100;
   int conf_is_logits = 0;
-  int cross_class = 0;
+  int cross_class = 0;          // yb_nms_mode
+  float max_size = 550.f;       // cfg.max_size: box scale of traditional_nms (detection.py:194)
   int max_out = 100;
 };
 void launch_detect(const DetectParams& dp, const float* loc, const float* conf, const float* coef,
@@ -131,6 +132,21 @@ void launch_mask_assembly(const float* proto, int ph, int pw, int k, const float
 // global max over HxW per (n, c) then gather channel cls[n] (yolact.py:373, output_utils.py:83)
 void launch_maxpool_gather(const float* x_nhwc, int n, int H, int W, int C, const int64_t* cls,
                            float* out, cudaStream_t stream, LaunchCounter* lc);
+
+// ---- frame preparation / eval.py consumers (evalops.cu) -----------------------------------------
+void launch_fast_base_transform(const void* img, int img_is_u8, int B, int H, int W, int out_h, int out_w, int mode,
+                                const float* mean_bgr, const float* std_bgr, float* out, cudaStream_t stream,
+                                LaunchCounter* lc);
+void launch_pack_mask_bits(const void* in, int in_format, int64_t rows, int w, uint32_t* out, cudaStream_t stream,
+                           LaunchCounter* lc);
+void launch_mask_iou_bits(const uint32_t* a, int n, const uint32_t* b, int m, int64_t words, int iscrowd, float* out,
+                          cudaStream_t stream, LaunchCounter* lc);
+void launch_box_iou(const float* a, int n, const float* b, int m, int iscrowd, float* out, cudaStream_t stream,
+                    LaunchCounter* lc);
+void launch_mask_rle(const void* masks, int mask_format, int n, int h, int w, uint32_t* counts, int64_t cap,
+                     int32_t* nruns, cudaStream_t stream, LaunchCounter* lc);
+void launch_display_blend(const float* img, int img_is_255, const void* masks, int mask_format, int n, int h, int w,
+                          const float* colors, float alpha, uint8_t* out, cudaStream_t stream, LaunchCounter* lc);
 
 // ---- DCNv2 -------------------------------------------------------------------------------------
 // x NHWC (T) [B,H,W,C]; om = offset/mask conv output NHWC fp32 [B,Ho,Wo,27] (18 offsets

@@ -1,4 +1,4 @@
-"""Detect: drop-in for layers/functions/detection.py:11-108 (Fast NMS paths) on the CUDA library.
+"""Detect: drop-in for layers/functions/detection.py:11-228 (fast_nms, cc_fast_nms, traditional_nms) on the CUDA library.
 
 `Detect(num_classes, bkg_label, top_k, conf_thresh, nms_thresh)` and
 `detect(predictions, net) -> [{'detection': dict|None, 'net': net}]` keep the reference signature;
@@ -25,9 +25,10 @@ class Detect(object):
             raise ValueError('nms_threshold must be non negative.')  # detection.py:25-26
         self.conf_thresh = conf_thresh
         self.use_cross_class_nms = False
-        self.use_fast_nms = True   # eval.py:50,871 default; traditional NMS is out of scope
+        self.use_fast_nms = True   # eval.py:50,871 default; False -> traditional_nms (detection.py:182-228)
         self.max_num_detections = getattr(cfg, "max_num_detections", 100) if cfg is not None else 100
         self.mask_dim = getattr(cfg, "mask_dim", 32) if cfg is not None else 32
+        self.max_size = getattr(cfg, "max_size", 550) if cfg is not None else 550   # traditional_nms box scale
         self._handles = {}
 
     def _handle(self, device):
@@ -35,7 +36,7 @@ class Detect(object):
             raise _lib.YbError("yolact_b200.Detect runs on CUDA (B200) only; there is no CPU path.")
         idx = device.index if device.index is not None else torch.cuda.current_device()
         key = (idx, self.top_k, self.conf_thresh, self.nms_thresh, self.max_num_detections, self.num_classes,
-               self.mask_dim)
+               self.mask_dim, self.max_size)
         if key not in self._handles:
             lib = _lib.load()
             yc = _lib.YbConfig()
@@ -47,15 +48,23 @@ class Detect(object):
             yc.nms_conf_thresh = self.conf_thresh
             yc.nms_thresh = self.nms_thresh
             yc.max_num_detections = self.max_num_detections
+            yc.max_size = int(self.max_size)
             h = ctypes.c_void_p()
             _lib.check(lib.yb_create(ctypes.byref(yc), idx, ctypes.byref(h)), "yb_create(ops)")
             self._handles[key] = h
         return self._handles[key]
 
+    def nms_mode(self):
+        """detection.py:97-106: fast_nms / cc_fast_nms, or traditional_nms when use_fast_nms is False (the
+        reference then ignores use_cross_class_nms with a warning)."""
+        if not self.use_fast_nms:
+            if self.use_cross_class_nms:
+                print('Warning: Cross Class Traditional NMS is not implemented.')
+            return _lib.YB_NMS_TRADITIONAL
+        return _lib.YB_NMS_CROSS_CLASS if self.use_cross_class_nms else _lib.YB_NMS_FAST
+
     def detect_padded(self, loc, conf, mask, priors, conf_is_logits=False):
         """Fixed-size outputs, no host sync: (box [B,M,4], coef [B,M,k], cls [B,M] int64, score [B,M], count [B])."""
-        if not self.use_fast_nms:
-            raise NotImplementedError("yolact_b200 implements Fast NMS only; traditional NMS is out of scope")
         lib = _lib.load()
         dev = loc.device
         self.mask_dim = int(mask.shape[-1])
@@ -65,7 +74,8 @@ class Detect(object):
         conf = conf.contiguous().float().view(B, P, self.num_classes)
         mask = mask.contiguous().float()
         priors = priors.contiguous().float()
-        cc = bool(self.use_cross_class_nms)
+        mode = self.nms_mode()
+        cc = mode == _lib.YB_NMS_CROSS_CLASS
         M = self.top_k if cc else self.max_num_detections
         box = torch.empty(B, M, 4, dtype=torch.float32, device=dev)
         coef = torch.empty(B, M, mask.shape[-1], dtype=torch.float32, device=dev)
@@ -73,7 +83,7 @@ class Detect(object):
         score = torch.empty(B, M, dtype=torch.float32, device=dev)
         count = torch.empty(B, dtype=torch.int32, device=dev)
         _lib.check(lib.yb_detect(h, _lib.ptr(loc), _lib.ptr(conf), _lib.ptr(mask), _lib.ptr(priors), B, P,
-                                 1 if conf_is_logits else 0, 1 if cc else 0, M, _lib.ptr(box), _lib.ptr(coef),
+                                 1 if conf_is_logits else 0, mode, M, _lib.ptr(box), _lib.ptr(coef),
                                  _lib.ptr(cls), _lib.ptr(score), _lib.ptr(count), _lib.current_stream(dev)),
                    "yb_detect")
         return box, coef, cls, score, count

@@ -373,11 +373,11 @@ class Yolact(nn.Module):
         h = self._handle_for(x.device)
         B, _, H, W = x.shape
         c = self.cfg
-        if not self.detect.use_fast_nms:
-            raise NotImplementedError("yolact_b200 implements Fast NMS only (eval.py default --fast_nms=True); "
-                                      "traditional NMS (utils/cython_nms.pyx) is out of scope")
-        cc = self.detect.use_cross_class_nms if cross_class is None else cross_class
-        M = c.nms_top_k if cc else c.max_num_detections
+        if cross_class is None:
+            mode = self.detect.nms_mode()   # fast_nms | cc_fast_nms | traditional_nms (--fast_nms=False)
+        else:
+            mode = _lib.YB_NMS_CROSS_CLASS if cross_class else _lib.YB_NMS_FAST
+        M = c.nms_top_k if mode == _lib.YB_NMS_CROSS_CLASS else c.max_num_detections
         ph, pw = ctypes.c_int32(), ctypes.c_int32()
         _lib.check(lib.yb_proto_size(h, H, W, ctypes.byref(ph), ctypes.byref(pw)), "yb_proto_size")
         o = dict(device=x.device)
@@ -387,7 +387,7 @@ class Yolact(nn.Module):
         score = torch.empty(B, M, dtype=torch.float32, **o)
         count = torch.empty(B, dtype=torch.int32, **o)
         proto = torch.empty(B, ph.value, pw.value, c.mask_dim, dtype=torch.float32, **o) if c.eval_mask_branch else None
-        _lib.check(lib.yb_infer(h, _lib.ptr(x), B, H, W, 1 if cc else 0, M, _lib.ptr(box), _lib.ptr(coef),
+        _lib.check(lib.yb_infer(h, _lib.ptr(x), B, H, W, mode, M, _lib.ptr(box), _lib.ptr(coef),
                                 _lib.ptr(cls), _lib.ptr(score), _lib.ptr(count), _lib.ptr(proto),
                                 _lib.current_stream(x.device)), "yb_infer")
         self._last_B = B
