@@ -2,6 +2,8 @@
 fp16 kernel (same quantised operands, different summation order) and vs torch on fp16-rounded inputs."""
 import ctypes
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -115,7 +117,13 @@ TC_MODES = {
     "default": {},
     "persistent_grid3": {"YB_CONV2D_GRID": "3"},
     "persistent_grid5_bn64": {"YB_CONV2D_GRID": "5", "YB_CONV2D_BN": "64"},
+    # CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256): default grid, and 2 clusters walking many units
+    # (TMEM double buffering across the pair, odd M-tile counts -> a padding tile in the last pair)
+    "pair": {"YB_CONV2D_PAIR": "1"},
+    "pair_grid4_bn128": {"YB_CONV2D_PAIR": "1", "YB_CONV2D_GRID": "4", "YB_CONV2D_BN": "128"},
 }
+if os.environ.get("YB_TEST_NO_PAIR"):   # escape hatch while the pair kernel is being brought up
+    TC_MODES = {k: v for k, v in TC_MODES.items() if not k.startswith("pair")}
 
 
 @pytest.mark.parametrize("mode", sorted(TC_MODES))

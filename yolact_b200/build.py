@@ -42,7 +42,20 @@ def _newer(path, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, watchdog=False):
+    """watchdog=True builds libyolact_b200_wd.so with -DYB_WATCHDOG (mbarrier waits trap after ~2 s instead of
+    hanging the GPU): the library to point YB_LIB at while a new kernel protocol is being brought up."""
+    global OBJ, LIB
+    flags = list(NVCC_FLAGS)
+    obj_dir, lib = OBJ, LIB
+    if watchdog:
+        flags.append("-DYB_WATCHDOG")
+        obj_dir = OBJ + "_wd"
+        lib = os.path.join(HERE, "libyolact_b200_wd.so")
+    return _build(force, verbose, flags, obj_dir, lib)
+
+
+def _build(force, verbose, NVCC_FLAGS, OBJ, LIB):
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
     hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
@@ -73,5 +86,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, verbose=True)
+    p = build(force="--force" in sys.argv, verbose=True, watchdog="--watchdog" in sys.argv)
     print("built", p)

@@ -95,13 +95,14 @@ struct yb_handle {
   bool pdl = false;         // YB_PDL=1: programmatic dependent launch between consecutive tcgen05 convs
   bool stem_on_tc = true;   // YB_STEM_TC=0 falls back to the SIMT stem
   bool autotune = true;     // YB_AUTOTUNE=0 disables plan-time autotuning of the tcgen05 tiles
+  bool pair_candidates = false;   // YB_PAIR=1: the autotuner also times CTA-pair (cta_group::2) plans
   float last_total_ms = 0.f, last_conv_ms = 0.f;
   yb::LaunchCounter lc;
   std::map<std::string, yb::HostTensor> host;
   std::map<std::string, yb::ConvW> convs;
   std::map<std::string, std::unique_ptr<yb::Executor>> execs;
   std::vector<void*> weight_allocs;
-  std::map<std::string, std::array<int, 3>> tune_cache;  // layer shape -> (BN, stages, grid) from the autotuner
+  std::map<std::string, std::array<int, 4>> tune_cache;  // layer shape -> (BN, stages, grid, pair) from the autotuner
   yb::Executor* last_exec = nullptr;
   // standalone op workspaces
   void* detect_ws = nullptr;

@@ -48,8 +48,10 @@ struct TcConvPlan;  // opaque: tensor maps + tiling; built once per (layer, shap
 // w_packed: device half [KH*KW][CoutPad][Cin], CoutPad = round_up(Cout,16). Requires Cin % 64 == 0.
 // bn_override in {32,64,128,256} / stages_override > 0 pin the N tile / pipeline depth (autotuner); 0 = heuristic.
 // grid_override > 0 caps the number of (persistent) CTAs; default 148 = one per SM.
+// pair_override > 0: CTA pairs (cluster of 2, tcgen05 cta_group::2, UMMA M = 256; each CTA stages half the weight tile).
 TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override = 0,
-                                int stages_override = 0, int grid_override = 0);
+                                int stages_override = 0, int grid_override = 0, int pair_override = 0);
+int tc_conv_plan_pair(const TcConvPlan* plan);
 int tc_conv_plan_grid(const TcConvPlan* plan);
 void tc_conv_plan_set_pdl(TcConvPlan* plan, int enable);   // programmatic dependent launch (prologue overlap)
 int tc_conv_plan_bn(const TcConvPlan* plan);

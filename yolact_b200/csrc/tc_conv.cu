@@ -18,6 +18,11 @@
 // Pipeline: warp 0 = TMA producer, warp 1 = TMEM alloc + single-thread tcgen05.mma issue,
 //   warps 2..5 = epilogue (tcgen05.ld -> +bias -> +residual -> activation -> 16-byte stores).
 //   `stages`-deep mbarrier ring (full/empty), tcgen05.commit releases shared memory slots.
+// CTA pairs (PAIR = true): a cluster of two CTAs on one TPC computes two adjacent M tiles of the same N tile
+//   with ONE tcgen05.mma.cta_group::2 (M = 256).  Each CTA loads its own A tile and only HALF of the weight
+//   tile, so the bytes a CTA pulls from L2 per k-block drop from 16 KB + BN*128 to 16 KB + BN*64 -- the conv
+//   stack at batch 8 is L2->SM bandwidth bound, not tensor bound.  The even CTA issues
+//   the MMAs; both CTAs' TMA loads signal ITS full barrier; tcgen05.commit multicasts to both CTAs' barriers.
 #include <vector>
 #include "tc_common.cuh"
 
@@ -51,6 +56,8 @@ struct alignas(64) TcParams {
   float* seg_y[3];
   int tmem_cols;        // power of two >= acc_stages * BN
   int pdl;              // launched with programmatic stream serialization
+  int pair;             // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2, UMMA M = 256)
+  int nb;               // batch extent of the tile grid (1 when flattened): tiles with b >= nb are padding
   int ntaps, kchunks, stages;
   int tap_map[MAX_TAPS], tap_dx[MAX_TAPS], tap_dy[MAX_TAPS];
   int tw, th, tiles_x, tiles_y;
@@ -162,10 +169,8 @@ __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1
 struct TileCoord {
   int b, x0, y0, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, int BN) {
+__device__ __forceinline__ TileCoord decode_mn(const TcParams& p, int m, int nt, int BN) {
   TileCoord t;
-  const int nt = tile % p.n_tiles;
-  int m = tile / p.n_tiles;
   const int tx = m % p.tiles_x;
   m /= p.tiles_x;
   const int ty = m % p.tiles_y;
@@ -175,11 +180,20 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, in
   t.n0 = nt * BN;
   return t;
 }
+// Work unit u of a CTA: one (M tile, N tile).  Single CTAs walk tiles; a CTA pair walks (M-tile pair, N tile)
+// units, CTA `rank` taking M tile 2*group + rank (a padding tile when the M-tile count is odd: its loads are
+// zero-filled and its stores clipped by the tensor maps, b >= nb marks it for the direct epilogue).
+template <bool PAIR>
+__device__ __forceinline__ TileCoord decode_unit(const TcParams& p, int u, int rank, int BN) {
+  const int nt = u % p.n_tiles;
+  const int mg = u / p.n_tiles;
+  return decode_mn(p, PAIR ? 2 * mg + rank : mg, nt, BN);
+}
 
-template <int BN>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS)
 tc_conv_kernel(const __grid_constant__ TcParams p) {
-  constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  constexpr int B_STAGE_BYTES = (PAIR ? BN / 2 : BN) * BLOCK_K * 2;   // a pair CTA stages half of the weight tile
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 
   extern __shared__ uint8_t smem_dyn[];
@@ -200,7 +214,11 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
   const int num_kb = p.ntaps * p.kchunks;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  // work units of this CTA: unit0, unit0 + ustep, ... < num_units
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int unit0 = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int ustep = PAIR ? (int)cluster_nclusters_x() : (int)gridDim.x;
+  const int num_units = (PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
   const int acc_stages = p.acc_stages;
 
   if (warp == 0 && lane == 0) {
@@ -210,7 +228,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], PAIR ? 2 : 1);   // pair leader: both CTAs' epilogues drain the accumulator
       mbar_init(&res_full_bar[i], 1);
     }
     fence_barrier_init();
@@ -221,6 +239,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   if (warp == 1) tmem_alloc_dyn(&s_tmem_base, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
   // Programmatic dependent launch: everything above overlaps the tail of the previous kernel in the
@@ -233,10 +252,12 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)p.a_box_bytes + (uint32_t)B_STAGE_BYTES;
+      // a pair's leader expects the bytes of BOTH CTAs (each: its A tile + its half of the weight tile)
+      const uint32_t tx_bytes = ((uint32_t)p.a_box_bytes + (uint32_t)B_STAGE_BYTES) * (PAIR ? 2u : 1u);
+      const uint32_t leader_full = PAIR ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0u;
       uint32_t kbg = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord tc_ = decode_tile(p, tile, BN);
+      for (int u = unit0; u < num_units; u += ustep) {
+        const TileCoord tc_ = decode_unit<PAIR>(p, u, rank, BN);
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)stages;
           const uint32_t it = kbg / (uint32_t)stages;
@@ -245,18 +266,26 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           const int kc = kb - tap * p.kchunks;
           uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[s], tx_bytes);
-          tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[s], kc * BLOCK_K, tc_.x0 + p.tap_dx[tap],
-                      tc_.y0 + p.tap_dy[tap], tc_.b);
-          tma_load_3d(sb, &p.tmB, &full_bar[s], kc * BLOCK_K, tc_.n0, tap);
+          if (PAIR) {
+            if (rank == 0) mbar_expect_tx(&full_bar[s], tx_bytes);
+            const uint32_t fb = leader_full + s * (uint32_t)sizeof(uint64_t);
+            tma_load_4d_pair(sa, &p.tmA[p.tap_map[tap]], fb, kc * BLOCK_K, tc_.x0 + p.tap_dx[tap],
+                             tc_.y0 + p.tap_dy[tap], tc_.b);
+            tma_load_3d_pair(sb, &p.tmB, fb, kc * BLOCK_K, tc_.n0 + rank * (BN / 2), tap);
+          } else {
+            mbar_expect_tx(&full_bar[s], tx_bytes);
+            tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[s], kc * BLOCK_K, tc_.x0 + p.tap_dx[tap],
+                        tc_.y0 + p.tap_dy[tap], tc_.b);
+            tma_load_3d(sb, &p.tmB, &full_bar[s], kc * BLOCK_K, tc_.n0, tap);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {   // in a pair only the even CTA issues (for both)
       uint32_t kbg = 0, t = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      for (int u = unit0; u < num_units; u += ustep, ++t) {
         const uint32_t acc = t % (uint32_t)acc_stages;
         const uint32_t use = t / (uint32_t)acc_stages;
         mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
@@ -274,11 +303,16 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 field
-            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (PAIR)
+              umma_f16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);  // frees this smem slot once the MMAs above have read it
+          // frees this smem slot (in both CTAs of a pair) once the MMAs above have read it
+          if (PAIR) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        // accumulator complete (both halves)
+        if (PAIR) umma_commit_pair(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
       }
     }
   } else {
@@ -293,11 +327,18 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 
     // residual chunk stream (epi_tma only): global chunk g lives in res buffer g&1; the issuer keeps it
     // two chunks ahead of the consumer, across tile boundaries.  (pf_tile, pf_c) = next chunk to fetch.
-    int pf_tile = blockIdx.x, pf_c = 0;
+    const uint32_t leader_tmem_empty = PAIR ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
+    auto release_acc = [&](uint32_t acc) {   // this CTA's 128 epilogue threads have read the accumulator
+      if (PAIR && rank != 0)
+        mbar_arrive_cluster(leader_tmem_empty + acc * (uint32_t)sizeof(uint64_t));
+      else
+        mbar_arrive(&tmem_empty_bar[acc]);
+    };
+    int pf_tile = unit0, pf_c = 0;
     uint32_t pf_g = 0;
     auto prefetch_res = [&]() {
-      if (pf_tile >= num_tiles) return;
-      const TileCoord tcp = decode_tile(p, pf_tile, BN);
+      if (pf_tile >= num_units) return;
+      const TileCoord tcp = decode_unit<PAIR>(p, pf_tile, rank, BN);
       const int nch = (min(BN, p.Cout - tcp.n0) + 63) >> 6;
       const uint32_t buf = pf_g & 1u;
       mbar_expect_tx(&res_full_bar[buf], (uint32_t)p.a_box_bytes);
@@ -305,7 +346,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       ++pf_g;
       if (++pf_c >= nch) {
         pf_c = 0;
-        pf_tile += gridDim.x;
+        pf_tile += ustep;
       }
     };
     if (p.epi_tma && has_res && issuer) {
@@ -314,8 +355,8 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
     }
 
     uint32_t t = 0, g = 0;  // local tile counter, global staged-chunk counter
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-      const TileCoord tc_ = decode_tile(p, tile, BN);
+    for (int u = unit0; u < num_units; u += ustep, ++t) {
+      const TileCoord tc_ = decode_unit<PAIR>(p, u, rank, BN);
       const int x0 = tc_.x0, y0 = tc_.y0, b = tc_.b, n0 = tc_.n0;
       const uint32_t acc = t % (uint32_t)acc_stages;
       const uint32_t use = t / (uint32_t)acc_stages;
@@ -365,7 +406,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           if (c == nchunks - 1) tc_fence_before();
           epi_bar_sync();
           if (issuer) {
-            if (c == nchunks - 1) mbar_arrive(&tmem_empty_bar[acc]);  // all 128 threads have read their rows
+            if (c == nchunks - 1) release_acc(acc);  // all 128 threads have read their rows
             tma_store_4d(&p.tmY, out_tile, nbase, x0, y0, b);
             bulk_commit();
             if (has_res) prefetch_res();   // everyone is done reading res_tile[buf]: refill it two chunks ahead
@@ -410,7 +451,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             const int trow = quad * 32 + rr;
             const int ty_ = trow / p.tw, tx_ = trow - ty_ * p.tw;
             const int oy = y0 + ty_, ox = x0 + tx_;
-            if (trow >= p.tw * p.th || oy >= p.Ho || ox >= p.Wo) continue;   // warp-uniform
+            if (trow >= p.tw * p.th || oy >= p.Ho || ox >= p.Wo || b >= p.nb) continue;   // warp-uniform
             if (lane >= nvalid) continue;
             const long long pix = (long long)oy * p.Wo + ox;
             float v = tbuf[rr * 33 + lane] + bias_l;
@@ -431,7 +472,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
         }
         tc_fence_before();
         epi_bar_sync();
-        if (issuer) mbar_arrive(&tmem_empty_bar[acc]);
+        if (issuer) release_acc(acc);
       }
     }
     if (p.epi_tma && issuer) bulk_wait_read<0>();  // smem must outlive the bulk reads
@@ -442,6 +483,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // no CTA leaves while its peer's MMAs / signals may still touch it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_dyn(tmem_base, (uint32_t)p.tmem_cols);
@@ -503,6 +545,7 @@ void tc::encode_map_f16(CUtensorMap* map, const void* base, int rank, const uint
 struct TcConvPlan {
   TcParams prm;
   int BN = 128;
+  int pair = 0;
   dim3 grid;
   size_t smem_bytes = 0;
 };
@@ -517,7 +560,7 @@ bool tc_conv_supported(const ConvProblem& p) {
 }
 
 TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override, int stages_override,
-                                int grid_override) {
+                                int grid_override, int pair_override) {
   YB_REQUIRE(tc_conv_supported(p), "tc_conv: unsupported problem");
   YB_REQUIRE(p.Ho == (p.H + 2 * p.pad - p.KH) / p.stride + 1, "tc_conv: bad Ho");
   YB_REQUIRE(p.Wo == (p.W + 2 * p.pad - p.KW) / p.stride + 1, "tc_conv: bad Wo");
@@ -595,15 +638,24 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
       plan->BN = std::max(bn_override, bn_min);
   }
   const int BN = plan->BN;
-  const int stage_bytes = A_STAGE_BYTES + BN * BLOCK_K * 2;
+  // ---- CTA pairs: two adjacent M tiles per (cluster of 2), each CTA stages half of the weight tile
+  const int pair = (pair_override > 0 && m_tiles >= 2 && BN >= 64) ? 1 : 0;
+  plan->pair = pair;
+  q.pair = pair;
+  q.nb = Bv;
+  const int stage_bytes = A_STAGE_BYTES + (pair ? BN / 2 : BN) * BLOCK_K * 2;
   // ---- persistent grid + shared-memory layout: [pipeline stages][2 x 16 KB out tiles][2 x 16 KB residual tiles]
   q.m_tiles = (int)m_tiles;
   q.n_tiles = ceil_div(p.Cout, BN);
-  const int num_tiles = q.m_tiles * q.n_tiles;
-  int grid = std::min(num_tiles, grid_override > 0 ? grid_override : 148);
+  const int num_tiles = (pair ? (q.m_tiles + 1) / 2 : q.m_tiles) * q.n_tiles;   // work units (pairs of M tiles when paired)
+  int grid = std::min(num_tiles, grid_override > 0 ? (pair ? std::max(1, grid_override / 2) : grid_override) : (pair ? 74 : 148));
+  if (pair) grid = std::min(grid, 74);   // one cluster per TPC: 148 SMs = 74 CTA pairs, one CTA per SM
   q.acc_stages = (grid < num_tiles) ? 2 : 1;
   int tmem_cols = 32;
   while (tmem_cols < q.acc_stages * BN) tmem_cols *= 2;
+  // Pairs allocate all of TMEM (and > half of the shared memory, below): one CTA per SM, so both CTAs of a pair
+  // get the SAME accumulator address, which the single cta_group::2 MMA requires.
+  if (pair) tmem_cols = 512;
   q.tmem_cols = tmem_cols;
   const int tiles_per_cta = ceil_div(num_tiles, grid);
   const int out_bytes = 2 * A_STAGE_BYTES;
@@ -615,11 +667,12 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   q.out_off = stages * stage_bytes;
   q.res_off = q.out_off + out_bytes;
   plan->smem_bytes = (size_t)q.res_off + res_bytes + 1024;
-  plan->grid = dim3((unsigned)grid, 1, 1);
+  if (pair) plan->smem_bytes = std::max(plan->smem_bytes, (size_t)120 * 1024);   // at most one pair CTA per SM
+  plan->grid = dim3((unsigned)(pair ? 2 * grid : grid), 1, 1);
 
-  // ---- instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major, N, M=128
+  // ---- instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major, N, M=128 (256 for a CTA pair)
   q.idesc = (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) |
-            ((uint32_t)(BLOCK_M >> 4) << 24);
+            ((uint32_t)((pair ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
 
   // ---- A tensor maps
   const __half* x = reinterpret_cast<const __half*>(p.x);
@@ -660,7 +713,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   {
     uint64_t dims[3] = {(uint64_t)p.Cin, (uint64_t)p.Cout, (uint64_t)q.ntaps};
     uint64_t str[2] = {(uint64_t)p.Cin * 2, (uint64_t)p.Cout * p.Cin * 2};
-    uint32_t box[3] = {(uint32_t)BLOCK_K, (uint32_t)BN, 1};
+    uint32_t box[3] = {(uint32_t)BLOCK_K, (uint32_t)(pair ? BN / 2 : BN), 1};   // a pair CTA loads half a weight tile
     encode_map_f16(&q.tmB, w_packed, 3, dims, str, box);
   }
   // ---- epilogue
@@ -712,45 +765,63 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
 }
 
 void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
-void tc_conv_plan_set_pdl(TcConvPlan* plan, int enable) { plan->prm.pdl = enable ? 1 : 0; }
+void tc_conv_plan_set_pdl(TcConvPlan* plan, int enable) { plan->prm.pdl = (enable && !plan->pair) ? 1 : 0; }
 int tc_conv_plan_bn(const TcConvPlan* plan) { return plan->BN; }
 int tc_conv_plan_stages(const TcConvPlan* plan) { return plan->prm.stages; }
 int tc_conv_plan_grid(const TcConvPlan* plan) { return (int)plan->grid.x; }
+int tc_conv_plan_pair(const TcConvPlan* plan) { return plan->pair; }
 
-template <int BN>
+template <int BN, bool PAIR>
 static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
   static bool attr_set = false;
-  static size_t attr_bytes = 0;
-  if (!attr_set || plan->smem_bytes > attr_bytes) {
-    YB_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (!attr_set) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(220 * 1024)));
     attr_set = true;
-    attr_bytes = 220 * 1024;
   }
-  if (plan->prm.pdl) {
+  if (plan->prm.pdl || PAIR) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = plan->grid;
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = plan->smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (PAIR) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    } else {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN>, plan->prm));
+    cfg.numAttrs = na;
+    YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN, PAIR>, plan->prm));
   } else {
-    tc_conv_kernel<BN><<<plan->grid, NUM_THREADS, plan->smem_bytes, stream>>>(plan->prm);
+    tc_conv_kernel<BN, PAIR><<<plan->grid, NUM_THREADS, plan->smem_bytes, stream>>>(plan->prm);
   }
 }
 
 void launch_tc_conv(const TcConvPlan* plan, cudaStream_t stream, LaunchCounter* lc) {
-  switch (plan->BN) {
-    case 256: launch_bn<256>(plan, stream); break;
-    case 128: launch_bn<128>(plan, stream); break;
-    case 64: launch_bn<64>(plan, stream); break;
-    case 32: launch_bn<32>(plan, stream); break;
-    default: YB_REQUIRE(false, "tc_conv: bad BN");
+  if (plan->pair) {
+    switch (plan->BN) {
+      case 256: launch_bn<256, true>(plan, stream); break;
+      case 128: launch_bn<128, true>(plan, stream); break;
+      case 64: launch_bn<64, true>(plan, stream); break;
+      default: YB_REQUIRE(false, "tc_conv: bad BN for a CTA pair");
+    }
+  } else {
+    switch (plan->BN) {
+      case 256: launch_bn<256, false>(plan, stream); break;
+      case 128: launch_bn<128, false>(plan, stream); break;
+      case 64: launch_bn<64, false>(plan, stream); break;
+      case 32: launch_bn<32, false>(plan, stream); break;
+      default: YB_REQUIRE(false, "tc_conv: bad BN");
+    }
   }
   YB_CHECK_LAUNCH();
   if (lc) lc->n++;
