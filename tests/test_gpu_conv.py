@@ -121,6 +121,10 @@ TC_MODES = {
     # (TMEM double buffering across the pair, odd M-tile counts -> a padding tile in the last pair)
     "pair": {"YB_CONV2D_PAIR": "1"},
     "pair_grid4_bn128": {"YB_CONV2D_PAIR": "1", "YB_CONV2D_GRID": "4", "YB_CONV2D_BN": "128"},
+    # two epilogue groups (8 epilogue warps, even / odd 64-channel chunks), alone, persistent and with CTA pairs
+    "epi2": {"YB_CONV2D_EPI": "2"},
+    "epi2_grid3_bn256": {"YB_CONV2D_EPI": "2", "YB_CONV2D_GRID": "3", "YB_CONV2D_BN": "256"},
+    "pair_epi2": {"YB_CONV2D_PAIR": "1", "YB_CONV2D_EPI": "2"},
 }
 if os.environ.get("YB_TEST_NO_PAIR"):   # escape hatch while the pair kernel is being brought up
     TC_MODES = {k: v for k, v in TC_MODES.items() if not k.startswith("pair")}

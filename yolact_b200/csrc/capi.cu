@@ -127,6 +127,8 @@ int yb_create(const yb_config* cfg, int device, yb_handle** out) {
   h->ops_only = (cfg->backbone == YB_BACKBONE_NONE);
   if (const char* at = getenv("YB_AUTOTUNE")) h->autotune = (atoi(at) != 0);
   if (const char* pc = getenv("YB_PAIR")) h->pair_candidates = (atoi(pc) != 0);
+  if (const char* ec = getenv("YB_EPI2")) h->epi2_candidates = (atoi(ec) != 0);
+  if (const char* sw = getenv("YB_STEM_WG")) h->stem_wg = atoi(sw) == 2 ? 2 : 1;
   if (const char* st = getenv("YB_STEM_TC")) h->stem_on_tc = (atoi(st) != 0);
   if (const char* pd = getenv("YB_PDL")) h->pdl = (atoi(pd) != 0);
   if (const char* fh = getenv("YB_FUSE_HEADS")) h->fuse_heads = (atoi(fh) != 0);
@@ -587,7 +589,8 @@ int yb_conv2d(yb_handle* h, const float* d_x, const float* h_w, const float* h_b
       const char* be = getenv("YB_CONV2D_BN");
       const char* ge = getenv("YB_CONV2D_GRID");
       const char* pe = getenv("YB_CONV2D_PAIR");
-      plan = tc_conv_plan_create(p, wd, be ? atoi(be) : 0, 0, ge ? atoi(ge) : 0, pe ? atoi(pe) : 0);
+      const char* ee = getenv("YB_CONV2D_EPI");
+      plan = tc_conv_plan_create(p, wd, be ? atoi(be) : 0, 0, ge ? atoi(ge) : 0, pe ? atoi(pe) : 0, ee ? atoi(ee) : 0);
     }
     run = [&]() { launch_tc_conv(plan, s, &h->lc); };
   } else if (precision == 2) {

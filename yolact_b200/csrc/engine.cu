@@ -239,7 +239,9 @@ struct NetBuilder {
     if (stem_tc) {
       StemTcPlan* sp = stem_tc_plan_create((const float*)in.ptr, w.w_tc, w.bias, (__half*)out.ptr, in.B, in.H, in.W, k,
                                            stride, pad, w.Cout, act);
+      stem_tc_plan_set_worker_groups(sp, h->stem_wg);
       ex->stem_plans.push_back(sp);
+      op.name += h->stem_wg == 2 ? " stem wg=2" : " stem";
       op.fn = [sp, lc](cudaStream_t s) { launch_stem_tc(sp, s, lc); };
       push(op);
       return out;
@@ -249,7 +251,7 @@ struct NetBuilder {
       TcConvPlan* plan = autotune_tc(p, w.w_tc);
       ex->plans.push_back(plan);
       op.name += " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) + " st=" + std::to_string(tc_conv_plan_stages(plan)) +
-                 " g=" + std::to_string(tc_conv_plan_grid(plan)) + (tc_conv_plan_pair(plan) ? " pair" : "");
+                 " g=" + std::to_string(tc_conv_plan_grid(plan)) + (tc_conv_plan_pair(plan) ? " pair" : "") + (tc_conv_plan_epi_groups(plan) == 2 ? " epi2" : "");
       tc_conv_plan_set_pdl(plan, h->pdl ? 1 : 0);
       op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
     } else {
@@ -414,7 +416,7 @@ struct NetBuilder {
     op.name = hn + ".bbox+conf+mask " + std::to_string(in.C) + "->" + std::to_string(w.Cout) + " k3s1 " +
               std::to_string(in.H) + "x" + std::to_string(in.W) + " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) +
               " st=" + std::to_string(tc_conv_plan_stages(plan)) + " g=" + std::to_string(tc_conv_plan_grid(plan)) +
-              (tc_conv_plan_pair(plan) ? " pair" : "");
+              (tc_conv_plan_pair(plan) ? " pair" : "") + (tc_conv_plan_epi_groups(plan) == 2 ? " epi2" : "");
     op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
     push(op);
   }
@@ -431,7 +433,7 @@ struct NetBuilder {
                              (p.y_f32 ? "f" : "h") + std::to_string(p.nseg) + "," + std::to_string(p.y_pix_stride) + "," + std::to_string((long long)p.y_batch_stride);
     auto it = h->tune_cache.find(tkey);
     if (it != h->tune_cache.end())
-      return tc_conv_plan_create(p, w, it->second[0], it->second[1], it->second[2], it->second[3]);
+      return tc_conv_plan_create(p, w, it->second[0], it->second[1], it->second[2], it->second[3], it->second[4]);
     const int bns[4] = {256, 128, 64, 32};
     const int sts[3] = {0, 3, 2};
     const int grids[3] = {148, 296, 1 << 30};
@@ -441,21 +443,25 @@ struct NetBuilder {
     cudaEvent_t e0, e1;
     YB_CHECK_CUDA(cudaEventCreate(&e0));
     YB_CHECK_CUDA(cudaEventCreate(&e1));
-    // CTA pairs (cta_group::2) are extra candidates: opt-in with YB_PAIR=1 until they have been validated on hardware
+    // extra candidates: CTA pairs (cta_group::2, persistent grid only) and two epilogue groups per CTA
     const int npair = h->pair_candidates ? 2 : 1;
+    const int nepi = h->epi2_candidates ? 2 : 1;
+    for (int ei = 0; ei < nepi; ++ei)
     for (int pi = 0; pi < npair; ++pi)
     for (int bi = 0; bi < 4; ++bi)
       for (int si = 0; si < 3; ++si)
         for (int gi = 0; gi < (pi ? 1 : 3); ++gi) {
           if (bns[bi] > 64 && bns[bi] >= 2 * p.Cout) continue;
           if (pi && bns[bi] < 64) continue;
-          TcConvPlan* cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi], pi);
-          if (pi && !tc_conv_plan_pair(cand)) {
+          if (ei && (bns[bi] < 64 || gi == 1)) continue;   // 320-thread CTAs: one per SM
+          TcConvPlan* cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi], pi, ei ? 2 : 1);
+          if ((pi && !tc_conv_plan_pair(cand)) || (ei && tc_conv_plan_epi_groups(cand) != 2)) {
             tc_conv_plan_destroy(cand);
             continue;
           }
           const std::string ck = std::to_string(tc_conv_plan_bn(cand)) + "/" + std::to_string(tc_conv_plan_stages(cand)) +
-                                 "/" + std::to_string(tc_conv_plan_grid(cand)) + "/" + std::to_string(tc_conv_plan_pair(cand));
+                                 "/" + std::to_string(tc_conv_plan_grid(cand)) + "/" + std::to_string(tc_conv_plan_pair(cand)) + "/" +
+                                 std::to_string(tc_conv_plan_epi_groups(cand));
           if (!seen.insert(ck).second) {  // overrides were clamped to an already-timed configuration
             tc_conv_plan_destroy(cand);
             continue;
@@ -486,7 +492,8 @@ struct NetBuilder {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     YB_REQUIRE(best != nullptr, "autotune: no candidate");
-    h->tune_cache[tkey] = {tc_conv_plan_bn(best), tc_conv_plan_stages(best), tc_conv_plan_grid(best), tc_conv_plan_pair(best)};
+    h->tune_cache[tkey] = {tc_conv_plan_bn(best), tc_conv_plan_stages(best), tc_conv_plan_grid(best), tc_conv_plan_pair(best),
+                           tc_conv_plan_epi_groups(best)};
     return best;
   }
 };

@@ -50,8 +50,10 @@ struct TcConvPlan;  // opaque: tensor maps + tiling; built once per (layer, shap
 // grid_override > 0 caps the number of (persistent) CTAs; default 148 = one per SM.
 // pair_override > 0: CTA pairs (cluster of 2, tcgen05 cta_group::2, UMMA M = 256; each CTA stages half the weight tile).
 TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override = 0,
-                                int stages_override = 0, int grid_override = 0, int pair_override = 0);
+                                int stages_override = 0, int grid_override = 0, int pair_override = 0,
+                                int epi_override = 0);   // epi_override == 2: two 4-warp epilogue groups (320 threads)
 int tc_conv_plan_pair(const TcConvPlan* plan);
+int tc_conv_plan_epi_groups(const TcConvPlan* plan);
 int tc_conv_plan_grid(const TcConvPlan* plan);
 void tc_conv_plan_set_pdl(TcConvPlan* plan, int enable);   // programmatic dependent launch (prologue overlap)
 int tc_conv_plan_bn(const TcConvPlan* plan);
@@ -68,6 +70,7 @@ int stem_tc_kpad(int ks);   // K = 3*ks*ks rounded up to 64
 StemTcPlan* stem_tc_plan_create(const float* x_nchw, const __half* w_packed, const float* bias, __half* y, int B,
                                 int H, int W, int ks, int stride, int pad, int cout, int act);
 void stem_tc_plan_destroy(StemTcPlan* plan);
+void stem_tc_plan_set_worker_groups(StemTcPlan* plan, int wg);   // 2: two threads per pixel (7x7 stem)
 void launch_stem_tc(const StemTcPlan* plan, cudaStream_t stream, LaunchCounter* lc);
 
 // ---- pointwise -------------------------------------------------------------------------------

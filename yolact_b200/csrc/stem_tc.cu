@@ -5,6 +5,8 @@
 // Cin = 3 is useless for TMA (6 bytes per pixel) so the A operand is built by the CUDA cores:
 // each of the 128 worker threads owns one output pixel, gathers its KxKx3 patch straight from the
 // fp32 NCHW frame (zero padding by predication, layout conversion and fp32->fp16 cast fused in),
+// (with WG = 2 worker groups, two threads share a pixel: alternate 16-byte k-groups of the patch, and half of
+// the output channels each in the epilogue -- twice the warps in flight for the latency-bound gather)
 // and writes it as one K-major SWIZZLE_128B row of the UMMA A tile in shared memory
 // (k = c*K*K + r*K + s, the OIHW flattening, so the weights need no permutation).  A fifth warp
 // TMA-loads the [Cout][Kpad] weight tile, issues ceil(K/16) tcgen05.mma (M=128, N=Cout) and commits;
@@ -19,7 +21,7 @@ using namespace tc;
 namespace {
 
 constexpr int ST_M = 128;
-constexpr int ST_THREADS = 160;  // warps 0-3 workers (TMEM lane quadrant == warp), warp 4 MMA
+// threads = 128 * WG workers (TMEM lane quadrant == warp % 4) + one MMA warp
 
 struct alignas(64) StemParams {
   CUtensorMap tmW;
@@ -36,9 +38,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int KS, int STRIDE, int PAD, int COUT>
-__global__ void __launch_bounds__(ST_THREADS)
+template <int KS, int STRIDE, int PAD, int COUT, int WG>
+__global__ void __launch_bounds__(128 * WG + 32)
 stem_tc_kernel(const __grid_constant__ StemParams p) {
+  constexpr int MMA_WARP = 4 * WG;
   constexpr int K = 3 * KS * KS;
   constexpr int ATOMS = (K + 63) / 64;
   constexpr int KSTEPS = (K + 15) / 16;
@@ -54,19 +57,19 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    mbar_init(&a_full, 128);
+    mbar_init(&a_full, 128 * WG);
     mbar_init(&b_full, 1);
     mbar_init(&tmem_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.tmW);
   }
-  if (warp == 4) tmem_alloc<COUT>(&s_tmem);
+  if (warp == MMA_WARP) tmem_alloc<COUT>(&s_tmem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
 
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     if (lane == 0) {
       mbar_expect_tx(&b_full, ATOMS * B_ATOM_BYTES);
       for (int a = 0; a < ATOMS; ++a) tma_load_3d(sB + a * B_ATOM_BYTES, &p.tmW, &b_full, a * 64, 0, 0);
@@ -83,7 +86,8 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
       umma_commit(&tmem_full);
     }
   } else {
-    const int row = tid;
+    const int row = tid & 127;
+    const int wg = tid >> 7;   // worker group: which half of the k-groups / output channels this thread handles
     const long long m = (long long)blockIdx.x * ST_M + row;
     const bool valid = m < p.M;
     int b = 0, ho = 0, wo = 0;
@@ -105,6 +109,7 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
     const uint32_t sw = (uint32_t)(row & 7);
 #pragma unroll
     for (int kg = 0; kg < ATOMS * 8; ++kg) {
+      if (WG > 1 && (kg % WG) != wg) continue;   // warp-uniform
       uint4 pk;
       __half2* h2 = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
@@ -134,8 +139,9 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
     __half* yrow = p.y + m * COUT;
 #pragma unroll
     for (int c0 = 0; c0 < COUT; c0 += 32) {
+      if (WG > 1 && ((c0 >> 5) % WG) != wg) continue;   // warp-uniform
       uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, r);
       if (!valid) continue;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -154,25 +160,25 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<COUT>(tmem_base);
   }
 }
 
-template <int KS, int STRIDE, int PAD, int COUT>
+template <int KS, int STRIDE, int PAD, int COUT, int WG>
 void launch_variant(const StemParams& prm, cudaStream_t stream) {
   constexpr int K = 3 * KS * KS;
   constexpr int ATOMS = (K + 63) / 64;
   const size_t smem = (size_t)ATOMS * (ST_M * 128 + COUT * 128) + 1024;
   static bool attr = false;
   if (!attr) {
-    YB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<KS, STRIDE, PAD, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    YB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<KS, STRIDE, PAD, COUT, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     attr = true;
   }
   const unsigned grid = (unsigned)((prm.M + ST_M - 1) / ST_M);
-  stem_tc_kernel<KS, STRIDE, PAD, COUT><<<grid, ST_THREADS, smem, stream>>>(prm);
+  stem_tc_kernel<KS, STRIDE, PAD, COUT, WG><<<grid, 128 * WG + 32, smem, stream>>>(prm);
 }
 
 }  // namespace
@@ -180,6 +186,7 @@ void launch_variant(const StemParams& prm, cudaStream_t stream) {
 struct StemTcPlan {
   StemParams prm;
   int ks, stride, pad, cout;
+  int wg = 1;   // worker groups (7x7 stem only)
 };
 
 bool stem_tc_supported(int ks, int stride, int pad, int cin, int cout) {
@@ -218,12 +225,17 @@ StemTcPlan* stem_tc_plan_create(const float* x_nchw, const __half* w_packed, con
 }
 
 void stem_tc_plan_destroy(StemTcPlan* plan) { delete plan; }
+void stem_tc_plan_set_worker_groups(StemTcPlan* plan, int wg) { plan->wg = (wg == 2 && plan->ks == 7) ? 2 : 1; }
 
 void launch_stem_tc(const StemTcPlan* plan, cudaStream_t stream, LaunchCounter* lc) {
-  if (plan->ks == 7)
-    launch_variant<7, 2, 3, 64>(plan->prm, stream);
-  else
-    launch_variant<3, 1, 1, 32>(plan->prm, stream);
+  if (plan->ks == 7) {
+    if (plan->wg == 2)
+      launch_variant<7, 2, 3, 64, 2>(plan->prm, stream);
+    else
+      launch_variant<7, 2, 3, 64, 1>(plan->prm, stream);
+  } else {
+    launch_variant<3, 1, 1, 32, 1>(plan->prm, stream);
+  }
   YB_CHECK_LAUNCH();
   if (lc) lc->n++;
 }

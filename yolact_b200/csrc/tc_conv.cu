@@ -36,7 +36,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;              // fp16 elements = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 192;         // 2 + 4*H warps: producer, MMA issuer, H epilogue groups (H = 1 here)
 constexpr int MAX_TAPS = 9;
 constexpr int MAX_STAGES = 8;
 
@@ -190,8 +190,8 @@ __device__ __forceinline__ TileCoord decode_unit(const TcParams& p, int u, int r
   return decode_mn(p, PAIR ? 2 * mg + rank : mg, nt, BN);
 }
 
-template <int BN, bool PAIR>
-__global__ void __launch_bounds__(NUM_THREADS)
+template <int BN, bool PAIR, int H>
+__global__ void __launch_bounds__(64 + 128 * H)
 tc_conv_kernel(const __grid_constant__ TcParams p) {
   constexpr int B_STAGE_BYTES = (PAIR ? BN / 2 : BN) * BLOCK_K * 2;   // a pair CTA stages half of the weight tile
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -203,7 +203,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint64_t res_full_bar[2];
   __shared__ uint32_t s_tmem_base;
-  __shared__ __align__(16) float sbias[BN];
+  __shared__ __align__(16) float sbias[H * BN];   // one copy per epilogue group
 
   // 1024-byte alignment required by SWIZZLE_128B (host adds 1024 bytes of slack)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -228,7 +228,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], PAIR ? 2 : 1);   // pair leader: both CTAs' epilogues drain the accumulator
+      mbar_init(&tmem_empty_bar[i], (PAIR ? 2 : 1) * H);   // every epilogue group (of both CTAs of a pair) drains it
       mbar_init(&res_full_bar[i], 1);
     }
     fence_barrier_init();
@@ -316,80 +316,98 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5 -> TMEM lane quadrant warp%4) =====================
+    // ===================== epilogue: H groups of 4 warps (TMEM lane quadrant = warp % 4) =====================
+    // H == 1: warps 2..5 process every 64-channel chunk of the tile, double-buffered staging tiles.
+    // H == 2: warps 2..5 take the even chunks and warps 6..9 the odd ones, one staging tile (and one
+    //         residual tile) per group: two chunks are in flight at once, which halves the epilogue a CTA
+    //         with a single tile cannot hide behind its main loop.
     const int quad = warp & 3;
+    const int hgrp = (H == 2) ? ((warp - 2) >> 2) : 0;       // epilogue group of this warp
     const int row = quad * 32 + lane;  // accumulator row == tile-local output pixel
-    const int ly = row / p.tw, lx = row - ly * p.tw;
-    const bool issuer = (warp == 2 && lane == 0);
+    const bool issuer = (warp == 2 + 4 * hgrp && lane == 0);
     const bool has_res = (p.residual != nullptr);
     const uint32_t sw = (uint32_t)(row & 7);
-    const int nchunks_full = (min(BN, p.Cout) + 63) >> 6;
+    float* my_bias = sbias + hgrp * BN;
+    constexpr int NBUF = (H == 2) ? 1 : 2;                    // staging / residual tiles per group
+    auto group_sync = [&]() {                                 // the 128 threads of this group
+      if (hgrp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
 
-    // residual chunk stream (epi_tma only): global chunk g lives in res buffer g&1; the issuer keeps it
-    // two chunks ahead of the consumer, across tile boundaries.  (pf_tile, pf_c) = next chunk to fetch.
     const uint32_t leader_tmem_empty = PAIR ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
-    auto release_acc = [&](uint32_t acc) {   // this CTA's 128 epilogue threads have read the accumulator
+    auto release_acc = [&](uint32_t acc) {   // this group's 128 threads have read the accumulator
       if (PAIR && rank != 0)
         mbar_arrive_cluster(leader_tmem_empty + acc * (uint32_t)sizeof(uint64_t));
       else
         mbar_arrive(&tmem_empty_bar[acc]);
     };
-    int pf_tile = unit0, pf_c = 0;
+    // residual chunk stream (epi_tma only): this group's chunks, in order and across tiles; chunk number gq of
+    // the group lives in residual tile (H == 2 ? hgrp : gq & 1); the issuer keeps NBUF chunks in flight.
+    // (pf_tile, pf_c) = next chunk to fetch.
+    int pf_tile = unit0, pf_c = hgrp;
     uint32_t pf_g = 0;
     auto prefetch_res = [&]() {
-      if (pf_tile >= num_units) return;
-      const TileCoord tcp = decode_unit<PAIR>(p, pf_tile, rank, BN);
-      const int nch = (min(BN, p.Cout - tcp.n0) + 63) >> 6;
-      const uint32_t buf = pf_g & 1u;
-      mbar_expect_tx(&res_full_bar[buf], (uint32_t)p.a_box_bytes);
-      tma_load_4d(res_base + buf * A_STAGE_BYTES, &p.tmR, &res_full_bar[buf], tcp.n0 + pf_c * 64, tcp.x0, tcp.y0, tcp.b);
-      ++pf_g;
-      if (++pf_c >= nch) {
-        pf_c = 0;
-        pf_tile += ustep;
+      while (pf_tile < num_units) {
+        const TileCoord tcp = decode_unit<PAIR>(p, pf_tile, rank, BN);
+        const int nch = (min(BN, p.Cout - tcp.n0) + 63) >> 6;
+        if (pf_c >= nch) {            // this group has no (more) chunks in that tile
+          pf_c = hgrp;
+          pf_tile += ustep;
+          continue;
+        }
+        const uint32_t buf = (H == 2) ? (uint32_t)hgrp : (pf_g & 1u);
+        mbar_expect_tx(&res_full_bar[buf], (uint32_t)p.a_box_bytes);
+        tma_load_4d(res_base + buf * A_STAGE_BYTES, &p.tmR, &res_full_bar[buf], tcp.n0 + pf_c * 64, tcp.x0, tcp.y0, tcp.b);
+        ++pf_g;
+        pf_c += H;
+        return;
       }
     };
     if (p.epi_tma && has_res && issuer) {
-      prefetch_res();
-      prefetch_res();
+      for (int i = 0; i < NBUF; ++i) prefetch_res();
     }
 
-    uint32_t t = 0, g = 0;  // local tile counter, global staged-chunk counter
+    uint32_t t = 0, g = 0;  // local tile counter, staged-chunk counter of this group
     for (int u = unit0; u < num_units; u += ustep, ++t) {
       const TileCoord tc_ = decode_unit<PAIR>(p, u, rank, BN);
       const int x0 = tc_.x0, y0 = tc_.y0, b = tc_.b, n0 = tc_.n0;
       const uint32_t acc = t % (uint32_t)acc_stages;
       const uint32_t use = t / (uint32_t)acc_stages;
       const uint32_t tmem_acc = tmem_base + acc * (uint32_t)BN + ((uint32_t)(quad * 32) << 16);
-      // bias of this tile's BN output channels -> shared memory (read back as broadcast float4)
+      // bias of this tile's BN output channels -> this group's copy in shared memory (broadcast float4 reads)
       {
-        const int et = threadIdx.x - 64;   // 0..127 within the epilogue warps
-        for (int j = et; j < BN; j += 128) sbias[j] = (p.bias && n0 + j < p.Cout) ? __ldg(p.bias + n0 + j) : 0.f;
+        const int et = (threadIdx.x - 64) & 127;   // 0..127 within the group
+        for (int j = et; j < BN; j += 128) my_bias[j] = (p.bias && n0 + j < p.Cout) ? __ldg(p.bias + n0 + j) : 0.f;
       }
       mbar_wait(&tmem_full_bar[acc], use & 1u);
       tc_fence_after();
-      epi_bar_sync();   // sbias visible; also: the previous tile's readers of sbias are long done
+      group_sync();   // bias visible; the group's readers of the previous tile's bias are done
 
       if (p.epi_tma) {
         // ---- staged epilogue: TMEM -> regs -> (+bias, +residual from smem, act) -> swizzled smem tile
         //      -> one TMA store per 64-channel chunk (full 128-byte lines, OOB rows clipped by hardware)
         const int nchunks = (min(BN, p.Cout - n0) + 63) >> 6;
+        const int c_last = ((nchunks - 1 - hgrp) / H) * H + hgrp;   // this group's last chunk (< hgrp: none)
+        if (nchunks <= hgrp) {   // nothing to read for this group in this tile
+          tc_fence_before();
+          if (issuer) release_acc(acc);
+        }
 #pragma unroll 1
-        for (int c = 0; c < nchunks; ++c, ++g) {
-          const uint32_t buf = g & 1u;
+        for (int c = hgrp; c < nchunks; c += H, ++g) {
+          const uint32_t buf = (H == 2) ? (uint32_t)hgrp : (g & 1u);
           uint8_t* out_tile = out_base + buf * A_STAGE_BYTES;
           uint8_t* res_tile = res_base + buf * A_STAGE_BYTES;
-          if (g >= 2) {
-            if (issuer) bulk_wait_read<1>();  // the store that used this buffer two chunks ago has read it
-            epi_bar_sync();
+          if (g >= (uint32_t)NBUF) {
+            if (issuer) bulk_wait_read<NBUF - 1>();  // the store that last used this staging tile has read it
+            group_sync();
           }
           uint32_t r0[32], r1[32];
           tmem_ld32_nowait(tmem_acc + (uint32_t)(c * 64), r0);
           tmem_ld32_nowait(tmem_acc + (uint32_t)(c * 64 + 32), r1);
           tmem_ld_wait();
-          if (has_res) mbar_wait(&res_full_bar[buf], (g >> 1) & 1u);
+          if (has_res) mbar_wait(&res_full_bar[buf], (H == 2) ? (g & 1u) : ((g >> 1) & 1u));
           const int nbase = n0 + c * 64;
-          const float* sb = sbias + c * 64;
+          const float* sb = my_bias + c * 64;
           const uint8_t* rt = has_res ? res_tile : nullptr;
           switch (p.act) {
             case ACT_RELU: epi_chunk<ACT_RELU, false>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw); break;
@@ -403,23 +421,23 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             default: epi_chunk<ACT_NONE, false>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw); break;
           }
           fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-          if (c == nchunks - 1) tc_fence_before();
-          epi_bar_sync();
+          if (c == c_last) tc_fence_before();
+          group_sync();
           if (issuer) {
-            if (c == nchunks - 1) release_acc(acc);  // all 128 threads have read their rows
+            if (c == c_last) release_acc(acc);  // all 128 threads of the group have read their rows
             tma_store_4d(&p.tmY, out_tile, nbase, x0, y0, b);
             bulk_commit();
-            if (has_res) prefetch_res();   // everyone is done reading res_tile[buf]: refill it two chunks ahead
+            if (has_res) prefetch_res();   // the group is done reading res_tile[buf]: refill it
           }
         }
       } else {
         // ---- direct epilogue (fp32 / unaligned outputs: the head tensors): each warp transposes its
         //      32 rows x 32 columns through shared memory so that a store instruction writes 32
         //      consecutive channels of ONE pixel (coalesced), not one channel of 32 pixels.
-        float* tbuf = reinterpret_cast<float*>(out_base) + quad * (32 * 33);
+        float* tbuf = reinterpret_cast<float*>(out_base) + (hgrp * 4 + quad) * (32 * 33);
         const int ncols = min(BN, p.Cout - n0);
 #pragma unroll 1
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
+        for (int c0 = hgrp * 32; c0 < ncols; c0 += 32 * H) {
           uint32_t r[32];
           tmem_ld32(tmem_acc + (uint32_t)c0, r);
           const int nbase = n0 + c0;
@@ -428,7 +446,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
           __syncwarp();
-          const float bias_l = sbias[c0 + lane];
+          const float bias_l = my_bias[c0 + lane];
           int act = p.act;
           const int raa = p.res_after_act;
           // fused prediction head: this lane's channel belongs to one of up to 3 output tensors
@@ -471,14 +489,11 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           }
         }
         tc_fence_before();
-        epi_bar_sync();
+        group_sync();
         if (issuer) release_acc(acc);
       }
     }
     if (p.epi_tma && issuer) bulk_wait_read<0>();  // smem must outlive the bulk reads
-    (void)nchunks_full;
-    (void)ly;
-    (void)lx;
   }
 
   tc_fence_before();
@@ -546,6 +561,7 @@ struct TcConvPlan {
   TcParams prm;
   int BN = 128;
   int pair = 0;
+  int epi_groups = 1;   // H: 4-warp epilogue groups per CTA
   dim3 grid;
   size_t smem_bytes = 0;
 };
@@ -560,7 +576,7 @@ bool tc_conv_supported(const ConvProblem& p) {
 }
 
 TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override, int stages_override,
-                                int grid_override, int pair_override) {
+                                int grid_override, int pair_override, int epi_override) {
   YB_REQUIRE(tc_conv_supported(p), "tc_conv: unsupported problem");
   YB_REQUIRE(p.Ho == (p.H + 2 * p.pad - p.KH) / p.stride + 1, "tc_conv: bad Ho");
   YB_REQUIRE(p.Wo == (p.W + 2 * p.pad - p.KW) / p.stride + 1, "tc_conv: bad Wo");
@@ -658,7 +674,11 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   if (pair) tmem_cols = 512;
   q.tmem_cols = tmem_cols;
   const int tiles_per_cta = ceil_div(num_tiles, grid);
-  const int out_bytes = 2 * A_STAGE_BYTES;
+  // two epilogue groups (8 warps) work on two 64-channel chunks at once; pointless for a single-chunk tile
+  plan->epi_groups = (epi_override == 2 && BN >= 64) ? 2 : 1;
+  // staging: 2 x 16 KB tiles (one per group when there are two); the direct (fp32) epilogue needs a padded
+  // 32x33 float transpose buffer per epilogue warp
+  const int out_bytes = plan->epi_groups == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES;
   const int res_bytes = (q.epi_tma && p.residual) ? 2 * A_STAGE_BYTES : 0;
   int stages = std::min(MAX_STAGES, (200 * 1024 - out_bytes - res_bytes) / stage_bytes);
   if (stages_override > 0) stages = std::min(stages, stages_override);
@@ -770,19 +790,21 @@ int tc_conv_plan_bn(const TcConvPlan* plan) { return plan->BN; }
 int tc_conv_plan_stages(const TcConvPlan* plan) { return plan->prm.stages; }
 int tc_conv_plan_grid(const TcConvPlan* plan) { return (int)plan->grid.x; }
 int tc_conv_plan_pair(const TcConvPlan* plan) { return plan->pair; }
+int tc_conv_plan_epi_groups(const TcConvPlan* plan) { return plan->epi_groups; }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, int H>
 static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    YB_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    YB_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, PAIR, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(220 * 1024)));
     attr_set = true;
   }
+  constexpr int THREADS = 64 + 128 * H;
   if (plan->prm.pdl || PAIR) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = plan->grid;
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = plan->smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -800,26 +822,34 @@ static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN, PAIR>, plan->prm));
+    YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN, PAIR, H>, plan->prm));
   } else {
-    tc_conv_kernel<BN, PAIR><<<plan->grid, NUM_THREADS, plan->smem_bytes, stream>>>(plan->prm);
+    tc_conv_kernel<BN, PAIR, H><<<plan->grid, THREADS, plan->smem_bytes, stream>>>(plan->prm);
   }
+}
+
+template <int BN, bool PAIR>
+static void launch_h(const TcConvPlan* plan, cudaStream_t stream) {
+  if (plan->epi_groups == 2)
+    launch_bn<BN, PAIR, (BN >= 64 ? 2 : 1)>(plan, stream);
+  else
+    launch_bn<BN, PAIR, 1>(plan, stream);
 }
 
 void launch_tc_conv(const TcConvPlan* plan, cudaStream_t stream, LaunchCounter* lc) {
   if (plan->pair) {
     switch (plan->BN) {
-      case 256: launch_bn<256, true>(plan, stream); break;
-      case 128: launch_bn<128, true>(plan, stream); break;
-      case 64: launch_bn<64, true>(plan, stream); break;
+      case 256: launch_h<256, true>(plan, stream); break;
+      case 128: launch_h<128, true>(plan, stream); break;
+      case 64: launch_h<64, true>(plan, stream); break;
       default: YB_REQUIRE(false, "tc_conv: bad BN for a CTA pair");
     }
   } else {
     switch (plan->BN) {
-      case 256: launch_bn<256, false>(plan, stream); break;
-      case 128: launch_bn<128, false>(plan, stream); break;
-      case 64: launch_bn<64, false>(plan, stream); break;
-      case 32: launch_bn<32, false>(plan, stream); break;
+      case 256: launch_h<256, false>(plan, stream); break;
+      case 128: launch_h<128, false>(plan, stream); break;
+      case 64: launch_h<64, false>(plan, stream); break;
+      case 32: launch_h<32, false>(plan, stream); break;
       default: YB_REQUIRE(false, "tc_conv: bad BN");
     }
   }
