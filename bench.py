@@ -259,12 +259,25 @@ def main():
     n_rot = 6  # 6 distinct input batches (6 x 29 MB = 174 MB > 126 MB L2) rotate through the loop
     xs = [deterministic_input(B, size, size, 1234 + 100 * rank + i).to(dev) for i in range(n_rot)]
     M, k = cfg.max_num_detections, cfg.mask_dim
-    masks_f32 = torch.empty(B, M, size, size, dtype=torch.float32, device=dev)
+    # Two compute streams: the mask assembly of step i (HBM-write bound) runs on s_post while the conv stack of step
+    # i+1 (tensor / L2 bound) already runs on the main stream; outputs are double-buffered.  BENCH_OVERLAP=0 serialises.
+    overlap = os.environ.get("BENCH_OVERLAP", "1") != "0"
+    masks_f32 = [torch.empty(B, M, size, size, dtype=torch.float32, device=dev) for _ in range(2 if overlap else 1)]
+    s_post = torch.cuda.Stream() if overlap else None
 
     def step_device(i, fmt="f32", out=None):
         box, coef, cls, score, count, proto = net.infer_padded(xs[i % n_rot])
         # all M padded rows are assembled (no host sync on the count); with these weights count == M
-        res = assemble_masks_batch(proto, coef, box, size, size, True, fmt, masks_out=out)
+        if overlap:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(s_post):
+                s_post.wait_event(ev)
+                for t_ in (box, coef, proto):
+                    t_.record_stream(s_post)
+                res = assemble_masks_batch(proto, coef, box, size, size, True, fmt, masks_out=out[i % 2])
+        else:
+            res = assemble_masks_batch(proto, coef, box, size, size, True, fmt, masks_out=out[0])
         if world > 1:
             gather_detections(box, coef, cls, score, count, per_rank_batch=B)
         return box, coef, cls, score, count, res
@@ -282,6 +295,8 @@ def main():
         e0.record()
         for i in range(steps):
             fn(warmup + i)
+        if s_post is not None:
+            torch.cuda.current_stream().wait_stream(s_post)   # the last steps' mask assembly is inside the timed region
         e1.record()
         barrier_sync()
         ms = e0.elapsed_time(e1)
@@ -321,6 +336,7 @@ def main():
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_comp = [torch.cuda.Event() for _ in range(2)]
+    ev_post = [torch.cuda.Event() for _ in range(2)]
     ev_d2h = [torch.cuda.Event() for _ in range(2)]
     state = {"n": 0}
 
@@ -335,12 +351,22 @@ def main():
             ev_in[k].record(s_in)
         s_main.wait_event(ev_in[k])
         if i >= 2:
-            s_main.wait_event(ev_d2h[k])             # d_masks[k] / d_boxes[k] were last read by step i-2's D2H
+            # d_masks[k] / d_boxes[k] were last read by step i-2's D2H
+            (s_post if overlap else s_main).wait_event(ev_d2h[k])
         box, coef, cls, score, count, proto = net.infer_padded(dx[k])
-        assemble_masks_batch(proto, coef, box, size, size, True, "bits", masks_out=d_masks[k], boxes_out=d_boxes[k])
-        ev_comp[k].record(s_main)
+        ev_comp[k].record(s_main)                    # dx[k] is free again once the network has read it
+        if overlap:
+            with torch.cuda.stream(s_post):
+                s_post.wait_event(ev_comp[k])
+                for t_ in (box, coef, proto):
+                    t_.record_stream(s_post)
+                assemble_masks_batch(proto, coef, box, size, size, True, "bits", masks_out=d_masks[k], boxes_out=d_boxes[k])
+                ev_post[k].record(s_post)
+        else:
+            assemble_masks_batch(proto, coef, box, size, size, True, "bits", masks_out=d_masks[k], boxes_out=d_boxes[k])
+            ev_post[k].record(s_main)
         with torch.cuda.stream(s_out):
-            s_out.wait_event(ev_comp[k])
+            s_out.wait_event(ev_post[k])
             for t in (cls, score, count):
                 t.record_stream(s_out)
             h_cls[k].copy_(cls, non_blocking=True)
@@ -366,6 +392,8 @@ def main():
         step_e2e(i)
     e2e_drain()
     s_main.wait_stream(s_out)
+    if s_post is not None:
+        s_main.wait_stream(s_post)
     e1.record()
     barrier_sync()
     ms_e2e = e0.elapsed_time(e1)
@@ -407,10 +435,12 @@ def main():
         "config": {"workload": workload, "global_batch": world * B, "image_size": size, "parallelism": "dp%d" % world,
                    "detections_per_image": M, "mask_format_value": "f32 [n,h,w]", "mask_format_e2e": "1 bit/pixel",
                    "l2": "6 rotating input batches (174 MB) and ~2 GB of activations+masks per step exceed the 126 MB L2",
-                   "cuda_graph": True},
+                   "cuda_graph": True,
+                   "streams": "mask assembly of step i overlaps the conv stack of step i+1 (2 compute streams)" if overlap
+                              else "single compute stream"},
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "host_wall_ms_per_step": wall_e2e / args.steps,
-                "pipelining": "3 streams, double-buffered: H2D(i+1) | compute(i) | D2H(i-1); host blocks on each step's D2H"},
+                "pipelining": "double-buffered streams: H2D(i+1) | network(i+1) | mask assembly(i) | D2H(i-1); host blocks on each step's D2H"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -120,26 +120,33 @@ mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
 
     // ---- stream out the band -------------------------------------------------------------
     if (FORMAT == YB_MASK_BITS) {
+      // one warp per output word: lane j evaluates pixel 32*wx + j, the ballot is the packed word
       uint32_t* out = reinterpret_cast<uint32_t*>(masks_v) + (size_t)d * out_h * wpr;
       const int words = (y1 - y0) * wpr;
-      for (int wi = tid; wi < words; wi += MT) {
-        const int yy = wi / wpr, wx = wi - yy * wpr;
-        const int y = y0 + yy;
-        uint32_t bits = 0u;
-        if (any) {
+      if (!any) {
+        for (int wi = tid; wi < words; wi += MT) out[(size_t)y0 * wpr + wi] = 0u;   // the band's words are contiguous
+      } else {
+        const int wrp = tid >> 5, lane = tid & 31;
+        for (int wi = wrp; wi < words; wi += MT / 32) {
+          const int yy = wi / wpr, wx = wi - yy * wpr;
+          const int y = y0 + yy;
+          const int x = wx * 32 + lane;
           const ColTab rt = interp_entry(y, scale_h, ph);
-          const float* ra = mrows + (size_t)(rt.i0 - r_lo) * pw;
-          const float* rb = mrows + (size_t)(rt.i1 - r_lo) * pw;
-          const int xe = min(out_w - wx * 32, 32);
-          for (int j = 0; j < xe; ++j) {
-            const ColTab ct = coltab[wx * 32 + j];
+          // both source rows outside the crop window -> the whole output row is zero
+          const bool row_live = ((float)rt.i0 >= cy1 && (float)rt.i0 < cy2) || ((float)rt.i1 >= cy1 && (float)rt.i1 < cy2);
+          bool bit = false;
+          if (row_live && x < out_w) {
+            const float* ra = mrows + (size_t)(rt.i0 - r_lo) * pw;
+            const float* rb = mrows + (size_t)(rt.i1 - r_lo) * pw;
+            const ColTab ct = coltab[x];
             float top = __fadd_rn(__fmul_rn(ct.l0, ra[ct.i0]), __fmul_rn(ct.l1, ra[ct.i1]));
             float bot = __fadd_rn(__fmul_rn(ct.l0, rb[ct.i0]), __fmul_rn(ct.l1, rb[ct.i1]));
             float v = __fadd_rn(__fmul_rn(rt.l0, top), __fmul_rn(rt.l1, bot));
-            bits |= (v > 0.5f ? 1u : 0u) << j;
+            bit = v > 0.5f;
           }
+          const uint32_t word = __ballot_sync(0xffffffffu, bit);
+          if (lane == 0) out[(size_t)y * wpr + wx] = word;
         }
-        out[(size_t)y * wpr + wx] = bits;
       }
     } else {
       // The band of one detection is contiguous in memory: stream it as aligned 4-pixel quads
