@@ -79,6 +79,42 @@ mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
 
   const size_t plane = (size_t)out_h * out_w;
   const int wpr = (out_w + 31) >> 5;  // words per row, bit format
+  const int L = (y1 - y0) * out_w;    // elements of one detection's band (contiguous in memory)
+
+  // ---- phase A (fp32 / uint8): zero the band of EVERY detection of the group in one flat, memset-like loop of
+  //      aligned 4-element stores (streaming: the masks are never read back here).  Phase B below then writes only
+  //      the ones, inside the crop window of the detections that reach this band -- a few % of the pixels -- so
+  //      the bulk of the output moves at the plain store rate instead of behind per-pixel interpolation code.
+  if (FORMAT != YB_MASK_BITS) {
+    constexpr size_t esz = (FORMAT == YB_MASK_F32) ? 4 : 1;
+    const int nq_max = (L + 6) >> 2;   // quads per band incl. a possible leading / trailing partial quad
+    const int total = (d1 - d0) * nq_max;
+    for (int i = tid; i < total; i += MT) {
+      const int dd = i / nq_max, q = i - dd * nq_max;
+      const size_t band_off = (size_t)(d0 + dd) * plane + (size_t)y0 * out_w;
+      // elements to the previous 4-element boundary of the ACTUAL address (the per-image offset of a batched
+      // call need not be 16-byte aligned)
+      const int lead = (int)(((reinterpret_cast<uintptr_t>(masks_v) / esz) + band_off) & 3);
+      const int i0 = 4 * q - lead;
+      if (i0 >= L) continue;
+      if (i0 >= 0 && i0 + 4 <= L) {
+        if (FORMAT == YB_MASK_F32)
+          __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(masks_v) + band_off + i0), make_float4(0.f, 0.f, 0.f, 0.f));
+        else
+          *reinterpret_cast<uchar4*>(reinterpret_cast<unsigned char*>(masks_v) + band_off + i0) = make_uchar4(0, 0, 0, 0);
+      } else {
+        for (int j = 0; j < 4; ++j) {
+          const int idx = i0 + j;
+          if (idx < 0 || idx >= L) continue;
+          if (FORMAT == YB_MASK_F32)
+            reinterpret_cast<float*>(masks_v)[band_off + idx] = 0.f;
+          else
+            reinterpret_cast<unsigned char*>(masks_v)[band_off + idx] = 0;
+        }
+      }
+    }
+    __syncthreads();   // orders the zero stores before this CTA's phase-B stores to the same addresses
+  }
 
   for (int d = d0; d < d1; ++d) {
     // crop window in prototype coordinates (box_utils.py:359-371)
@@ -148,70 +184,37 @@ mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
           if (lane == 0) out[(size_t)y * wpr + wx] = word;
         }
       }
-    } else {
-      // The band of one detection is contiguous in memory: stream it as aligned 4-pixel quads
-      // (16-byte stores for fp32, 4-byte for uint8); quads may straddle a row boundary.
+    } else if (any) {
+      // ---- phase B: only the output columns whose interpolation sources can fall inside the crop window
+      //      (a conservative superset: pixels outside interpolate zeros), only the ones are stored.
+      int xa = (int)floorf(__fdiv_rn(cx1 - 0.5f, scale_w) - 0.5f) - 1;
+      int xb = (int)ceilf(__fdiv_rn(cx2 + 0.5f, scale_w) - 0.5f) + 2;
+      xa = max(xa, 0);
+      xb = min(xb, out_w);
+      const int xw = xb - xa;
       const size_t band_off = (size_t)d * plane + (size_t)y0 * out_w;
-      const int L = (y1 - y0) * out_w;
-      // elements to the previous 4-element boundary of the ACTUAL address (the per-image offset of a
-      // batched call need not be 16-byte aligned)
-      const size_t esz = (FORMAT == YB_MASK_F32) ? 4 : 1;
-      const int lead = (int)(((reinterpret_cast<uintptr_t>(masks_v) / esz) + band_off) & 3);
-      const int nq = (L + lead + 3) >> 2;
-      for (int q = tid; q < nq; q += MT) {
-        const int i0 = 4 * q - lead;
-        float res[4] = {0.f, 0.f, 0.f, 0.f};
-        if (any) {
-          int idx = max(i0, 0);
-          int yy = idx / out_w, x = idx - yy * out_w;
-          int cur_y = -1;
-          ColTab rt;
-          const float *ra = mrows, *rb = mrows;
-          bool row_live = false;
-          for (int j = max(0, -i0); j < 4 && i0 + j < L; ++j) {
-            if (yy != cur_y) {
-              cur_y = yy;
-              rt = interp_entry(y0 + yy, scale_h, ph);
-              ra = mrows + (size_t)(rt.i0 - r_lo) * pw;
-              rb = mrows + (size_t)(rt.i1 - r_lo) * pw;
-              // both source rows outside the crop window -> the whole output row is zero
-              row_live = ((float)rt.i0 >= cy1 && (float)rt.i0 < cy2) || ((float)rt.i1 >= cy1 && (float)rt.i1 < cy2);
-            }
-            if (row_live) {
-              const ColTab ct = coltab[x];
-              if (((float)ct.i0 >= cx1 && (float)ct.i0 < cx2) || ((float)ct.i1 >= cx1 && (float)ct.i1 < cx2)) {
-                float top = __fadd_rn(__fmul_rn(ct.l0, ra[ct.i0]), __fmul_rn(ct.l1, ra[ct.i1]));
-                float bot = __fadd_rn(__fmul_rn(ct.l0, rb[ct.i0]), __fmul_rn(ct.l1, rb[ct.i1]));
-                float v = __fadd_rn(__fmul_rn(rt.l0, top), __fmul_rn(rt.l1, bot));
-                res[j] = v > 0.5f ? 1.f : 0.f;
-              }
-            }
-            if (++x == out_w) {
-              x = 0;
-              ++yy;
-            }
-          }
-        }
-        if (i0 >= 0 && i0 + 4 <= L) {
+      for (int idx = tid; idx < (y1 - y0) * xw; idx += MT) {
+        const int yy = idx / xw;
+        const int x = xa + (idx - yy * xw);
+        const ColTab rt = interp_entry(y0 + yy, scale_h, ph);
+        // both source rows outside the crop window -> the whole output row is zero
+        if (!(((float)rt.i0 >= cy1 && (float)rt.i0 < cy2) || ((float)rt.i1 >= cy1 && (float)rt.i1 < cy2))) continue;
+        const ColTab ct = coltab[x];
+        if (!(((float)ct.i0 >= cx1 && (float)ct.i0 < cx2) || ((float)ct.i1 >= cx1 && (float)ct.i1 < cx2))) continue;
+        const float* ra = mrows + (size_t)(rt.i0 - r_lo) * pw;
+        const float* rb = mrows + (size_t)(rt.i1 - r_lo) * pw;
+        float top = __fadd_rn(__fmul_rn(ct.l0, ra[ct.i0]), __fmul_rn(ct.l1, ra[ct.i1]));
+        float bot = __fadd_rn(__fmul_rn(ct.l0, rb[ct.i0]), __fmul_rn(ct.l1, rb[ct.i1]));
+        float v = __fadd_rn(__fmul_rn(rt.l0, top), __fmul_rn(rt.l1, bot));
+        if (v > 0.5f) {
           if (FORMAT == YB_MASK_F32)
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(masks_v) + band_off + i0) =
-                make_float4(res[0], res[1], res[2], res[3]);
+            reinterpret_cast<float*>(masks_v)[band_off + (size_t)yy * out_w + x] = 1.f;
           else
-            *reinterpret_cast<uchar4*>(reinterpret_cast<unsigned char*>(masks_v) + band_off + i0) =
-                make_uchar4((unsigned char)res[0], (unsigned char)res[1], (unsigned char)res[2], (unsigned char)res[3]);
-        } else {
-          for (int j = 0; j < 4; ++j) {
-            const int idx = i0 + j;
-            if (idx < 0 || idx >= L) continue;
-            if (FORMAT == YB_MASK_F32)
-              reinterpret_cast<float*>(masks_v)[band_off + idx] = res[j];
-            else
-              reinterpret_cast<unsigned char*>(masks_v)[band_off + idx] = (unsigned char)res[j];
-          }
+            reinterpret_cast<unsigned char*>(masks_v)[band_off + (size_t)yy * out_w + x] = 1;
         }
       }
     }
-    __syncthreads();  // mrows / s_coef reuse
+    if (any) __syncthreads();  // mrows / s_coef reuse
   }
 }
 
