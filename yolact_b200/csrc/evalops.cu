@@ -155,7 +155,7 @@ box_iou_kernel(const float* __restrict__ a, int n, const float* __restrict__ b, 
 // -------------------------------------------------------------------------------------------------
 // COCO RLE
 // -------------------------------------------------------------------------------------------------
-constexpr int RLE_THREADS = 256;
+constexpr int RLE_MAX_THREADS = 1024;   // one thread per mask column when w <= 1024 (one pass over the mask)
 
 template <int FORMAT>
 struct MaskReader {
@@ -181,8 +181,8 @@ __device__ __forceinline__ int rle_block_scan(int v, int* s_warp, int* total) {
   if (lane == 31) s_warp[wid] = inc;
   __syncthreads();
   int woff = 0, tot = 0;
-#pragma unroll
-  for (int w = 0; w < RLE_THREADS / 32; ++w) {
+  const int nwarps = (int)(blockDim.x >> 5);
+  for (int w = 0; w < nwarps; ++w) {
     int c = s_warp[w];
     if (w < wid) woff += c;
     tot += c;
@@ -191,20 +191,21 @@ __device__ __forceinline__ int rle_block_scan(int v, int* s_warp, int* total) {
   return woff + inc - v;
 }
 
-// One CTA per mask.  Thread t walks column c0+t top to bottom (reads are coalesced across the CTA),
+// One CTA per mask, one thread per column (up to 1024 per pass).  Thread t walks column c0+t top to bottom (reads are coalesced across the CTA),
 // once to count value changes and once to emit their column-major positions; a final in-place pass
 // turns positions into run lengths.  counts[0] is the number of leading zeros (0 when the mask starts
 // with a one), exactly maskApi.c's rleEncode.
 template <int FORMAT>
-__global__ void __launch_bounds__(RLE_THREADS)
+__global__ void __launch_bounds__(RLE_MAX_THREADS)
 mask_rle_kernel(const void* __restrict__ masks, size_t mask_stride_bytes, int h, int w, int wpr,
                 uint32_t* __restrict__ counts, int64_t cap, int32_t* __restrict__ nruns) {
-  __shared__ int s_warp[RLE_THREADS / 32];
+  __shared__ int s_warp[RLE_MAX_THREADS / 32];
+  const int NT = (int)blockDim.x;
   const int d = blockIdx.x, tid = threadIdx.x;
   MaskReader<FORMAT> px{reinterpret_cast<const uint8_t*>(masks) + (size_t)d * mask_stride_bytes, w, wpr};
   uint32_t* out = counts + (int64_t)d * cap;
   int64_t base = 0;   // transitions emitted by previous column chunks
-  for (int c0 = 0; c0 < w; c0 += RLE_THREADS) {
+  for (int c0 = 0; c0 < w; c0 += NT) {
     const int x = c0 + tid;
     const bool active = x < w;
     const int first_prev = (active && x > 0) ? px(h - 1, x - 1) : 0;
@@ -246,7 +247,7 @@ mask_rle_kernel(const void* __restrict__ masks, size_t mask_stride_bytes, int h,
   }
   __syncthreads();
   // positions -> lengths, in place, from the back (a chunk only reads entries at or below itself)
-  for (int64_t hi = T; hi > 0; hi -= RLE_THREADS) {
+  for (int64_t hi = T; hi > 0; hi -= NT) {
     const int64_t i = hi - 1 - tid;
     uint32_t cur = 0, prv = 0;
     if (i >= 0) {
@@ -375,15 +376,16 @@ void launch_mask_rle(const void* masks, int mask_format, int n, int h, int w, ui
   YB_REQUIRE(h > 0 && w > 0 && (int64_t)h * w < (1ll << 32), "mask_rle: bad mask size");
   YB_REQUIRE(cap >= 1, "mask_rle: cap must be >= 1");
   const int wpr = ceil_div(w, 32);
+  const int threads = std::min(RLE_MAX_THREADS, ceil_div(w, 32) * 32);
   switch (mask_format) {
     case YB_MASK_BITS:
-      mask_rle_kernel<YB_MASK_BITS><<<n, RLE_THREADS, 0, stream>>>(masks, (size_t)h * wpr * 4, h, w, wpr, counts, cap, nruns);
+      mask_rle_kernel<YB_MASK_BITS><<<n, threads, 0, stream>>>(masks, (size_t)h * wpr * 4, h, w, wpr, counts, cap, nruns);
       break;
     case YB_MASK_U8:
-      mask_rle_kernel<YB_MASK_U8><<<n, RLE_THREADS, 0, stream>>>(masks, (size_t)h * w, h, w, wpr, counts, cap, nruns);
+      mask_rle_kernel<YB_MASK_U8><<<n, threads, 0, stream>>>(masks, (size_t)h * w, h, w, wpr, counts, cap, nruns);
       break;
     case YB_MASK_F32:
-      mask_rle_kernel<YB_MASK_F32><<<n, RLE_THREADS, 0, stream>>>(masks, (size_t)h * w * 4, h, w, wpr, counts, cap, nruns);
+      mask_rle_kernel<YB_MASK_F32><<<n, threads, 0, stream>>>(masks, (size_t)h * w * 4, h, w, wpr, counts, cap, nruns);
       break;
     default: YB_REQUIRE(false, "mask_rle: unknown mask format");
   }

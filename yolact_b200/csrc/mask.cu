@@ -13,6 +13,8 @@
 // the CTA evaluates the cropped sigmoid mask on the few prototype rows the band interpolates from
 // (crop happens BEFORE the upsample, output_utils.py:72-74: each output pixel interpolates four
 // already-cropped values), parks them in shared memory and streams out the band.
+#include <stdlib.h>
+#include <algorithm>
 #include "kernels.cuh"
 
 namespace yb {
@@ -60,7 +62,6 @@ mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
   extern __shared__ unsigned char smem_raw[];
   ColTab* coltab = reinterpret_cast<ColTab*>(smem_raw);                 // [out_w]
   float* mrows = reinterpret_cast<float*>(coltab + out_w);               // [max_rows][pw]
-  float* s_coef = mrows + (size_t)max_rows * pw;                         // [k]
 
   const int tid = threadIdx.x;
   const int y0 = blockIdx.x * band;
@@ -87,30 +88,26 @@ mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
   //      the bulk of the output moves at the plain store rate instead of behind per-pixel interpolation code.
   if (FORMAT != YB_MASK_BITS) {
     constexpr size_t esz = (FORMAT == YB_MASK_F32) ? 4 : 1;
-    const int nq_max = (L + 6) >> 2;   // quads per band incl. a possible leading / trailing partial quad
-    const int total = (d1 - d0) * nq_max;
-    for (int i = tid; i < total; i += MT) {
-      const int dd = i / nq_max, q = i - dd * nq_max;
-      const size_t band_off = (size_t)(d0 + dd) * plane + (size_t)y0 * out_w;
-      // elements to the previous 4-element boundary of the ACTUAL address (the per-image offset of a batched
+    for (int d = d0; d < d1; ++d) {
+      const size_t band_off = (size_t)d * plane + (size_t)y0 * out_w;
+      // elements up to the next 4-element boundary of the ACTUAL address (the per-image offset of a batched
       // call need not be 16-byte aligned)
-      const int lead = (int)(((reinterpret_cast<uintptr_t>(masks_v) / esz) + band_off) & 3);
-      const int i0 = 4 * q - lead;
-      if (i0 >= L) continue;
-      if (i0 >= 0 && i0 + 4 <= L) {
-        if (FORMAT == YB_MASK_F32)
-          __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(masks_v) + band_off + i0), make_float4(0.f, 0.f, 0.f, 0.f));
-        else
-          *reinterpret_cast<uchar4*>(reinterpret_cast<unsigned char*>(masks_v) + band_off + i0) = make_uchar4(0, 0, 0, 0);
+      const int head = (int)((4 - (((reinterpret_cast<uintptr_t>(masks_v) / esz) + band_off) & 3)) & 3);
+      const int hd = min(head, L);
+      const int nq = (L - hd) >> 2;            // aligned 4-element stores
+      const int tail = L - hd - 4 * nq;        // < 4 trailing elements
+      if (FORMAT == YB_MASK_F32) {
+        float* base = reinterpret_cast<float*>(masks_v) + band_off;
+        float4* body = reinterpret_cast<float4*>(base + hd);
+        for (int q = tid; q < nq; q += MT) __stcs(body + q, make_float4(0.f, 0.f, 0.f, 0.f));
+        if (tid < hd) base[tid] = 0.f;
+        if (tid < tail) base[hd + 4 * nq + tid] = 0.f;
       } else {
-        for (int j = 0; j < 4; ++j) {
-          const int idx = i0 + j;
-          if (idx < 0 || idx >= L) continue;
-          if (FORMAT == YB_MASK_F32)
-            reinterpret_cast<float*>(masks_v)[band_off + idx] = 0.f;
-          else
-            reinterpret_cast<unsigned char*>(masks_v)[band_off + idx] = 0;
-        }
+        unsigned char* base = reinterpret_cast<unsigned char*>(masks_v) + band_off;
+        uchar4* body = reinterpret_cast<uchar4*>(base + hd);
+        for (int q = tid; q < nq; q += MT) body[q] = make_uchar4(0, 0, 0, 0);
+        if (tid < hd) base[tid] = 0;
+        if (tid < tail) base[hd + 4 * nq + tid] = 0;
       }
     }
     __syncthreads();   // orders the zero stores before this CTA's phase-B stores to the same addresses
@@ -130,26 +127,32 @@ mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
     any &= (cx1 < cx2);
 
     if (any) {
-      for (int j = tid; j < k; j += MT) s_coef[j] = coef[(size_t)d * k + j];
-      __syncthreads();
+      // cropped sigmoid(proto . coef) on the prototype rows of this band: zero outside the crop window, and the
+      // positions inside it (integer c in [cx1, cx2), r in [cy1, cy2)) enumerated densely so every thread works
+      const int c_lo = max((int)ceilf(cx1), 0), c_hi = min((int)ceilf(cx2), pw);
+      const int q_lo = max((int)ceilf(cy1), r_lo), q_hi = min((int)ceilf(cy2), r_hi + 1);
+      const int cw = c_hi - c_lo;
       for (int pos = tid; pos < nrows * pw; pos += MT) {
         const int r = pos / pw, c = pos - r * pw;
         const int pr = r_lo + r;
-        float v = 0.f;
-        const bool inside = ((float)c >= cx1) && ((float)c < cx2) && ((float)pr >= cy1) && ((float)pr < cy2);
-        if (inside) {
-          const float4* pp = reinterpret_cast<const float4*>(proto + ((size_t)pr * pw + c) * k);
-          float acc = 0.f;
-          for (int j = 0; j < k / 4; ++j) {
-            float4 q = __ldg(pp + j);
-            acc = fmaf(q.x, s_coef[4 * j + 0], acc);
-            acc = fmaf(q.y, s_coef[4 * j + 1], acc);
-            acc = fmaf(q.z, s_coef[4 * j + 2], acc);
-            acc = fmaf(q.w, s_coef[4 * j + 3], acc);
-          }
-          v = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-acc)));  // torch.sigmoid
+        if (!(c >= c_lo && c < c_hi && pr >= q_lo && pr < q_hi)) mrows[pos] = 0.f;
+      }
+      const float* cf = coef + (size_t)d * k;
+      for (int idx = tid; idx < (q_hi - q_lo) * cw; idx += MT) {
+        const int rr = idx / cw;
+        const int c = c_lo + (idx - rr * cw);
+        const int pr = q_lo + rr;
+        const float4* pp = reinterpret_cast<const float4*>(proto + ((size_t)pr * pw + c) * k);
+        float acc = 0.f;
+        for (int j = 0; j < k / 4; ++j) {
+          const float4 q = __ldg(pp + j);
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(cf) + j);   // same address in every lane: one L1 broadcast
+          acc = fmaf(q.x, w4.x, acc);
+          acc = fmaf(q.y, w4.y, acc);
+          acc = fmaf(q.z, w4.z, acc);
+          acc = fmaf(q.w, w4.w, acc);
         }
-        mrows[pos] = v;
+        mrows[(size_t)(pr - r_lo) * pw + c] = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-acc)));  // torch.sigmoid
       }
       __syncthreads();
     }
@@ -191,30 +194,29 @@ mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
       int xb = (int)ceilf(__fdiv_rn(cx2 + 0.5f, scale_w) - 0.5f) + 2;
       xa = max(xa, 0);
       xb = min(xb, out_w);
-      const int xw = xb - xa;
       const size_t band_off = (size_t)d * plane + (size_t)y0 * out_w;
-      for (int idx = tid; idx < (y1 - y0) * xw; idx += MT) {
-        const int yy = idx / xw;
-        const int x = xa + (idx - yy * xw);
-        const ColTab rt = interp_entry(y0 + yy, scale_h, ph);
-        // both source rows outside the crop window -> the whole output row is zero
+      for (int yy = 0; yy < y1 - y0; ++yy) {
+        const ColTab rt = interp_entry(y0 + yy, scale_h, ph);   // uniform
+        // both source rows outside the crop window -> the whole output row stays zero
         if (!(((float)rt.i0 >= cy1 && (float)rt.i0 < cy2) || ((float)rt.i1 >= cy1 && (float)rt.i1 < cy2))) continue;
-        const ColTab ct = coltab[x];
-        if (!(((float)ct.i0 >= cx1 && (float)ct.i0 < cx2) || ((float)ct.i1 >= cx1 && (float)ct.i1 < cx2))) continue;
         const float* ra = mrows + (size_t)(rt.i0 - r_lo) * pw;
         const float* rb = mrows + (size_t)(rt.i1 - r_lo) * pw;
-        float top = __fadd_rn(__fmul_rn(ct.l0, ra[ct.i0]), __fmul_rn(ct.l1, ra[ct.i1]));
-        float bot = __fadd_rn(__fmul_rn(ct.l0, rb[ct.i0]), __fmul_rn(ct.l1, rb[ct.i1]));
-        float v = __fadd_rn(__fmul_rn(rt.l0, top), __fmul_rn(rt.l1, bot));
-        if (v > 0.5f) {
-          if (FORMAT == YB_MASK_F32)
-            reinterpret_cast<float*>(masks_v)[band_off + (size_t)yy * out_w + x] = 1.f;
-          else
-            reinterpret_cast<unsigned char*>(masks_v)[band_off + (size_t)yy * out_w + x] = 1;
+        for (int x = xa + tid; x < xb; x += MT) {
+          const ColTab ct = coltab[x];
+          if (!(((float)ct.i0 >= cx1 && (float)ct.i0 < cx2) || ((float)ct.i1 >= cx1 && (float)ct.i1 < cx2))) continue;
+          float top = __fadd_rn(__fmul_rn(ct.l0, ra[ct.i0]), __fmul_rn(ct.l1, ra[ct.i1]));
+          float bot = __fadd_rn(__fmul_rn(ct.l0, rb[ct.i0]), __fmul_rn(ct.l1, rb[ct.i1]));
+          float v = __fadd_rn(__fmul_rn(rt.l0, top), __fmul_rn(rt.l1, bot));
+          if (v > 0.5f) {
+            if (FORMAT == YB_MASK_F32)
+              reinterpret_cast<float*>(masks_v)[band_off + (size_t)yy * out_w + x] = 1.f;
+            else
+              reinterpret_cast<unsigned char*>(masks_v)[band_off + (size_t)yy * out_w + x] = 1;
+          }
         }
       }
     }
-    if (any) __syncthreads();  // mrows / s_coef reuse
+    if (any) __syncthreads();  // mrows reuse
   }
 }
 
@@ -317,16 +319,18 @@ void launch_mask_assembly(const float* proto, int ph, int pw, int k, const float
     size_t smem;
     for (;;) {
       max_rows = (int)((double)(band - 1) * scale_h) + 4;
-      smem = (size_t)out_w * sizeof(ColTab) + (size_t)max_rows * pw * sizeof(float) + (size_t)k * sizeof(float);
+      smem = (size_t)out_w * sizeof(ColTab) + (size_t)max_rows * pw * sizeof(float);
       if (smem <= 200 * 1024 || band == 1) break;
       band = band / 2;
     }
     YB_REQUIRE(smem <= 200 * 1024, "mask_assembly: output too wide for the shared-memory tables");
     const int bands = ceil_div(out_h, band);
-    // ~12 resident CTAs per SM keep enough stores in flight to approach the HBM write rate; groups stay
-    // >= 8 detections so the band's prototype rows are reused from L1
+    // >= ~4 waves of 8 resident CTAs per SM: enough stores in flight to approach the HBM write rate and a short
+    // tail (bands that cross many boxes take several times longer than empty ones); groups stay >= 8 detections
+    // so the band's prototype rows are reused from L1.  YB_MASK_CTAS_PER_SM overrides the target (tuning hook).
+    static const int ctas_per_sm = getenv("YB_MASK_CTAS_PER_SM") ? std::max(1, atoi(getenv("YB_MASK_CTAS_PER_SM"))) : 32;
     int group = n;
-    while (group > 8 && (int64_t)bands * ceil_div(n, group) * batch < 12 * 148) group = (group + 1) / 2;
+    while (group > 8 && (int64_t)bands * ceil_div(n, group) * batch < (int64_t)ctas_per_sm * 148) group = (group + 1) / 2;
     dim3 grid(bands, ceil_div(n, group), batch);
     const size_t plane = (size_t)out_h * out_w;
     const long long img_stride = (long long)n * (mask_format == YB_MASK_F32 ? plane * 4
