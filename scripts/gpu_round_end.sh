@@ -20,6 +20,12 @@ timeout 300 python bench.py --steps 10 --warmup 3 --config yolact_im700_config -
 tail -1 gpurun_out/bench_im700.log | cut -c1-700 >> $S; tail -2 gpurun_out/bench_im700.err >> $S
 fi
 if [ -z "$NO_NCU" ]; then
+timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/launches_${ROUND:-r01}.csv python scripts/profile_step.py > gpurun_out/ncu_launches.log 2>&1
+echo "launch list exit $?" >> $S
+timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \
+    -k regex:tc_conv -c 12 -s 60 -o gpurun_out/prof_tc_${ROUND:-r01} -f python scripts/profile_step.py --conv-only > gpurun_out/ncu_full.log 2>&1
+echo "full capture exit $?" >> $S
 timeout 400 ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/traffic_${ROUND:-r01}.csv python scripts/profile_step.py > gpurun_out/ncu_traffic.log 2>&1
 echo "traffic exit $?" >> $S
