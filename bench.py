@@ -264,8 +264,15 @@ def main():
     overlap = os.environ.get("BENCH_OVERLAP", "1") != "0"
     masks_f32 = [torch.empty(B, M, size, size, dtype=torch.float32, device=dev) for _ in range(2 if overlap else 1)]
     s_post = torch.cuda.Stream() if overlap else None
+    # The network outputs of step i are read by s_post; they are kept referenced until step i+2, whose first action
+    # is to make the main stream wait for step i's mask assembly -- so the caching allocator (which only tracks the
+    # allocating stream) can never hand their memory to main-stream work that runs before s_post has read it.
+    hold = [None, None]
+    ev_post_v = [torch.cuda.Event(), torch.cuda.Event()]
 
     def step_device(i, fmt="f32", out=None):
+        if overlap and hold[i % 2] is not None:
+            torch.cuda.current_stream().wait_event(ev_post_v[i % 2])
         box, coef, cls, score, count, proto = net.infer_padded(xs[i % n_rot])
         # all M padded rows are assembled (no host sync on the count); with these weights count == M
         if overlap:
@@ -273,9 +280,9 @@ def main():
             ev.record()
             with torch.cuda.stream(s_post):
                 s_post.wait_event(ev)
-                for t_ in (box, coef, proto):
-                    t_.record_stream(s_post)
                 res = assemble_masks_batch(proto, coef, box, size, size, True, fmt, masks_out=out[i % 2])
+                ev_post_v[i % 2].record(s_post)
+            hold[i % 2] = (box, coef, proto, res)
         else:
             res = assemble_masks_batch(proto, coef, box, size, size, True, fmt, masks_out=out[0])
         if world > 1:
@@ -337,6 +344,7 @@ def main():
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_comp = [torch.cuda.Event() for _ in range(2)]
     ev_post = [torch.cuda.Event() for _ in range(2)]
+    hold_e = [None, None]
     ev_d2h = [torch.cuda.Event() for _ in range(2)]
     state = {"n": 0}
 
@@ -350,6 +358,8 @@ def main():
             dx[k].copy_(hx[k], non_blocking=True)
             ev_in[k].record(s_in)
         s_main.wait_event(ev_in[k])
+        if i >= 2 and overlap:
+            s_main.wait_event(ev_post[k])            # step i-2's mask assembly has read its inputs (see `hold`)
         if i >= 2:
             # d_masks[k] / d_boxes[k] were last read by step i-2's D2H
             (s_post if overlap else s_main).wait_event(ev_d2h[k])
@@ -358,10 +368,9 @@ def main():
         if overlap:
             with torch.cuda.stream(s_post):
                 s_post.wait_event(ev_comp[k])
-                for t_ in (box, coef, proto):
-                    t_.record_stream(s_post)
                 assemble_masks_batch(proto, coef, box, size, size, True, "bits", masks_out=d_masks[k], boxes_out=d_boxes[k])
                 ev_post[k].record(s_post)
+            hold_e[k] = (box, coef, proto)
         else:
             assemble_masks_batch(proto, coef, box, size, size, True, "bits", masks_out=d_masks[k], boxes_out=d_boxes[k])
             ev_post[k].record(s_main)
