@@ -84,6 +84,33 @@ def test_no_cpu_fallback():
     assert b"no CUDA device" in lib.yb_last_error()
 
 
+def test_no_cpu_fallback_for_the_row_ops():
+    """FastBaseTransform / mask_iou / jaccard / RLE / display blend: CPU tensors raise, nothing routes to torch ops."""
+    from yolact_b200.augmentations import FastBaseTransform
+    from yolact_b200 import eval_utils as E
+    cfg = CONFIGS["yolact_base_config"].copy()
+    with pytest.raises(_lib.YbError):
+        FastBaseTransform(cfg)(torch.zeros(1, 8, 8, 3))
+    m = torch.zeros(2, 4, 4)
+    for call in (lambda: E.mask_iou(m, m), lambda: E.jaccard(torch.zeros(2, 4), torch.zeros(3, 4)),
+                 lambda: E.encode_masks(m), lambda: E.pack_masks(m),
+                 lambda: E.display_blend(torch.zeros(4, 4, 3), m, [[0, 0, 0]] * 2)):
+        with pytest.raises(_lib.YbError):
+            call()
+    with pytest.raises(NotImplementedError):
+        E.prep_display([], torch.zeros(4, 4, 3), 4, 4, undo_transform=True)
+
+
+def test_detect_nms_mode_follows_the_eval_flags():
+    from yolact_b200.detection import Detect
+    d = Detect(81, 0, 200, 0.05, 0.5)
+    assert d.nms_mode() == _lib.YB_NMS_FAST                      # eval.py defaults
+    d.use_cross_class_nms = True
+    assert d.nms_mode() == _lib.YB_NMS_CROSS_CLASS
+    d.use_fast_nms = False                                       # --fast_nms=False wins (detection.py:100-106)
+    assert d.nms_mode() == _lib.YB_NMS_TRADITIONAL
+
+
 def test_product_never_imports_oracle():
     for root, _, files in os.walk(os.path.join(ROOT, "yolact_b200")):
         for f in files:

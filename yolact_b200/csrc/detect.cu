@@ -30,7 +30,6 @@ constexpr int K1_ROWS = 128;   // priors per CTA in K1
 constexpr int NT2 = 256;       // threads in K2 / K3
 constexpr int SORT_N = 256;    // bitonic sort width (>= top_k)
 constexpr int HIST_BINS = 2048;
-constexpr int SEL_ILP = 8;     // keys in flight per thread in the radix-select passes
 
 // ---------------------------------------------------------------------------------------------
 // K1
@@ -162,22 +161,11 @@ __device__ void block_select_topk(KeyFn key, int n, int K, unsigned long long* s
       for (int i = tid; i < nb; i += NT2) sc->hist[i] = 0u;
       __syncthreads();
       const unsigned long long prefix = sc->prefix;
-      // SEL_ILP keys are fetched before any is consumed: the key functions read global memory, and with one
-      // CTA per image (final_select) nothing else hides that latency
-      for (int i0 = tid; i0 < n; i0 += SEL_ILP * NT2) {
-        unsigned long long kk[SEL_ILP];
-#pragma unroll
-        for (int u = 0; u < SEL_ILP; ++u) {
-          const int i = i0 + u * NT2;
-          kk[u] = (i < n) ? key(i) : 0ull;
-        }
-#pragma unroll
-        for (int u = 0; u < SEL_ILP; ++u) {
-          const unsigned long long k = kk[u];
-          if (k == 0ull) continue;
-          bool match = (pass == 0) || ((k >> (shift + bits)) == prefix);
-          if (match) atomicAdd(&sc->hist[(unsigned)(k >> shift) & (nb - 1)], 1u);
-        }
+      for (int i = tid; i < n; i += NT2) {
+        unsigned long long k = key(i);
+        if (k == 0ull) continue;
+        bool match = (pass == 0) || ((k >> (shift + bits)) == prefix);
+        if (match) atomicAdd(&sc->hist[(unsigned)(k >> shift) & (nb - 1)], 1u);
       }
       __syncthreads();
       // each thread owns `per` consecutive bins, find the bin where the running count from the
@@ -211,22 +199,13 @@ __device__ void block_select_topk(KeyFn key, int n, int K, unsigned long long* s
     final_shift = 64;  // take everything present
   }
   const unsigned long long prefix = sc->prefix;
-  for (int i0 = tid; i0 < n; i0 += SEL_ILP * NT2) {
-    unsigned long long kk[SEL_ILP];
-#pragma unroll
-    for (int u = 0; u < SEL_ILP; ++u) {
-      const int i = i0 + u * NT2;
-      kk[u] = (i < n) ? key(i) : 0ull;
-    }
-#pragma unroll
-    for (int u = 0; u < SEL_ILP; ++u) {
-      const unsigned long long k = kk[u];
-      if (k == 0ull) continue;
-      bool take = (final_shift >= 64) || ((k >> final_shift) >= prefix);
-      if (take) {
-        int pos = atomicAdd(&sc->sel_count, 1);
-        if (pos < SORT_N) sel[pos] = k;
-      }
+  for (int i = tid; i < n; i += NT2) {
+    unsigned long long k = key(i);
+    if (k == 0ull) continue;
+    bool take = (final_shift >= 64) || ((k >> final_shift) >= prefix);
+    if (take) {
+      int pos = atomicAdd(&sc->sel_count, 1);
+      if (pos < SORT_N) sel[pos] = k;
     }
   }
   __syncthreads();
