@@ -35,6 +35,14 @@ GFLOP_PER_IMAGE = {
 }
 
 
+# FPS the reference publishes for each config (Titan Xp, batch 1, fp32, `eval.py --benchmark`,
+# README.md:70-80).  Other hardware and batch size, so it is reported as an informational ratio, not as `vs_baseline`.
+PUBLISHED_TITAN_XP_FPS = {
+    "yolact_resnet50_config": 42.5, "yolact_darknet53_config": 40.0, "yolact_base_config": 33.5,
+    "yolact_im700_config": 23.6, "yolact_plus_resnet50_config": 33.5, "yolact_plus_base_config": 27.3,
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -451,6 +459,10 @@ def main():
                 "ms_per_step": ms_e2e / args.steps, "host_wall_ms_per_step": wall_e2e / args.steps,
                 "pipelining": "double-buffered streams: H2D(i+1) | network(i+1) | mask assembly(i) | D2H(i-1); host blocks on each step's D2H"},
         "gpu_launches": int(launches),
+        "vs_published_titan_xp": {"ratio_per_gpu": fps / world / PUBLISHED_TITAN_XP_FPS[args.config],
+                                  "published_fps": PUBLISHED_TITAN_XP_FPS[args.config],
+                                  "note": "reference README (BASELINE.md section 1): 1 Titan Xp, batch 1, fp32"}
+        if args.config in PUBLISHED_TITAN_XP_FPS and size == cfg.max_size else None,
         "clocks": clocks,
         "roofline": roofline,
     })
