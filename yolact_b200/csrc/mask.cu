@@ -165,6 +165,10 @@ mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
       if (!any) {
         for (int wi = tid; wi < words; wi += MT) out[(size_t)y0 * wpr + wi] = 0u;   // the band's words are contiguous
       } else {
+        // output columns whose interpolation sources can fall inside the crop window (conservative superset,
+        // same bounds as the fp32 / uint8 path below): words entirely outside are zero without evaluation
+        const int xa = max((int)floorf(__fdiv_rn(cx1 - 0.5f, scale_w) - 0.5f) - 1, 0);
+        const int xb = min((int)ceilf(__fdiv_rn(cx2 + 0.5f, scale_w) - 0.5f) + 2, out_w);
         const int wrp = tid >> 5, lane = tid & 31;
         for (int wi = wrp; wi < words; wi += MT / 32) {
           const int yy = wi / wpr, wx = wi - yy * wpr;
@@ -173,8 +177,12 @@ mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
           const ColTab rt = interp_entry(y, scale_h, ph);
           // both source rows outside the crop window -> the whole output row is zero
           const bool row_live = ((float)rt.i0 >= cy1 && (float)rt.i0 < cy2) || ((float)rt.i1 >= cy1 && (float)rt.i1 < cy2);
+          if (!row_live || wx * 32 + 32 <= xa || wx * 32 >= xb) {   // warp-uniform
+            if (lane == 0) out[(size_t)y * wpr + wx] = 0u;
+            continue;
+          }
           bool bit = false;
-          if (row_live && x < out_w) {
+          if (x < out_w) {
             const float* ra = mrows + (size_t)(rt.i0 - r_lo) * pw;
             const float* rb = mrows + (size_t)(rt.i1 - r_lo) * pw;
             const ColTab ct = coltab[x];
