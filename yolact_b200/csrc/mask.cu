@@ -168,7 +168,7 @@ mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
         // output columns whose interpolation sources can fall inside the crop window (conservative superset,
         // same bounds as the fp32 / uint8 path below): words entirely outside are zero without evaluation
         const int xa = max((int)floorf(__fdiv_rn(cx1 - 0.5f, scale_w) - 0.5f) - 1, 0);
-        const int xb = min((int)ceilf(__fdiv_rn(cx2 + 0.5f, scale_w) - 0.5f) + 2, out_w);
+        const int xb = min((int)ceilf(__fdiv_rn(ceilf(cx2) + 0.5f, scale_w) - 0.5f) + 1, out_w);
         const int wrp = tid >> 5, lane = tid & 31;
         for (int wi = wrp; wi < words; wi += MT / 32) {
           const int yy = wi / wpr, wx = wi - yy * wpr;
@@ -198,8 +198,11 @@ mask_assembly_kernel(const float* __restrict__ proto, int ph, int pw, int k,
     } else if (any) {
       // ---- phase B: only the output columns whose interpolation sources can fall inside the crop window
       //      (a conservative superset: pixels outside interpolate zeros), only the ones are stored.
+      // A pixel x reads source columns i0 = floor(s), i1 = i0 + 1 with s = scale*(x+0.5)-0.5; the columns inside the
+      // window are the integers in [ceil(cx1), ceil(cx2)).  i1 >= ceil(cx1) needs s >= ceil(cx1) - 1 (cx1 - 0.5 below is
+      // smaller still), i0 < ceil(cx2) needs s < ceil(cx2): x < (ceil(cx2) + 0.5) / scale - 0.5.
       int xa = (int)floorf(__fdiv_rn(cx1 - 0.5f, scale_w) - 0.5f) - 1;
-      int xb = (int)ceilf(__fdiv_rn(cx2 + 0.5f, scale_w) - 0.5f) + 2;
+      int xb = (int)ceilf(__fdiv_rn(ceilf(cx2) + 0.5f, scale_w) - 0.5f) + 1;
       xa = max(xa, 0);
       xb = min(xb, out_w);
       const size_t band_off = (size_t)d * plane + (size_t)y0 * out_w;
