@@ -35,3 +35,19 @@ def test_masks_at_extreme_resize_ratios(size):
         assert (got != masks_ref).mean() < 1e-4, (fmt, size)
         # nothing may be set outside the (padded) crop window's pixel footprint
         assert got.sum() > 0
+
+
+def test_rle_wider_than_one_pass():
+    """w > 1024: the RLE kernel walks the columns in several passes of 1024 threads, carrying the run offset and the
+    previous column's last pixel across passes."""
+    from oracle import eval_oracle as E
+    from yolact_b200.eval_utils import mask_run_lengths
+    r = np.random.RandomState(5)
+    for (h, w) in [(40, 1300), (7, 2500), (33, 1024), (33, 1025)]:
+        ms = [(r.rand(h, w) < p).astype(np.uint8) for p in (0.0, 0.01, 0.5, 1.0)]
+        blob = np.zeros((h, w), np.uint8)
+        blob[h // 4:h // 2 + 1, 1000:1100] = 1          # straddles the pass boundary at column 1024
+        ms.append(blob)
+        runs = mask_run_lengths(torch.from_numpy(np.stack(ms)).cuda())
+        for i, m in enumerate(ms):
+            assert runs[i].tolist() == E.rle_counts(m), (h, w, i)
