@@ -80,6 +80,20 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute applies to the CURRENT device: a function-local static of this type remembers, per device,
+// whether the attribute of that kernel instantiation has been raised (one process may drive several GPUs).
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 // Launch counter (per handle); every launcher takes one of these.
 struct LaunchCounter {
   int64_t n = 0;

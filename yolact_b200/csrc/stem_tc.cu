@@ -171,12 +171,10 @@ void launch_variant(const StemParams& prm, cudaStream_t stream) {
   constexpr int K = 3 * KS * KS;
   constexpr int ATOMS = (K + 63) / 64;
   const size_t smem = (size_t)ATOMS * (ST_M * 128 + COUT * 128) + 1024;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first())
     YB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<KS, STRIDE, PAD, COUT, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-    attr = true;
-  }
   const unsigned grid = (unsigned)((prm.M + ST_M - 1) / ST_M);
   stem_tc_kernel<KS, STRIDE, PAD, COUT, WG><<<grid, 128 * WG + 32, smem, stream>>>(prm);
 }

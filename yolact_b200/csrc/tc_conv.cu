@@ -794,12 +794,10 @@ int tc_conv_plan_epi_groups(const TcConvPlan* plan) { return plan->epi_groups; }
 
 template <int BN, bool PAIR, int H>
 static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr;
+  if (attr.first())
     YB_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, PAIR, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(220 * 1024)));
-    attr_set = true;
-  }
   constexpr int THREADS = 64 + 128 * H;
   if (plan->prm.pdl || PAIR) {
     cudaLaunchConfig_t cfg = {};
