@@ -111,6 +111,24 @@ def test_detect_nms_mode_follows_the_eval_flags():
     assert d.nms_mode() == _lib.YB_NMS_TRADITIONAL
 
 
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary must be usable without C++ or torch: compile examples/c_abi_demo.c as C99 against the header,
+    link it with the shared library only, run it."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.join(ROOT, "yolact_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "c_abi_demo.c"), "-o", exe, os.path.join(libdir, "libyolact_b200.so"),
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "yolact_b200 ABI 1" in out
+    if not torch.cuda.is_available():
+        assert "no CPU fallback" in out
+
+
 def test_product_never_imports_oracle():
     for root, _, files in os.walk(os.path.join(ROOT, "yolact_b200")):
         for f in files:
