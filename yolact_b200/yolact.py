@@ -215,8 +215,9 @@ class Yolact(nn.Module):
         self.semantic_seg_conv = nn.Conv2d(f, c.num_classes - 1, 1)  # training-only, kept for key parity
         self.detect = Detect(c.num_classes, bkg_label=0, top_k=c.nms_top_k, conf_thresh=c.nms_conf_thresh,
                              nms_thresh=c.nms_thresh, cfg=c)
-        self._handles = {}
-        self._dirty = True
+        self._handles = {}      # device index -> yb_handle
+        self._version = 1       # bumped whenever the parameters may have changed
+        self._pushed = {}       # device index -> version of the weights that handle holds
 
     # ---- weights ---------------------------------------------------------------------------------
     def save_weights(self, path):
@@ -235,17 +236,17 @@ class Yolact(nn.Module):
 
     def load_state_dict(self, state_dict, strict=True):
         r = super().load_state_dict(state_dict, strict=strict)
-        self._dirty = True
+        self._version += 1
         return r
 
     def _apply(self, fn, *a, **k):
         r = super()._apply(fn, *a, **k)
-        self._dirty = True
+        self._version += 1
         return r
 
     def mark_weights_dirty(self):
-        """Call after modifying parameters in place; the next forward re-uploads them."""
-        self._dirty = True
+        """Call after modifying parameters in place; the next forward on each device re-uploads them."""
+        self._version += 1
 
     def train(self, mode=True):
         super().train(mode)
@@ -261,10 +262,10 @@ class Yolact(nn.Module):
             yc = make_yb_config(self.cfg, self.precision)
             _lib.check(lib.yb_create(ctypes.byref(yc), idx, ctypes.byref(h)), "yb_create")
             self._handles[idx] = h
-            self._dirty = True
         h = self._handles[idx]
-        if self._dirty:
+        if self._pushed.get(idx) != self._version:     # per device: every handle re-syncs on its next call
             self._push_weights(h)
+            self._pushed[idx] = self._version
         return h
 
     def _push_weights(self, h):
@@ -276,11 +277,7 @@ class Yolact(nn.Module):
             shape = (ctypes.c_int64 * max(1, t.dim()))(*t.shape)
             _lib.check(lib.yb_load_weight(h, name.encode(), ctypes.c_void_p(t.data_ptr()), shape, t.dim()),
                        "yb_load_weight(%s)" % name)
-        for hh in self._handles.values():
-            if hh is not h:
-                pass  # other devices re-sync lazily on their next call
         _lib.check(lib.yb_finalize_weights(h), "yb_finalize_weights")
-        self._dirty = False
 
     def __del__(self):
         try:
