@@ -126,6 +126,11 @@ TC_MODES = {
     "epi2_grid3_bn256": {"YB_CONV2D_EPI": "2", "YB_CONV2D_GRID": "3", "YB_CONV2D_BN": "256"},
     "pair_epi2": {"YB_CONV2D_PAIR": "1", "YB_CONV2D_EPI": "2"},
 }
+if os.environ.get("YB_TEST_EXPERIMENTAL"):
+    # not validated on hardware yet (written after the round-1 GPU budget was spent): PDL-friendly plans with the
+    # weight tiles requested before griddepcontrol.wait; yb_conv2d(iters > 1) launches the kernel back to back
+    TC_MODES["pdl_friendly"] = {"YB_CONV2D_PDL": "1"}
+    TC_MODES["pdl_friendly_bn64_grid3"] = {"YB_CONV2D_PDL": "1", "YB_CONV2D_BN": "64", "YB_CONV2D_GRID": "3"}
 if os.environ.get("YB_TEST_NO_PAIR"):   # escape hatch while the pair kernel is being brought up
     TC_MODES = {k: v for k, v in TC_MODES.items() if not k.startswith("pair")}
 

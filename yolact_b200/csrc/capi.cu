@@ -590,7 +590,10 @@ int yb_conv2d(yb_handle* h, const float* d_x, const float* h_w, const float* h_b
       const char* ge = getenv("YB_CONV2D_GRID");
       const char* pe = getenv("YB_CONV2D_PAIR");
       const char* ee = getenv("YB_CONV2D_EPI");
-      plan = tc_conv_plan_create(p, wd, be ? atoi(be) : 0, 0, ge ? atoi(ge) : 0, pe ? atoi(pe) : 0, ee ? atoi(ee) : 0);
+      const char* de = getenv("YB_CONV2D_PDL");   // experimental: PDL-friendly plan + programmatic dependent launch
+      plan = tc_conv_plan_create(p, wd, be ? atoi(be) : 0, 0, ge ? atoi(ge) : 0, pe ? atoi(pe) : 0, ee ? atoi(ee) : 0,
+                                 de ? atoi(de) : 0);
+      if (de && atoi(de)) tc_conv_plan_set_pdl(plan, 1);
     }
     run = [&]() { launch_tc_conv(plan, s, &h->lc); };
   } else if (precision == 2) {

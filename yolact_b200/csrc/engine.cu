@@ -251,7 +251,8 @@ struct NetBuilder {
       TcConvPlan* plan = autotune_tc(p, w.w_tc);
       ex->plans.push_back(plan);
       op.name += " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) + " st=" + std::to_string(tc_conv_plan_stages(plan)) +
-                 " g=" + std::to_string(tc_conv_plan_grid(plan)) + (tc_conv_plan_pair(plan) ? " pair" : "") + (tc_conv_plan_epi_groups(plan) == 2 ? " epi2" : "");
+                 " g=" + std::to_string(tc_conv_plan_grid(plan)) + (tc_conv_plan_pair(plan) ? " pair" : "") + (tc_conv_plan_epi_groups(plan) == 2 ? " epi2" : "") +
+              (tc_conv_plan_pdl_friendly(plan) ? " pdlf" : "");
       tc_conv_plan_set_pdl(plan, h->pdl ? 1 : 0);
       op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
     } else {
@@ -416,7 +417,8 @@ struct NetBuilder {
     op.name = hn + ".bbox+conf+mask " + std::to_string(in.C) + "->" + std::to_string(w.Cout) + " k3s1 " +
               std::to_string(in.H) + "x" + std::to_string(in.W) + " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) +
               " st=" + std::to_string(tc_conv_plan_stages(plan)) + " g=" + std::to_string(tc_conv_plan_grid(plan)) +
-              (tc_conv_plan_pair(plan) ? " pair" : "") + (tc_conv_plan_epi_groups(plan) == 2 ? " epi2" : "");
+              (tc_conv_plan_pair(plan) ? " pair" : "") + (tc_conv_plan_epi_groups(plan) == 2 ? " epi2" : "") +
+              (tc_conv_plan_pdl_friendly(plan) ? " pdlf" : "");
     op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
     push(op);
   }
@@ -433,7 +435,8 @@ struct NetBuilder {
                              (p.y_f32 ? "f" : "h") + std::to_string(p.nseg) + "," + std::to_string(p.y_pix_stride) + "," + std::to_string((long long)p.y_batch_stride);
     auto it = h->tune_cache.find(tkey);
     if (it != h->tune_cache.end())
-      return tc_conv_plan_create(p, w, it->second[0], it->second[1], it->second[2], it->second[3], it->second[4]);
+      return tc_conv_plan_create(p, w, it->second[0], it->second[1], it->second[2], it->second[3], it->second[4],
+                                 it->second[5]);
     const int bns[4] = {256, 128, 64, 32};
     const int sts[3] = {0, 3, 2};
     const int grids[3] = {148, 296, 1 << 30};
@@ -446,6 +449,17 @@ struct NetBuilder {
     // extra candidates: CTA pairs (cta_group::2, persistent grid only) and two epilogue groups per CTA
     const int npair = h->pair_candidates ? 2 : 1;
     const int nepi = h->epi2_candidates ? 2 : 1;
+    // YB_PDL=1 (experimental): every single-CTA candidate is timed with programmatic dependent launch on a private
+    // stream (consecutive launches of one kernel overlap like consecutive layers do), plus "PDL-friendly" plans that
+    // leave room on the SM for the next layer's CTA
+    const int npdl = h->pdl ? 2 : 1;
+    cudaStream_t ts = 0;
+    if (h->pdl) {
+      if (!h->tune_stream) YB_CHECK_CUDA(cudaStreamCreateWithFlags(&h->tune_stream, cudaStreamNonBlocking));
+      ts = h->tune_stream;
+      YB_CHECK_CUDA(cudaDeviceSynchronize());
+    }
+    for (int di = 0; di < npdl; ++di)
     for (int ei = 0; ei < nepi; ++ei)
     for (int pi = 0; pi < npair; ++pi)
     for (int bi = 0; bi < 4; ++bi)
@@ -454,24 +468,27 @@ struct NetBuilder {
           if (bns[bi] > 64 && bns[bi] >= 2 * p.Cout) continue;
           if (pi && bns[bi] < 64) continue;
           if (ei && (bns[bi] < 64 || gi == 1)) continue;   // 320-thread CTAs: one per SM
-          TcConvPlan* cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi], pi, ei ? 2 : 1);
-          if ((pi && !tc_conv_plan_pair(cand)) || (ei && tc_conv_plan_epi_groups(cand) != 2)) {
+          if (di && (pi || ei || gi == 1)) continue;        // PDL-friendly: single CTAs, one epilogue group, <= 1 CTA/SM of its own
+          TcConvPlan* cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi], pi, ei ? 2 : 1, di);
+          if ((pi && !tc_conv_plan_pair(cand)) || (ei && tc_conv_plan_epi_groups(cand) != 2) ||
+              (di && !tc_conv_plan_pdl_friendly(cand))) {
             tc_conv_plan_destroy(cand);
             continue;
           }
+          if (h->pdl) tc_conv_plan_set_pdl(cand, 1);
           const std::string ck = std::to_string(tc_conv_plan_bn(cand)) + "/" + std::to_string(tc_conv_plan_stages(cand)) +
                                  "/" + std::to_string(tc_conv_plan_grid(cand)) + "/" + std::to_string(tc_conv_plan_pair(cand)) + "/" +
-                                 std::to_string(tc_conv_plan_epi_groups(cand));
+                                 std::to_string(tc_conv_plan_epi_groups(cand)) + "/" + std::to_string(tc_conv_plan_pdl_friendly(cand));
           if (!seen.insert(ck).second) {  // overrides were clamped to an already-timed configuration
             tc_conv_plan_destroy(cand);
             continue;
           }
           float ms = 1e30f;
           try {
-            for (int i = 0; i < 3; ++i) launch_tc_conv(cand, 0, nullptr);
-            YB_CHECK_CUDA(cudaEventRecord(e0, 0));
-            for (int i = 0; i < 10; ++i) launch_tc_conv(cand, 0, nullptr);
-            YB_CHECK_CUDA(cudaEventRecord(e1, 0));
+            for (int i = 0; i < 3; ++i) launch_tc_conv(cand, ts, nullptr);
+            YB_CHECK_CUDA(cudaEventRecord(e0, ts));
+            for (int i = 0; i < 10; ++i) launch_tc_conv(cand, ts, nullptr);
+            YB_CHECK_CUDA(cudaEventRecord(e1, ts));
             YB_CHECK_CUDA(cudaEventSynchronize(e1));
             YB_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
           } catch (...) {
@@ -493,7 +510,7 @@ struct NetBuilder {
     cudaEventDestroy(e1);
     YB_REQUIRE(best != nullptr, "autotune: no candidate");
     h->tune_cache[tkey] = {tc_conv_plan_bn(best), tc_conv_plan_stages(best), tc_conv_plan_grid(best), tc_conv_plan_pair(best),
-                           tc_conv_plan_epi_groups(best)};
+                           tc_conv_plan_epi_groups(best), tc_conv_plan_pdl_friendly(best)};
     return best;
   }
 };
@@ -651,6 +668,7 @@ yb_handle::~yb_handle() {
   if (detect_ws) cudaFree(detect_ws);
   if (scratch) cudaFree(scratch);
   if (cap_stream) cudaStreamDestroy(cap_stream);
+  if (tune_stream) cudaStreamDestroy(tune_stream);
   for (auto s : lane_streams)
     if (s) cudaStreamDestroy(s);
   if (ev_fork) cudaEventDestroy(ev_fork);

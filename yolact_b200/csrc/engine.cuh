@@ -104,7 +104,8 @@ struct yb_handle {
   std::map<std::string, yb::ConvW> convs;
   std::map<std::string, std::unique_ptr<yb::Executor>> execs;
   std::vector<void*> weight_allocs;
-  std::map<std::string, std::array<int, 5>> tune_cache;  // layer shape -> (BN, stages, grid, pair, epilogue groups) from the autotuner
+  std::map<std::string, std::array<int, 6>> tune_cache;  // layer shape -> (BN, stages, grid, pair, epilogue groups, pdl-friendly) from the autotuner
+  cudaStream_t tune_stream = nullptr;   // private stream of the autotuner when PDL candidates are timed
   yb::Executor* last_exec = nullptr;
   // standalone op workspaces
   void* detect_ws = nullptr;

@@ -51,7 +51,9 @@ struct TcConvPlan;  // opaque: tensor maps + tiling; built once per (layer, shap
 // pair_override > 0: CTA pairs (cluster of 2, tcgen05 cta_group::2, UMMA M = 256; each CTA stages half the weight tile).
 TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override = 0,
                                 int stages_override = 0, int grid_override = 0, int pair_override = 0,
-                                int epi_override = 0);   // epi_override == 2: two 4-warp epilogue groups (320 threads)
+                                int epi_override = 0,    // epi_override == 2: two 4-warp epilogue groups (320 threads)
+                                int pdl_override = 0);   // > 0: plan sized for 2 CTAs/SM + programmatic dependent launch
+int tc_conv_plan_pdl_friendly(const TcConvPlan* plan);
 int tc_conv_plan_pair(const TcConvPlan* plan);
 int tc_conv_plan_epi_groups(const TcConvPlan* plan);
 int tc_conv_plan_grid(const TcConvPlan* plan);

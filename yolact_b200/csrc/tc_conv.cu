@@ -242,11 +242,25 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
-  // Programmatic dependent launch: everything above overlaps the tail of the previous kernel in the
-  // stream; its output is only touched below this point.
+  // Programmatic dependent launch: everything above overlaps the tail of the previous kernel in the stream, and so do
+  // the WEIGHT tiles of this CTA's first k-blocks (constants: they do not depend on the previous layer); the
+  // activations are only touched after griddepcontrol.wait.  Dependents are released at once: they can become resident
+  // (and do the same) as soon as an SM has room -- which needs a plan that leaves room (plan->pdl_friendly).
+  uint32_t pre = 0;   // producer thread only: k-blocks whose weight tile is already in flight
   if (p.pdl) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!PAIR && warp == 0 && lane == 0 && unit0 < num_units) {
+      const TileCoord t0 = decode_unit<PAIR>(p, unit0, rank, BN);
+      const int npre = min(stages, num_kb);
+      for (int kb = 0; kb < npre; ++kb) {
+        const int tap = kb / p.kchunks;
+        const int kc = kb - tap * p.kchunks;
+        mbar_expect_tx(&full_bar[kb], (uint32_t)p.a_box_bytes + (uint32_t)B_STAGE_BYTES);
+        tma_load_3d(smem + (size_t)kb * STAGE_BYTES + A_STAGE_BYTES, &p.tmB, &full_bar[kb], kc * BLOCK_K, t0.n0, tap);
+      }
+      pre = (uint32_t)npre;
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
   }
 
   if (warp == 0) {
@@ -272,6 +286,10 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             tma_load_4d_pair(sa, &p.tmA[p.tap_map[tap]], fb, kc * BLOCK_K, tc_.x0 + p.tap_dx[tap],
                              tc_.y0 + p.tap_dy[tap], tc_.b);
             tma_load_3d_pair(sb, &p.tmB, fb, kc * BLOCK_K, tc_.n0 + rank * (BN / 2), tap);
+          } else if (kbg < pre) {
+            // PDL: this stage was armed and its weight tile requested before the dependency wait
+            tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[s], kc * BLOCK_K, tc_.x0 + p.tap_dx[tap],
+                        tc_.y0 + p.tap_dy[tap], tc_.b);
           } else {
             mbar_expect_tx(&full_bar[s], tx_bytes);
             tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[s], kc * BLOCK_K, tc_.x0 + p.tap_dx[tap],
@@ -562,6 +580,7 @@ struct TcConvPlan {
   int BN = 128;
   int pair = 0;
   int epi_groups = 1;   // H: 4-warp epilogue groups per CTA
+  int pdl_friendly = 0; // sized so that two CTAs (this kernel's and the next layer's) fit on one SM
   dim3 grid;
   size_t smem_bytes = 0;
 };
@@ -576,7 +595,7 @@ bool tc_conv_supported(const ConvProblem& p) {
 }
 
 TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override, int stages_override,
-                                int grid_override, int pair_override, int epi_override) {
+                                int grid_override, int pair_override, int epi_override, int pdl_override) {
   YB_REQUIRE(tc_conv_supported(p), "tc_conv: unsupported problem");
   YB_REQUIRE(p.Ho == (p.H + 2 * p.pad - p.KH) / p.stride + 1, "tc_conv: bad Ho");
   YB_REQUIRE(p.Wo == (p.W + 2 * p.pad - p.KW) / p.stride + 1, "tc_conv: bad Wo");
@@ -675,18 +694,30 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   q.tmem_cols = tmem_cols;
   const int tiles_per_cta = ceil_div(num_tiles, grid);
   // two epilogue groups (8 warps) work on two 64-channel chunks at once; pointless for a single-chunk tile
-  plan->epi_groups = (epi_override == 2 && BN >= 64) ? 2 : 1;
+  // PDL-friendly plan: <= ~108 KB of shared memory, one epilogue group (192 threads x 122 registers) and <= 256 TMEM
+  // columns, so a CTA of the NEXT layer can become resident beside it and overlap its prologue + first weight tiles
+  const int pdlf = (pdl_override > 0 && !pair) ? 1 : 0;
+  plan->pdl_friendly = pdlf;
+  if (pdlf && q.acc_stages * BN > 256) q.acc_stages = 1;
+  if (pdlf) {
+    int tc = 32;
+    while (tc < q.acc_stages * BN) tc *= 2;
+    q.tmem_cols = tc;
+  }
+  plan->epi_groups = (epi_override == 2 && BN >= 64 && !pdlf) ? 2 : 1;
   // staging: 2 x 16 KB tiles (one per group when there are two); the direct (fp32) epilogue needs a padded
   // 32x33 float transpose buffer per epilogue warp
   const int out_bytes = plan->epi_groups == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES;
   const int res_bytes = (q.epi_tma && p.residual) ? 2 * A_STAGE_BYTES : 0;
-  int stages = std::min(MAX_STAGES, (200 * 1024 - out_bytes - res_bytes) / stage_bytes);
+  int stages = std::min(MAX_STAGES, ((pdlf ? 108 : 200) * 1024 - out_bytes - res_bytes) / stage_bytes);
   if (stages_override > 0) stages = std::min(stages, stages_override);
   stages = std::max(1, std::min(stages, q.ntaps * q.kchunks * tiles_per_cta));
   q.stages = stages;
   q.out_off = stages * stage_bytes;
   q.res_off = q.out_off + out_bytes;
   plan->smem_bytes = (size_t)q.res_off + res_bytes + 1024;
+  if (pdlf && plan->smem_bytes > (size_t)112 * 1024) plan->pdl_friendly = 0;   // does not fit twice: plain plan
+  q.pdl = plan->pdl_friendly;
   if (pair) plan->smem_bytes = std::max(plan->smem_bytes, (size_t)120 * 1024);   // at most one pair CTA per SM
   plan->grid = dim3((unsigned)(pair ? 2 * grid : grid), 1, 1);
 
@@ -791,6 +822,7 @@ int tc_conv_plan_stages(const TcConvPlan* plan) { return plan->prm.stages; }
 int tc_conv_plan_grid(const TcConvPlan* plan) { return (int)plan->grid.x; }
 int tc_conv_plan_pair(const TcConvPlan* plan) { return plan->pair; }
 int tc_conv_plan_epi_groups(const TcConvPlan* plan) { return plan->epi_groups; }
+int tc_conv_plan_pdl_friendly(const TcConvPlan* plan) { return plan->pdl_friendly; }
 
 template <int BN, bool PAIR, int H>
 static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
