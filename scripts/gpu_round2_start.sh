@@ -30,6 +30,21 @@ PY
   done
   YB_PDL=1 timeout 300 python scripts/layer_profile.py > gpurun_out/layers_pdl.md 2> gpurun_out/layers_pdl.err; echo "layers pdl exit $?; pdlf layers: $(grep -c pdlf gpurun_out/layers_pdl.md)" >> $S
 fi
+# experimental: warp-cooperative DCN gather (YB_DCN_GATHER=warp)
+YB_DCN_GATHER=warp timeout 300 python -m pytest tests/test_gpu_dcn.py tests/test_gpu_network.py -m gpu -q -k "dcn or plus" -p no:cacheprovider > gpurun_out/r2_dcn_warp_tests.log 2>&1
+rc=$?; echo "dcn warp-gather tests exit $rc" >> $S; tail -1 gpurun_out/r2_dcn_warp_tests.log >> $S
+for tag in "YB_DCN_GATHER=thread" "YB_DCN_GATHER=warp"; do
+  env $tag timeout 300 python bench.py --steps 10 --warmup 3 --config yolact_plus_base_config --no-cpu-baseline > gpurun_out/r2_plus_$tag.log 2> gpurun_out/r2_plus_$tag.err
+  echo "bench plus_base [$tag] exit $?" >> $S
+  python - "gpurun_out/r2_plus_$tag.log" >> $S <<'PY'
+import json, sys
+try:
+    j = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print("  value %.0f FPS (%.3f ms)  conv %.3f ms" % (j["value"], j["ms_per_step"], j["roofline"]["ms_conv_stack_per_step"]))
+except Exception as e:
+    print("  parse error", e)
+PY
+done
 cap() {  # cap <tag> <kernel regex> <command...>
   tag=$1; re=$2; shift 2
   timeout 240 ncu --set full --clock-control none --import-source on -k regex:"$re" -c 1 -o gpurun_out/prof_${tag}_r02 -f "$@" > gpurun_out/ncu_$tag.log 2>&1
