@@ -103,3 +103,42 @@ def test_package_rle_string_matches_oracle():
         assert rle_to_string(np.array(c, np.uint32)) == E.rle_to_string(c)
     big = [0, 1 << 20, 3, (1 << 31) - 7, 1, 2]
     assert rle_to_string(np.array(big, np.uint32)) == E.rle_to_string(big)
+
+
+def _rle_encode_loop(mask):
+    """maskApi.c rleEncode, literally: walk the column-major pixels, emit a count at every value change."""
+    flat = np.asarray(mask).T.reshape(-1)
+    cnts, c, p = [], 0, 0
+    for v in flat:
+        v = int(v)
+        if v != p:
+            cnts.append(c)
+            c = 0
+            p = v
+        c += 1
+    cnts.append(c)
+    return cnts
+
+
+def test_vectorised_rle_counts_equal_the_literal_loop():
+    r = np.random.RandomState(3)
+    for (h, w) in [(1, 1), (1, 7), (6, 1), (5, 4), (13, 17)]:
+        for p in (0.0, 0.2, 0.5, 0.9, 1.0):
+            m = (r.rand(h, w) < p).astype(np.uint8)
+            assert E.rle_counts(m) == _rle_encode_loop(m), (h, w, p)
+
+
+def test_rle_string_round_trip_property():
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(min_value=0, max_value=(1 << 31) - 1), min_size=1, max_size=64))
+    def check(counts):
+        from yolact_b200.eval_utils import rle_to_string
+        s = E.rle_to_string(counts)
+        assert all(48 <= ch < 48 + 64 for ch in s)               # printable: '0' .. 'o'
+        assert E.rle_from_string(s) == counts
+        assert rle_to_string(np.array(counts, np.int64)) == s    # the package's vectorised encoder agrees
+
+    check()
