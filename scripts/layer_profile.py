@@ -6,14 +6,15 @@ from oracle.weights import deterministic_state_dict, deterministic_input
 from yolact_b200.config import CONFIGS
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="yolact_base_config"); ap.add_argument("--batch", type=int, default=8)
+ap.add_argument("--precision", default="f16x3")
 a = ap.parse_args()
 cfg = CONFIGS[a.config].copy(); yolact_b200.cfg.replace(cfg.copy())
-net = yolact_b200.Yolact(cfg); net.load_state_dict(deterministic_state_dict(net.state_dict(), 0)); net.eval()
+net = yolact_b200.Yolact(cfg, precision=a.precision); net.load_state_dict(deterministic_state_dict(net.state_dict(), 0)); net.eval()
 x = deterministic_input(a.batch, cfg.max_size, cfg.max_size, 1).cuda()
 net.profile_conv_stack(x)
 prof = net.profile_conv_stack(x)
 tot = sum(ms for _, ms in prof)
-print("# per-layer conv-stack times, %s batch %d (eager, CUDA events, warm L2): total %.3f ms\n" % (cfg.name, a.batch, tot))
+print("# per-layer conv-stack times, %s batch %d, precision %s (eager, CUDA events, warm L2): total %.3f ms\n" % (cfg.name, a.batch, a.precision, tot))
 print("| layer | ms | GFLOP | TFLOP/s |\n|---|---:|---:|---:|")
 import re
 for name, ms in prof:

@@ -155,6 +155,48 @@ def test_tcgen05_matches_simt_f16_and_torch(ops, case, mode, monkeypatch):
     assert (y_tc - y_simt).abs().max() < 3e-3 * scale, "tcgen05 vs SIMT fp16"
 
 
+# ---- split precision (YB_PREC_F16X3): fp16 hi+lo operand pairs, three MMA passes -> fp32-equivalent results -----
+SPLIT_MODES = {
+    "default": {},
+    "persistent_grid3": {"YB_CONV2D_GRID": "3"},
+    "persistent_grid5_bn64": {"YB_CONV2D_GRID": "5", "YB_CONV2D_BN": "64"},
+    "pair": {"YB_CONV2D_PAIR": "1"},
+    "pair_grid4_bn128": {"YB_CONV2D_PAIR": "1", "YB_CONV2D_GRID": "4", "YB_CONV2D_BN": "128"},
+    "pair_bn256": {"YB_CONV2D_PAIR": "1", "YB_CONV2D_BN": "256"},
+    "epi2": {"YB_CONV2D_EPI": "2"},
+    "pair_epi2": {"YB_CONV2D_PAIR": "1", "YB_CONV2D_EPI": "2"},
+}
+
+
+@pytest.mark.parametrize("mode", sorted(SPLIT_MODES))
+@pytest.mark.parametrize("case", TC_CASES)
+def test_tcgen05_split_matches_torch_fp32(ops, case, mode, monkeypatch):
+    """The reference arithmetic is fp32 (yolact.py:564-676 under eval.py:1077-1081): the split mode is compared with
+    torch fp32 on the UNROUNDED operands.  Tolerance 2e-5 of the output range: ~30x the fp32 summation-order noise
+    of a K = 2304 dot product, 100x below the single-pass fp16 mode's error."""
+    for k_, v_ in SPLIT_MODES[mode].items():
+        monkeypatch.setenv(k_, v_)
+    B, Ci, H, W, Co, k, s, p, act, wr = case
+    x, w, bias, res = make(B, Ci, H, W, Co, k, s, p, True, wr, seed=2)
+    y, _ = run_conv(ops, x, w, bias, res, s, p, act, 3)
+    ref = ref_conv(x, w, bias, res, s, p, act)
+    scale = max(1.0, ref.abs().max().item())
+    assert torch.isfinite(y).all()
+    err = (y - ref).abs().max().item()
+    assert err < 2e-5 * scale, "split tcgen05 vs torch fp32: %.3e of range" % (err / scale)
+
+
+def test_tcgen05_split_small_and_large_magnitudes(ops):
+    """hi + lo must hold across magnitudes: tiny weights (lo would be subnormal without the power-of-two pre-scale)
+    and activations up to a few thousand."""
+    x, w, bias, _ = make(1, 128, 20, 20, 64, 3, 1, 1)
+    for xs, ws in ((1.0, 1e-3), (3e3, 1.0), (1e-2, 1e-2), (30.0, 20.0)):
+        y, _ = run_conv(ops, x * xs, w * ws, bias, None, 1, 1, 0, 3)
+        ref = ref_conv(x * xs, w * ws, bias, None, 1, 1, 0)
+        err = (y - ref).abs().max().item() / max(1e-30, ref.abs().max().item())
+        assert err < 2e-5, (xs, ws, err)
+
+
 def test_tcgen05_throughput_smoke(ops):
     # the dominant backbone shape at batch 8: 256->256 3x3 @35x35 (not a bench number; sanity only)
     x, w, bias, _ = make(8, 256, 35, 35, 256, 3, 1, 1)
@@ -162,3 +204,6 @@ def test_tcgen05_throughput_smoke(ops):
     flops = 2.0 * 8 * 35 * 35 * 256 * 256 * 9
     print("tc 3x3 256->256 @35^2 B=8: %.3f ms, %.1f TFLOP/s" % (ms, flops / ms / 1e9))
     assert ms > 0
+    _, ms3 = run_conv(ops, x, w, bias, None, 1, 1, 1, 3, iters=20)
+    print("split tc 3x3 256->256 @35^2 B=8: %.3f ms, %.1f algorithmic TFLOP/s (3 MMA passes)" % (ms3, flops / ms3 / 1e9))
+    assert ms3 > 0

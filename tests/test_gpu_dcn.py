@@ -48,6 +48,23 @@ def test_dcn_f16_paths_vs_oracle(C, stride):
     assert np.abs(y - ref).max() < 1e-2 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("C,stride", [(64, 1), (128, 2)])
+def test_dcn_split_precision_vs_oracle(C, stride):
+    """YB_PREC_F16X3: gather of hi+lo samples -> split columns -> three-pass tcgen05 contraction; fp32-equivalent."""
+    r = np.random.RandomState(7 * C + stride)
+    B, H, W, Co = 2, 21, 19, 96
+    x = r.standard_normal((B, C, H, W)).astype(np.float32)
+    w = (r.standard_normal((Co, C, 3, 3)) * (2.0 / (9 * C)) ** 0.5).astype(np.float32)
+    bias = r.standard_normal(Co).astype(np.float32) * 0.1
+    Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+    off = (r.standard_normal((B, 18, Ho, Wo)) * 1.5).astype(np.float32)
+    msk = (1 / (1 + np.exp(-r.standard_normal((B, 9, Ho, Wo))))).astype(np.float32)
+    ref = O.dcn_v2_forward(x, off, msk, w, bias, stride, 1, 1)
+    t = lambda a: torch.from_numpy(a).cuda()
+    y = dcn_v2_conv(t(x), t(off), t(msk), t(w), t(bias), stride, 1, 1, 1, precision="f16x3").cpu().numpy()
+    assert np.abs(y - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+
+
 def test_dcn_module_names():
     m = DCN(64, 64, 3, 1, 1)
     assert sorted(k for k, _ in m.named_parameters()) == ["bias", "conv_offset_mask.bias", "conv_offset_mask.weight", "weight"]

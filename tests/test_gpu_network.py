@@ -1,9 +1,10 @@
 """Whole path through the reference-facing API (yolact_b200.Yolact / postprocess) against the
 reference's golden outputs.
 
-  * precision='f32'  (fp32 CUDA-core parity mode): raw head tensors within 1e-4 of the reference,
-    class ids bit-exact, boxes/scores within 1e-5.
-  * precision='f16tc' (tcgen05 production mode): fp16 operands, fp32 accumulation.  Tolerances are
+  * precision='f16x3' (split-precision tcgen05, the default and benched mode) and precision='f32' (fp32 CUDA-core
+    second opinion): raw head tensors within 1e-4 of the reference, class ids bit-exact, boxes/scores within 2e-5
+    (north_star asks for 1e-3), binarised masks < 1e-3 mismatching pixels.
+  * precision='f16tc' (single-pass fp16 tcgen05, the fast mode): fp16 operands, fp32 accumulation.  Tolerances are
     written next to each assert; discrete outputs (class ids, NMS keep set) are reported as agreement
     ratios because they are discontinuous in the scores (hard part 1).
 """
@@ -38,9 +39,13 @@ def build(case, precision):
     return g, cfg, net
 
 
+EXACT_MODES = ["f16x3", "f32"]
+
+
+@pytest.mark.parametrize("prec", EXACT_MODES)
 @pytest.mark.parametrize("case", NET_CASES)
-def test_raw_heads_f32_mode(case):
-    g, cfg, net = build(case, "f32")
+def test_raw_heads_exact_modes(case, prec):
+    g, cfg, net = build(case, prec)
     net.train()
     out = net(torch.from_numpy(g["x"]).cuda())
     rs = int(g["row_stride"])
@@ -50,7 +55,7 @@ def test_raw_heads_f32_mode(case):
         if k != "proto":
             got = got[:, ::rs]
         e = rel_err(got, g["raw_" + k])
-        print(case, "f32", k, "rel err %.2e" % e)
+        print(case, prec, k, "rel err %.2e" % e)
         assert e < tol, (k, e)
 
 
@@ -72,9 +77,10 @@ def test_raw_heads_f16tc_mode(case):
         assert e < 1.5e-2, (k, e)
 
 
+@pytest.mark.parametrize("prec", EXACT_MODES)
 @pytest.mark.parametrize("case", ["net_resnet50_160", "net_base_192x160_b2", "net_plus_resnet50_256"])
-def test_backbone_features_f32_mode(case):
-    g, cfg, net = build(case, "f32")
+def test_backbone_features_exact_modes(case, prec):
+    g, cfg, net = build(case, prec)
     net.train()
     net(torch.from_numpy(g["x"]).cuda())
     for i in range(4):
@@ -83,10 +89,11 @@ def test_backbone_features_f32_mode(case):
         assert e < 1e-4, (i, e)
 
 
+@pytest.mark.parametrize("prec", EXACT_MODES)
 @pytest.mark.parametrize("case", NET_CASES)
-def test_eval_pipeline_f32_mode(case):
+def test_eval_pipeline_exact_modes(case, prec):
     """net(x) in eval mode + postprocess: the exact call sequence of eval.py (eval.py:949,266)."""
-    g, cfg, net = build(case, "f32")
+    g, cfg, net = build(case, prec)
     net.eval()
     preds = net(torch.from_numpy(g["x"]).cuda())
     ph, pw = (int(v) for v in g["post_hw"])
@@ -108,7 +115,7 @@ def test_eval_pipeline_f32_mode(case):
         assert np.abs(boxes.cpu().numpy() - g["post%d_boxes" % b]).max() <= 1     # .long() of x*w at 1e-5 noise
         ref = unpack_masks(g["post%d_masks_packed" % b], pw)
         mism = float((masks.cpu().numpy() != ref).mean())
-        print(case, "image", b, "mask pixel mismatch %.2e" % mism)
+        print(case, prec, "image", b, "mask pixel mismatch %.2e" % mism)
         assert mism < 1e-3
 
 
@@ -149,7 +156,7 @@ def test_full_size_yolact_base_f16tc_vs_f32_and_oracle():
     yolact_b200.cfg.replace(cfg.copy())
     x = deterministic_input(2, 550, 550, 99)
     outs = {}
-    for prec in ("f32", "f16tc"):
+    for prec in ("f32", "f16tc", "f16x3"):
         net = yolact_b200.Yolact(cfg, precision=prec)
         sd = deterministic_state_dict(net.state_dict(), 1)
         net.load_state_dict(sd)
@@ -165,10 +172,11 @@ def test_full_size_yolact_base_f16tc_vs_f32_and_oracle():
         assert e < (4e-2 if k == "mask" else 1.5e-2)
     orc = O.ConvStackOracle(cfg, sd)
     ref = orc.forward(x[:1])
-    for k in ("loc", "conf", "mask", "proto"):
-        e = rel_err(outs["f32"][k][:1].numpy(), ref[k].numpy())
-        print("yolact_base@550 f32 vs CPU oracle", k, "rel err %.2e" % e)
-        assert e < 2e-4
+    for prec in ("f32", "f16x3"):
+        for k in ("loc", "conf", "mask", "proto"):
+            e = rel_err(outs[prec][k][:1].numpy(), ref[k].numpy())
+            print("yolact_base@550 %s vs CPU oracle" % prec, k, "rel err %.2e" % e)
+            assert e < 2e-4
     assert np.array_equal(outs["f32"]["priors"].numpy(), ref["priors"].numpy())
 
 

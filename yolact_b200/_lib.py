@@ -39,7 +39,8 @@ class YbConfig(ctypes.Structure):
 
 
 YB_BACKBONE_NONE, YB_BACKBONE_RESNET, YB_BACKBONE_DARKNET = -1, 0, 1
-YB_PREC_F32, YB_PREC_F16TC = 0, 1
+YB_PREC_F32, YB_PREC_F16TC, YB_PREC_F16X3 = 0, 1, 2
+PRECISIONS = {"f32": YB_PREC_F32, "f16tc": YB_PREC_F16TC, "f16x3": YB_PREC_F16X3}
 YB_MASK_F32, YB_MASK_U8, YB_MASK_BITS = 0, 1, 2
 YB_NMS_FAST, YB_NMS_CROSS_CLASS, YB_NMS_TRADITIONAL = 0, 1, 2
 YB_XFORM_NORMALIZE, YB_XFORM_SUBTRACT_MEANS, YB_XFORM_TO_FLOAT, YB_XFORM_NONE = 0, 1, 2, 3

@@ -63,6 +63,22 @@ __global__ void pack_w_dcn_tc_kernel(const float* __restrict__ w, __half* __rest
     out[(int64_t)o * taps * Ci + (int64_t)t * Ci + c] = from_f32<__half>(w[i]);
   }
 }
+// split-precision variant: [Cout][hi(9*Cin) | lo(9*Cin)] of w * up (up = a power of two)
+__global__ void pack_w_dcn_tc_split_kernel(const float* __restrict__ w, __half* __restrict__ out, int Co, int Ci, int taps,
+                                           float up) {
+  const int64_t total = (int64_t)Co * Ci * taps;
+  const int64_t K = (int64_t)taps * Ci;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int t = (int)(i % taps);
+    int64_t r = i / taps;
+    int c = (int)(r % Ci);
+    int o = (int)(r / Ci);
+    __half hi, lo;
+    split_f32(w[i] * up, hi, lo);
+    out[(int64_t)o * 2 * K + (int64_t)t * Ci + c] = hi;
+    out[(int64_t)o * 2 * K + K + (int64_t)t * Ci + c] = lo;
+  }
+}
 // offset [B,18,HW] + mask [B,9,HW] (NCHW fp32) -> om [B,HW,27]
 __global__ void pack_om_kernel(const float* __restrict__ off, const float* __restrict__ msk, float* __restrict__ om,
                                int B, int HW) {
@@ -141,7 +157,8 @@ int yb_create(const yb_config* cfg, int device, yb_handle** out) {
     for (int i = 0; i < 3; ++i)
       YB_REQUIRE(cfg->selected_layers[i] >= 0 && cfg->selected_layers[i] < cfg->num_stages, "bad selected_layers");
   }
-  YB_REQUIRE(cfg->precision == YB_PREC_F32 || cfg->precision == YB_PREC_F16TC, "unknown precision");
+  YB_REQUIRE(cfg->precision == YB_PREC_F32 || cfg->precision == YB_PREC_F16TC || cfg->precision == YB_PREC_F16X3,
+             "unknown precision");
   YB_REQUIRE(cfg->mask_dim % 4 == 0 && cfg->mask_dim > 0, "mask_dim must be a positive multiple of 4");
   DeviceGuard g(device);
   YB_CHECK_CUDA(cudaFree(0));
@@ -260,7 +277,8 @@ int yb_debug_feature(yb_handle* h, int which, float* d_out, int32_t* chw, void* 
     if (a.f32)
       launch_nhwc_to_nchw_f32<float>((const float*)a.ptr, d_out, a.B, a.H, a.W, a.C, (cudaStream_t)stream, &h->lc);
     else
-      launch_nhwc_to_nchw_f32<__half>((const __half*)a.ptr, d_out, a.B, a.H, a.W, a.C, (cudaStream_t)stream, &h->lc);
+      launch_nhwc_to_nchw_f32<__half>((const __half*)a.ptr, d_out, a.B, a.H, a.W, a.C, (cudaStream_t)stream, &h->lc,
+                                      a.split ? 1 : 0);
   }
   YB_API_END
 }
@@ -470,7 +488,10 @@ int yb_dcn_forward(yb_handle* h, const float* d_input, const float* d_weight, co
   pack_om_kernel<<<grid1d((int64_t)B * Ho * Wo * 27), 256, 0, s>>>(d_offset, d_mask, om, B, Ho * Wo);
   YB_CHECK_LAUNCH();
   const int64_t wn = (int64_t)Co * C * 9;
-  const bool f16 = (h->cfg.precision == YB_PREC_F16TC);
+  const bool f16 = (h->cfg.precision != YB_PREC_F32);
+  const int sp = (h->cfg.precision == YB_PREC_F16X3) ? 1 : 0;
+  YB_REQUIRE(!sp || C % 64 == 0, "yb_dcn_forward: the split-precision mode needs C % 64 == 0");
+  const int npl = sp ? 2 : 1;
   if (!f16) {
     float* x = (float*)tp.get((size_t)B * H * W * C * 4);
     float* y = (float*)tp.get((size_t)B * Ho * Wo * Co * 4);
@@ -482,15 +503,30 @@ int yb_dcn_forward(yb_handle* h, const float* d_input, const float* d_weight, co
                            &h->lc);
     launch_nhwc_to_nchw_f32<float>(y, d_output, B, Ho, Wo, Co, s, &h->lc);
   } else {
-    __half* x = (__half*)tp.get((size_t)B * H * W * C * 2);
-    __half* y = (__half*)tp.get((size_t)B * Ho * Wo * Co * 2);
-    launch_nchw_f32_to_nhwc<__half>(d_input, x, B, C, H, W, s, &h->lc);
+    __half* x = (__half*)tp.get((size_t)B * H * W * C * 2 * npl);
+    __half* y = (__half*)tp.get((size_t)B * Ho * Wo * Co * 2 * npl);
+    launch_nchw_f32_to_nhwc<__half>(d_input, x, B, C, H, W, s, &h->lc, sp);
     if (C % 64 == 0) {
-      __half* cols = (__half*)tp.get((size_t)B * Ho * Wo * 9 * C * 2);
-      __half* wk = (__half*)tp.get((size_t)wn * 2);
-      pack_w_dcn_tc_kernel<<<grid1d(wn), 256, 0, s>>>(d_weight, wk, Co, C, 9);
+      __half* cols = (__half*)tp.get((size_t)B * Ho * Wo * 9 * C * 2 * npl);
+      __half* wk = (__half*)tp.get((size_t)wn * 2 * npl);
+      float out_scale = 1.f;
+      if (sp) {
+        // one power of two for the whole weight tensor: max |w| is read back (op-level hook, not the hot path)
+        std::vector<float> hw((size_t)wn);
+        YB_CHECK_CUDA(cudaMemcpyAsync(hw.data(), d_weight, (size_t)wn * 4, cudaMemcpyDeviceToHost, s));
+        YB_CHECK_CUDA(cudaStreamSynchronize(s));
+        float mx = 0.f;
+        for (float v : hw) mx = std::max(mx, fabsf(v));
+        int ex = 0;
+        if (mx > 0.f) frexpf(mx, &ex);
+        const int e = mx > 0.f ? std::max(-24, std::min(40, 14 - ex)) : 0;
+        out_scale = ldexpf(1.f, -e);
+        pack_w_dcn_tc_split_kernel<<<grid1d(wn), 256, 0, s>>>(d_weight, wk, Co, C, 9, ldexpf(1.f, e));
+      } else {
+        pack_w_dcn_tc_kernel<<<grid1d(wn), 256, 0, s>>>(d_weight, wk, Co, C, 9);
+      }
       YB_CHECK_LAUNCH();
-      launch_dcn_gather_f16(x, om, cols, B, H, W, C, Ho, Wo, stride_h, pad_h, dilation_h, 0, s, &h->lc);
+      launch_dcn_gather_f16(x, om, cols, B, H, W, C, Ho, Wo, stride_h, pad_h, dilation_h, 0, s, &h->lc, sp);
       ConvProblem p;
       p.B = B;
       p.H = Ho;
@@ -501,8 +537,10 @@ int yb_dcn_forward(yb_handle* h, const float* d_input, const float* d_weight, co
       p.Cout = Co;
       p.x = cols;
       p.y = y;
-      p.y_batch_stride = (int64_t)Ho * Wo * Co;
-      p.y_pix_stride = Co;
+      p.split = sp;
+      p.out_scale = out_scale;
+      p.y_pix_stride = Co * npl;
+      p.y_batch_stride = (int64_t)Ho * Wo * p.y_pix_stride;
       p.bias = d_bias;
       TcConvPlan* plan = tc_conv_plan_create(p, wk);
       try {
@@ -519,7 +557,7 @@ int yb_dcn_forward(yb_handle* h, const float* d_input, const float* d_weight, co
       launch_dcn_simt<__half>(x, om, wk, d_bias, y, B, H, W, C, Ho, Wo, Co, stride_h, pad_h, dilation_h, ACT_NONE, 0,
                               s, &h->lc);
     }
-    launch_nhwc_to_nchw_f32<__half>(y, d_output, B, Ho, Wo, Co, s, &h->lc);
+    launch_nhwc_to_nchw_f32<__half>(y, d_output, B, Ho, Wo, Co, s, &h->lc, sp);
   }
   YB_CHECK_CUDA(cudaStreamSynchronize(s));  // temporaries are freed on return
   YB_API_END
@@ -530,7 +568,9 @@ int yb_conv2d(yb_handle* h, const float* d_x, const float* h_w, const float* h_b
               int precision, int iters, float* ms, void* stream) {
   YB_API_BEGIN
   YB_REQUIRE(h && d_x && h_w && d_y, "yb_conv2d: null argument");
-  YB_REQUIRE(precision >= 0 && precision <= 2, "yb_conv2d: precision must be 0 (f32 simt), 1 (f16 tcgen05), 2 (f16 simt)");
+  YB_REQUIRE(precision >= 0 && precision <= 3,
+             "yb_conv2d: precision must be 0 (f32 simt), 1 (f16 tcgen05), 2 (f16 simt), 3 (split-precision tcgen05)");
+  const int sp = (precision == 3) ? 1 : 0;
   DeviceGuard g(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
@@ -539,7 +579,7 @@ int yb_conv2d(yb_handle* h, const float* d_x, const float* h_w, const float* h_b
   const int taps = kh * kw;
   const size_t K = (size_t)taps * Ci;
   const bool f16 = precision != 0;
-  const size_t es = f16 ? 2 : 4;
+  const size_t es = (f16 && !sp) ? 2 : 4;   // split: two halfs per element
   void* x = tp.get((size_t)B * H * W * Ci * es);
   void* y = tp.get((size_t)B * Ho * Wo * Co * es);
   void* res = d_residual ? tp.get((size_t)B * Ho * Wo * Co * es) : nullptr;
@@ -563,22 +603,41 @@ int yb_conv2d(yb_handle* h, const float* d_x, const float* h_w, const float* h_b
   p.act = act;
   p.x = x;
   p.y = y;
-  p.y_batch_stride = (int64_t)Ho * Wo * Co;
-  p.y_pix_stride = Co;
+  p.split = sp;
+  p.y_pix_stride = sp ? 2 * Co : Co;
+  p.y_batch_stride = (int64_t)Ho * Wo * p.y_pix_stride;
   p.bias = bias;
   p.residual = res;
   if (!f16) {
     launch_nchw_f32_to_nhwc<float>(d_x, (float*)x, B, Ci, H, W, s, &h->lc);
     if (res) launch_nchw_f32_to_nhwc<float>(d_residual, (float*)res, B, Co, Ho, Wo, s, &h->lc);
   } else {
-    launch_nchw_f32_to_nhwc<__half>(d_x, (__half*)x, B, Ci, H, W, s, &h->lc);
-    if (res) launch_nchw_f32_to_nhwc<__half>(d_residual, (__half*)res, B, Co, Ho, Wo, s, &h->lc);
+    launch_nchw_f32_to_nhwc<__half>(d_x, (__half*)x, B, Ci, H, W, s, &h->lc, sp);
+    if (res) launch_nchw_f32_to_nhwc<__half>(d_residual, (__half*)res, B, Co, Ho, Wo, s, &h->lc, sp);
   }
   std::function<void()> run;
   TcConvPlan* plan = nullptr;
-  if (precision == 1) {
+  if (precision == 1 || precision == 3) {
     YB_REQUIRE(tc_conv_supported(p), "yb_conv2d: shape not supported by the tcgen05 kernel (Cin % 64, taps <= 9)");
-    std::vector<__half> pk(K * Co);
+    std::vector<__half> pk(K * Co * (sp ? 2 : 1));
+    if (sp) {
+      float mx = 0.f;
+      for (size_t i = 0; i < K * Co; ++i) mx = std::max(mx, fabsf(h_w[i]));
+      int ex = 0;
+      if (mx > 0.f) frexpf(mx, &ex);
+      const int e = mx > 0.f ? std::max(-24, std::min(40, 14 - ex)) : 0;
+      const float up = ldexpf(1.f, e);
+      p.out_scale = ldexpf(1.f, -e);
+      for (int o = 0; o < Co; ++o)
+        for (int c = 0; c < Ci; ++c)
+          for (int t = 0; t < taps; ++t) {
+            const float vs = h_w[((size_t)o * Ci + c) * taps + t] * up;
+            const __half hi = __float2half_rn(vs);
+            const size_t idx = ((size_t)t * Co + o) * 2 * Ci + c;
+            pk[idx] = hi;
+            pk[idx + Ci] = __float2half_rn(vs - __half2float(hi));
+          }
+    } else
     for (int o = 0; o < Co; ++o)
       for (int c = 0; c < Ci; ++c)
         for (int t = 0; t < taps; ++t)
@@ -639,7 +698,7 @@ int yb_conv2d(yb_handle* h, const float* d_x, const float* h_w, const float* h_b
   if (!f16)
     launch_nhwc_to_nchw_f32<float>((const float*)y, d_y, B, Ho, Wo, Co, s, &h->lc);
   else
-    launch_nhwc_to_nchw_f32<__half>((const __half*)y, d_y, B, Ho, Wo, Co, s, &h->lc);
+    launch_nhwc_to_nchw_f32<__half>((const __half*)y, d_y, B, Ho, Wo, Co, s, &h->lc, sp);
   YB_CHECK_CUDA(cudaStreamSynchronize(s));
   YB_API_END
 }

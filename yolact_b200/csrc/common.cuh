@@ -68,6 +68,15 @@ __device__ __forceinline__ __half from_f32<__half>(float v) {
   return __float2half_rn(v);
 }
 
+// Split-precision activations (YB_PREC_F16X3): a value is stored as TWO fp16 numbers hi + lo with
+// hi = rn(v), lo = rn(v - hi): 22 significand bits (fp16 subnormals bound the absolute error of lo by 2^-25).
+// A pixel of a split NHWC tensor is [hi(C) | lo(C)], i.e. 2*C halfs.
+__device__ __forceinline__ void split_f32(float v, __half& hi, __half& lo) {
+  v = fminf(fmaxf(v, -65504.f), 65504.f);
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
     case ACT_RELU: return fmaxf(v, 0.f);

@@ -153,7 +153,8 @@ struct NetBuilder {
   yb_handle* h;
   Executor* ex;
   bool dry;
-  bool f16;
+  bool f16;     // fp16 storage + tcgen05 kernels (YB_PREC_F16TC and YB_PREC_F16X3)
+  bool split;   // YB_PREC_F16X3: split-precision activations / weights, three MMA passes
   int lane = 0;
   void push(Op& op) {
     op.lane = lane;
@@ -169,7 +170,8 @@ struct NetBuilder {
     a.W = W;
     a.C = C;
     a.f32 = f32 || !f16;
-    if (!dry) a.ptr = dmalloc(ex->allocs, (size_t)a.numel() * (a.f32 ? 4 : 2));
+    a.split = split && !a.f32;
+    if (!dry) a.ptr = dmalloc(ex->allocs, (size_t)a.numel() * ((a.f32 || a.split) ? 4 : 2));
     return a;
   }
 
@@ -197,7 +199,9 @@ struct NetBuilder {
     p.Wo = conv_out(in.W, k, stride, pad);
     p.x = in.ptr;
     p.x_nchw_f32 = in_nchw ? 1 : 0;
+    p.split = in.split ? 1 : 0;
     const bool tc = f16 && !in_nchw && (in.C % 64 == 0) && !in.f32;
+    YB_REQUIRE(!split || tc || in_nchw, ("conv " + key + ": the split-precision mode has tensor-core kernels only").c_str());
     const bool simt_half = f16 && !tc && !in.f32;
     const bool stem_tc = f16 && in_nchw && !ospec && !out_f32 && !residual && h->stem_on_tc &&
                          stem_tc_supported(k, stride, pad, in.C, h->peek_cout(key));
@@ -206,6 +210,7 @@ struct NetBuilder {
     YB_REQUIRE(w.Cin == in.C && w.KH == k && w.KW == k, ("conv " + key + ": weight shape mismatch").c_str());
     p.Cout = w.Cout;
     p.bias = w.bias;
+    p.out_scale = w.out_scale;
     Act out;
     if (ospec) {
       out.B = in.B;
@@ -222,11 +227,13 @@ struct NetBuilder {
       out = alloc_act(in.B, p.Ho, p.Wo, w.Cout, out_f32);
       p.y = out.ptr;
       p.y_f32 = (f16 && out.f32) ? 1 : 0;
-      p.y_batch_stride = (int64_t)p.Ho * p.Wo * w.Cout;
-      p.y_pix_stride = w.Cout;
+      const int ps = out.split ? 2 * w.Cout : w.Cout;
+      p.y_batch_stride = (int64_t)p.Ho * p.Wo * ps;
+      p.y_pix_stride = ps;
     }
     if (residual) {
-      YB_REQUIRE(residual->H == p.Ho && residual->W == p.Wo && residual->C == w.Cout && residual->f32 == !f16,
+      YB_REQUIRE(residual->H == p.Ho && residual->W == p.Wo && residual->C == w.Cout && residual->f32 == !f16 &&
+                     residual->split == split,
                  ("conv " + key + ": residual shape mismatch").c_str());
       p.residual = residual->ptr;
     }
@@ -238,7 +245,7 @@ struct NetBuilder {
               std::to_string(stride) + " " + std::to_string(p.Ho) + "x" + std::to_string(p.Wo);
     if (stem_tc) {
       StemTcPlan* sp = stem_tc_plan_create((const float*)in.ptr, w.w_tc, w.bias, (__half*)out.ptr, in.B, in.H, in.W, k,
-                                           stride, pad, w.Cout, act);
+                                           stride, pad, w.Cout, act, split ? 1 : 0, w.out_scale);
       stem_tc_plan_set_worker_groups(sp, h->stem_wg);
       ex->stem_plans.push_back(sp);
       op.name += h->stem_wg == 2 ? " stem wg=2" : " stem";
@@ -277,9 +284,10 @@ struct NetBuilder {
     LaunchCounter* lc = &h->lc;
     Op op;
     op.name = "maxpool";
+    const int sp = in.split ? 1 : 0;
     if (f16)
-      op.fn = [in, out, lc](cudaStream_t s) {
-        launch_maxpool3x3s2<__half>((const __half*)in.ptr, (__half*)out.ptr, in.B, in.H, in.W, in.C, out.H, out.W, s, lc);
+      op.fn = [in, out, lc, sp](cudaStream_t s) {
+        launch_maxpool3x3s2<__half>((const __half*)in.ptr, (__half*)out.ptr, in.B, in.H, in.W, in.C, out.H, out.W, s, lc, sp);
       };
     else
       op.fn = [in, out, lc](cudaStream_t s) {
@@ -297,10 +305,11 @@ struct NetBuilder {
     const void* addp = add ? add->ptr : nullptr;
     Op op;
     op.name = "upsample " + std::to_string(Ho) + "x" + std::to_string(Wo);
+    const int sp = in.split ? 1 : 0;
     if (f16)
-      op.fn = [in, out, addp, sh, sw, relu, lc](cudaStream_t s) {
+      op.fn = [in, out, addp, sh, sw, relu, lc, sp](cudaStream_t s) {
         launch_upsample_bilinear<__half>((const __half*)in.ptr, (const __half*)addp, (__half*)out.ptr, in.B, in.H,
-                                         in.W, in.C, out.H, out.W, sh, sw, relu, s, lc);
+                                         in.W, in.C, out.H, out.W, sh, sw, relu, s, lc, sp);
       };
     else
       op.fn = [in, out, addp, sh, sw, relu, lc](cudaStream_t s) {
@@ -338,9 +347,10 @@ struct NetBuilder {
       Op g;
       g.is_conv = true;
       g.name = key + " dcn_gather";
-      g.fn = [in, om, cols, stride, lc](cudaStream_t s) {
+      const int sp = in.split ? 1 : 0;
+      g.fn = [in, om, cols, stride, lc, sp](cudaStream_t s) {
         launch_dcn_gather_f16((const __half*)in.ptr, (const float*)om.ptr, (__half*)cols.ptr, in.B, in.H, in.W, in.C,
-                              cols.H, cols.W, stride, 1, 1, 1, s, lc);
+                              cols.H, cols.W, stride, 1, 1, 1, s, lc, sp);
       };
       push(g);
       ConvProblem p;
@@ -357,8 +367,10 @@ struct NetBuilder {
       p.act = ACT_RELU;
       p.x = cols.ptr;
       p.y = out.ptr;
-      p.y_batch_stride = (int64_t)Ho * Wo * w.Cout;
-      p.y_pix_stride = w.Cout;
+      p.split = sp;
+      p.out_scale = w.out_scale;
+      p.y_pix_stride = sp ? 2 * w.Cout : w.Cout;
+      p.y_batch_stride = (int64_t)Ho * Wo * p.y_pix_stride;
       p.bias = w.bias;
       TcConvPlan* plan = autotune_tc(p, w.w_tc);
       ex->plans.push_back(plan);
@@ -394,6 +406,8 @@ struct NetBuilder {
     p.y_batch_stride = P * 4;
     p.y_pix_stride = c4;
     p.bias = w.bias;
+    p.split = in.split ? 1 : 0;
+    p.out_scale = w.out_scale;
     p.nseg = 3;
     const int begins[4] = {0, c4, c4 + cc, c4 + cc + cm};
     float* bases[3] = {loc, conf, coef};
@@ -432,7 +446,7 @@ struct NetBuilder {
     const std::string tkey = std::to_string(p.B) + "," + std::to_string(p.H) + "," + std::to_string(p.W) + "," +
                              std::to_string(p.Cin) + "," + std::to_string(p.Cout) + "," + std::to_string(p.KH) + "," +
                              std::to_string(p.stride) + "," + std::to_string(p.pad) + "," + (p.residual ? "r" : "-") +
-                             (p.y_f32 ? "f" : "h") + std::to_string(p.nseg) + "," + std::to_string(p.y_pix_stride) + "," + std::to_string((long long)p.y_batch_stride);
+                             (p.y_f32 ? "f" : "h") + (p.split ? "s" : "") + std::to_string(p.nseg) + "," + std::to_string(p.y_pix_stride) + "," + std::to_string((long long)p.y_batch_stride);
     auto it = h->tune_cache.find(tkey);
     if (it != h->tune_cache.end())
       return tc_conv_plan_create(p, w, it->second[0], it->second[1], it->second[2], it->second[3], it->second[4],
@@ -469,7 +483,12 @@ struct NetBuilder {
           if (pi && bns[bi] < 64) continue;
           if (ei && (bns[bi] < 64 || gi == 1)) continue;   // 320-thread CTAs: one per SM
           if (di && (pi || ei || gi == 1)) continue;        // PDL-friendly: single CTAs, one epilogue group, <= 1 CTA/SM of its own
-          TcConvPlan* cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi], pi, ei ? 2 : 1, di);
+          TcConvPlan* cand = nullptr;
+          try {
+            cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi], pi, ei ? 2 : 1, di);
+          } catch (const Error&) {
+            continue;   // this tiling does not fit in shared memory (split precision doubles every stage)
+          }
           if ((pi && !tc_conv_plan_pair(cand)) || (ei && tc_conv_plan_epi_groups(cand) != 2) ||
               (di && !tc_conv_plan_pdl_friendly(cand))) {
             tc_conv_plan_destroy(cand);
@@ -526,7 +545,7 @@ static bool block_uses_dcn(const yb_config& cfg, int stage, int j) {
 
 void build_network(yb_handle* h, Executor* ex, bool dry) {
   const yb_config& cfg = h->cfg;
-  NetBuilder nb{h, ex, dry, cfg.precision == YB_PREC_F16TC};
+  NetBuilder nb{h, ex, dry, cfg.precision != YB_PREC_F32, cfg.precision == YB_PREC_F16X3};
   const int B = ex->B, H = ex->H, W = ex->W;
   const int NC = cfg.num_classes, MD = cfg.mask_dim, A = cfg.num_scales * cfg.num_ars;
 
@@ -712,6 +731,23 @@ int yb_handle::peek_cout(const std::string& conv_key) const {
   return (it == host.end() || it->second.shape.empty()) ? 0 : (int)it->second.shape[0];
 }
 
+// ---- split-precision weight packing (YB_PREC_F16X3) -----------------------------------------------------------------
+// w * 2^e = hi + lo with hi = rn_fp16(w * 2^e), lo = rn_fp16(w * 2^e - hi).  e puts the largest |w| of the layer
+// just below 2^14, so that hi never overflows and lo (<= 2^-11 |hi|) is a normal fp16 number for every weight larger
+// than 2^-17 of the layer's maximum; the kernels multiply the fp32 accumulator by 2^-e (exact).
+static int split_exponent(float max_abs) {
+  if (!(max_abs > 0.f) || !std::isfinite(max_abs)) return 0;
+  int ex = 0;
+  frexpf(max_abs, &ex);          // max_abs = m * 2^ex, m in [0.5, 1)
+  return std::max(-24, std::min(40, 14 - ex));
+}
+static inline void split_pack(float v, float scale, __half* hi, __half* lo) {
+  const float vs = v * scale;
+  const __half h = __float2half_rn(vs);
+  *hi = h;
+  *lo = __float2half_rn(vs - __half2float(h));
+}
+
 static const HostTensor& need(yb_handle* h, const std::string& name) {
   auto it = h->host.find(name);
   if (it == h->host.end()) throw Error(YB_ERR_MISSING_WEIGHT, "missing weight: " + name);
@@ -778,7 +814,37 @@ ConvW& yb_handle::get_conv(const std::string& conv_key, const std::string& bn_ke
     cw.w_f16 = (__half*)dmalloc(weight_allocs, pk.size() * 2);
     YB_CHECK_CUDA(cudaMemcpy(cw.w_f16, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
   }
-  if (need_tc) {
+  const bool split = (cfg.precision == YB_PREC_F16X3);
+  if (need_tc && split) {
+    float mx = 0.f;
+    for (int o = 0; o < Co; ++o)
+      for (size_t i = 0; i < (size_t)Ci * taps; ++i) mx = std::max(mx, fabsf(w.data[(size_t)o * Ci * taps + i] * scale[o]));
+    const int e = split_exponent(mx);
+    const float up = ldexpf(1.f, e);
+    cw.out_scale = ldexpf(1.f, -e);
+    const size_t kpad = (pack == 2) ? (size_t)stem_tc_kpad(KH) : K;   // plane length along K
+    std::vector<__half> pk(2 * kpad * Co, __float2half_rn(0.f));
+    for (int o = 0; o < Co; ++o)
+      for (int c = 0; c < Ci; ++c)
+        for (int t = 0; t < taps; ++t) {
+          const float v = w.data[((size_t)o * Ci + c) * taps + t] * scale[o];
+          size_t hi;   // index of the hi half; lo lives one plane further
+          size_t plane;
+          if (pack == 2) {          // stem: [Cout][hi(Kpad) | lo(Kpad)], k = c*taps + t
+            hi = (size_t)o * 2 * kpad + (size_t)c * taps + t;
+            plane = kpad;
+          } else if (pack == 1) {   // DCN: [Cout][hi(9*Cin) | lo(9*Cin)], k = t*Cin + c
+            hi = (size_t)o * 2 * K + (size_t)t * Ci + c;
+            plane = K;
+          } else {                  // [tap][Cout][hi(Cin) | lo(Cin)]
+            hi = ((size_t)t * Co + o) * 2 * Ci + c;
+            plane = (size_t)Ci;
+          }
+          split_pack(v, up, &pk[hi], &pk[hi + plane]);
+        }
+    cw.w_tc = (__half*)dmalloc(weight_allocs, pk.size() * 2);
+    YB_CHECK_CUDA(cudaMemcpy(cw.w_tc, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+  } else if (need_tc) {
     std::vector<__half> pk(K * Co);
     if (pack == 2) {
       // stem: [Cout][Kpad], k = c*taps + t (the OIHW flattening), zero padded to a multiple of 64
@@ -822,16 +888,34 @@ ConvW& yb_handle::get_fused_head(const std::string& hn) {
     Ci = (int)w.shape[1];
     Co += (int)w.shape[0];
   }
-  std::vector<__half> pk((size_t)9 * Co * Ci);
+  const bool split = (cfg.precision == YB_PREC_F16X3);
+  const int npl = split ? 2 : 1;
+  std::vector<__half> pk((size_t)9 * Co * Ci * npl);
   std::vector<float> bias(Co, 0.f);
+  float up = 1.f;
+  if (split) {   // one power-of-two scale for the three fused convs (they share the accumulator tile)
+    float mx = 0.f;
+    for (int i = 0; i < 3; ++i)
+      for (float v : need(this, hn + parts[i] + ".weight").data) mx = std::max(mx, fabsf(v));
+    const int e = split_exponent(mx);
+    up = ldexpf(1.f, e);
+    cw.out_scale = ldexpf(1.f, -e);
+  }
   int o0 = 0;
   for (int i = 0; i < 3; ++i) {
     const HostTensor& w = need(this, hn + parts[i] + ".weight");
     const int co = (int)w.shape[0];
     for (int o = 0; o < co; ++o)
       for (int c = 0; c < Ci; ++c)
-        for (int t = 0; t < 9; ++t)
-          pk[((size_t)t * Co + o0 + o) * Ci + c] = __float2half_rn(w.data[((size_t)o * Ci + c) * 9 + t]);
+        for (int t = 0; t < 9; ++t) {
+          const float v = w.data[((size_t)o * Ci + c) * 9 + t];
+          if (split) {
+            const size_t hi = ((size_t)t * Co + o0 + o) * 2 * Ci + c;
+            split_pack(v, up, &pk[hi], &pk[hi + Ci]);
+          } else {
+            pk[((size_t)t * Co + o0 + o) * Ci + c] = __float2half_rn(v);
+          }
+        }
     auto it = host.find(hn + parts[i] + ".bias");
     if (it != host.end())
       for (int o = 0; o < co; ++o) bias[o0 + o] = it->second.data[o];

@@ -30,13 +30,18 @@ struct ConvW {
   __half* w_tc = nullptr;    // [KH*KW][Cout][Cin]          (tcgen05), or [1][Cout][9*Cin] for DCN
   float* bias = nullptr;     // [Cout] or null
   int pack = 0;              // 0 normal, 1 DCN ([Cout][9*Cin]), 2 stem ([Cout][Kpad], OIHW order)
+  // YB_PREC_F16X3: w_tc holds [..][hi(K) | lo(K)] fp16 pairs of w * 2^e (e chosen so that max |w| * 2^e < 2^15:
+  // the lo parts stay normal fp16 numbers); out_scale = 2^-e is applied to the fp32 accumulator
+  float out_scale = 1.f;
 };
 
-// NHWC activation (element type float in YB_PREC_F32, __half in YB_PREC_F16TC unless f32 is set)
+// NHWC activation (element type float in YB_PREC_F32, __half in YB_PREC_F16TC unless f32 is set;
+// YB_PREC_F16X3: `split` -- every pixel is [hi(C) | lo(C)] halfs, value = hi + lo)
 struct Act {
   void* ptr = nullptr;
   int B = 0, H = 0, W = 0, C = 0;
   bool f32 = false;
+  bool split = false;
   int64_t numel() const { return (int64_t)B * H * W * C; }
 };
 

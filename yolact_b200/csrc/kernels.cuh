@@ -25,6 +25,11 @@ struct ConvProblem {
   const float* bias = nullptr;     // [Cout] fp32 (BN folded), nullable
   const void* residual = nullptr;  // dense NHWC [B,Ho,Wo,Cout], activation dtype, nullable
   int res_after_act = 0;           // 1: y = act(conv) + residual (DarkNetBlock, backbone.py:246-247)
+  // split precision (tcgen05 kernel only, YB_PREC_F16X3): x / residual / half outputs are [hi(C) | lo(C)] fp16 pairs
+  // per pixel (y_pix_stride and y_batch_stride count halfs and include both planes), weights are packed
+  // [tap][Cout][hi(Cin) | lo(Cin)] and pre-multiplied by 1 / out_scale (a power of two)
+  int split = 0;
+  float out_scale = 1.f;
   // fused prediction head (tcgen05 kernel only): output channels [seg_begin, seg_end) of segment i go to the
   // fp32 tensor seg_y[i] with its own strides and activation; y / y_* are ignored when nseg > 0
   int nseg = 0;
@@ -45,7 +50,7 @@ void launch_simt_conv(const ConvProblem& p, const void* w, int types, cudaStream
 
 // ---- tcgen05 implicit-GEMM convolution (fp16 in, fp32 accumulate) ----------------------------
 struct TcConvPlan;  // opaque: tensor maps + tiling; built once per (layer, shape, pointers)
-// w_packed: device half [KH*KW][CoutPad][Cin], CoutPad = round_up(Cout,16). Requires Cin % 64 == 0.
+// w_packed: device half [KH*KW][Cout][Cin] ([KH*KW][Cout][2*Cin] when p.split). Requires Cin % 64 == 0.
 // bn_override in {32,64,128,256} / stages_override > 0 pin the N tile / pipeline depth (autotuner); 0 = heuristic.
 // grid_override > 0 caps the number of (persistent) CTAs; default 148 = one per SM.
 // pair_override > 0: CTA pairs (cluster of 2, tcgen05 cta_group::2, UMMA M = 256; each CTA stages half the weight tile).
@@ -69,30 +74,33 @@ struct StemTcPlan;
 bool stem_tc_supported(int ks, int stride, int pad, int cin, int cout);
 int stem_tc_kpad(int ks);   // K = 3*ks*ks rounded up to 64
 // w_packed: device half [cout][kpad], k = c*ks*ks + r*ks + s (OIHW flattening), zero padded
+// split: w_packed is [cout][hi(kpad) | lo(kpad)] scaled by 1 / out_scale, y is [.., hi(cout) | lo(cout)]
 StemTcPlan* stem_tc_plan_create(const float* x_nchw, const __half* w_packed, const float* bias, __half* y, int B,
-                                int H, int W, int ks, int stride, int pad, int cout, int act);
+                                int H, int W, int ks, int stride, int pad, int cout, int act, int split = 0,
+                                float out_scale = 1.f);
 void stem_tc_plan_destroy(StemTcPlan* plan);
 void stem_tc_plan_set_worker_groups(StemTcPlan* plan, int wg);   // 2: two threads per pixel (7x7 stem)
 void launch_stem_tc(const StemTcPlan* plan, cudaStream_t stream, LaunchCounter* lc);
 
 // ---- pointwise -------------------------------------------------------------------------------
+// `split` (T = __half only): tensors are split-precision [hi(C) | lo(C)] pixel pairs (YB_PREC_F16X3).
 // 3x3 stride-2 pad-1 max pool, NHWC (backbone.py:80)
 template <typename T>
 void launch_maxpool3x3s2(const T* x, T* y, int B, int H, int W, int C, int Ho, int Wo,
-                         cudaStream_t stream, LaunchCounter* lc);
+                         cudaStream_t stream, LaunchCounter* lc, int split = 0);
 // y = bilinear(x -> [Ho,Wo], align_corners=False) (+ add), NHWC.  scale_h/scale_w are the
 // source/destination ratios PyTorch uses (in/out, or 1/scale_factor).  relu: clamp at 0.
 template <typename T>
 void launch_upsample_bilinear(const T* x, const T* add, T* y, int B, int H, int W, int C, int Ho,
                               int Wo, float scale_h, float scale_w, int relu, cudaStream_t stream,
-                              LaunchCounter* lc);
+                              LaunchCounter* lc, int split = 0);
 // layout / dtype conversion between the kernels' NHWC(T) and the API's NCHW fp32
 template <typename T>
 void launch_nhwc_to_nchw_f32(const T* x, float* y, int B, int H, int W, int C, cudaStream_t stream,
-                             LaunchCounter* lc);
+                             LaunchCounter* lc, int split = 0);
 template <typename T>
 void launch_nchw_f32_to_nhwc(const float* x, T* y, int B, int C, int H, int W, cudaStream_t stream,
-                             LaunchCounter* lc);
+                             LaunchCounter* lc, int split = 0);
 void launch_softmax_rows(const float* in, float* out, int64_t rows, int cols, cudaStream_t stream,
                          LaunchCounter* lc);
 void launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t stream, LaunchCounter* lc);
@@ -167,6 +175,6 @@ void launch_dcn_simt(const T* x, const float* om, const T* w, const float* bias,
 // [B,Ho,Wo,9*C] (tap-major) so the tcgen05 1x1 contraction can consume them.
 void launch_dcn_gather_f16(const __half* x, const float* om, __half* cols, int B, int H, int W,
                            int C, int Ho, int Wo, int stride, int pad, int dil, int mask_logits,
-                           cudaStream_t stream, LaunchCounter* lc);
+                           cudaStream_t stream, LaunchCounter* lc, int split = 0);
 
 }  // namespace yb

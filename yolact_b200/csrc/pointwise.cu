@@ -46,12 +46,40 @@ __device__ __forceinline__ uint4 pack<__half>(const float* f) {
   return r;
 }
 
+// One 16-byte channel vector of a pixel -> floats.  `px` points at the pixel's first element; split (fp16 only):
+// the pixel is [hi(C) | lo(C)] and the value is hi + lo (YB_PREC_F16X3).
+template <typename T>
+__device__ __forceinline__ void load_vec(const T* px, int C, int cv, int split, float* f) {
+  constexpr int V = DType<T>::kVec;
+  unpack<T>(*reinterpret_cast<const uint4*>(px + cv * V), f);
+  if (sizeof(T) == 2 && split) {
+    float l[V];
+    unpack<T>(*reinterpret_cast<const uint4*>(px + C + cv * V), l);
+#pragma unroll
+    for (int j = 0; j < V; ++j) f[j] += l[j];
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store_vec(T* px, int C, int cv, int split, const float* f) {
+  constexpr int V = DType<T>::kVec;
+  const uint4 hi = pack<T>(f);
+  *reinterpret_cast<uint4*>(px + cv * V) = hi;
+  if (sizeof(T) == 2 && split) {
+    float h[V], l[V];
+    unpack<T>(hi, h);
+#pragma unroll
+    for (int j = 0; j < V; ++j) l[j] = fabsf(f[j]) > 65504.f ? 0.f : f[j] - h[j];
+    *reinterpret_cast<uint4*>(px + C + cv * V) = pack<T>(l);
+  }
+}
+
 // ---- 3x3/s2/p1 max pool (backbone.py:80).  Padding acts as -inf (PyTorch semantics). ----------
 template <typename T>
 __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W,
-                                    int C, int Ho, int Wo) {
+                                    int C, int Ho, int Wo, int split) {
   constexpr int V = DType<T>::kVec;
   const int CV = C / V;
+  const int PS = split ? 2 * C : C;   // elements per pixel
   const int64_t total = (int64_t)B * Ho * Wo * CV;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -72,14 +100,13 @@ __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, 
       for (int s = 0; s < 3; ++s) {
         int wi = wo * 2 - 1 + s;
         if (wi < 0 || wi >= W) continue;
-        uint4 raw = *reinterpret_cast<const uint4*>(x + (((int64_t)b * H + hi) * W + wi) * C + cv * V);
         float f[V];
-        unpack<T>(raw, f);
+        load_vec<T>(x + (((int64_t)b * H + hi) * W + wi) * PS, C, cv, split, f);
 #pragma unroll
         for (int j = 0; j < V; ++j) m[j] = fmaxf(m[j], f[j]);
       }
     }
-    *reinterpret_cast<uint4*>(y + (((int64_t)b * Ho + ho) * Wo + wo) * C + cv * V) = pack<T>(m);
+    store_vec<T>(y + (((int64_t)b * Ho + ho) * Wo + wo) * PS, C, cv, split, m);
   }
 }
 
@@ -89,9 +116,10 @@ __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, 
 template <typename T>
 __global__ void upsample_bilinear_kernel(const T* __restrict__ x, const T* __restrict__ add,
                                          T* __restrict__ y, int B, int H, int W, int C, int Ho,
-                                         int Wo, float scale_h, float scale_w, int relu) {
+                                         int Wo, float scale_h, float scale_w, int relu, int split) {
   constexpr int V = DType<T>::kVec;
   const int CV = C / V;
+  const int PS = split ? 2 * C : C;
   const int64_t total = (int64_t)B * Ho * Wo * CV;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -108,15 +136,15 @@ __global__ void upsample_bilinear_kernel(const T* __restrict__ x, const T* __res
     int w1 = w0 + (w0 < W - 1 ? 1 : 0);
     float l1h = sh - (float)h0, l1w = sw - (float)w0;
     float l0h = 1.f - l1h, l0w = 1.f - l1w;
-    const T* base = x + (int64_t)b * H * W * C + cv * V;
+    const T* base = x + (int64_t)b * H * W * PS;
     float p00[V], p01[V], p10[V], p11[V], o[V];
-    unpack<T>(*reinterpret_cast<const uint4*>(base + ((int64_t)h0 * W + w0) * C), p00);
-    unpack<T>(*reinterpret_cast<const uint4*>(base + ((int64_t)h0 * W + w1) * C), p01);
-    unpack<T>(*reinterpret_cast<const uint4*>(base + ((int64_t)h1 * W + w0) * C), p10);
-    unpack<T>(*reinterpret_cast<const uint4*>(base + ((int64_t)h1 * W + w1) * C), p11);
-    int64_t oidx = (((int64_t)b * Ho + ho) * Wo + wo) * C + cv * V;
+    load_vec<T>(base + ((int64_t)h0 * W + w0) * PS, C, cv, split, p00);
+    load_vec<T>(base + ((int64_t)h0 * W + w1) * PS, C, cv, split, p01);
+    load_vec<T>(base + ((int64_t)h1 * W + w0) * PS, C, cv, split, p10);
+    load_vec<T>(base + ((int64_t)h1 * W + w1) * PS, C, cv, split, p11);
+    const int64_t opix = (((int64_t)b * Ho + ho) * Wo + wo) * PS;
     float a[V];
-    if (add) unpack<T>(*reinterpret_cast<const uint4*>(add + oidx), a);
+    if (add) load_vec<T>(add + opix, C, cv, split, a);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       float top = __fadd_rn(__fmul_rn(l0w, p00[j]), __fmul_rn(l1w, p01[j]));
@@ -126,22 +154,28 @@ __global__ void upsample_bilinear_kernel(const T* __restrict__ x, const T* __res
       if (relu) v = fmaxf(v, 0.f);
       o[j] = v;
     }
-    *reinterpret_cast<uint4*>(y + oidx) = pack<T>(o);
+    store_vec<T>(y + opix, C, cv, split, o);
   }
 }
 
 // ---- layout conversion (tile transpose through shared memory) -----------------------------------
 // NHWC(T) [B, HW, C] -> NCHW fp32 [B, C, HW]
 template <typename T>
-__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int HW, int C) {
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int HW, int C, int split) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const T* xb = x + (int64_t)b * HW * C;
+  const int PS = split ? 2 * C : C;
+  const T* xb = x + (int64_t)b * HW * PS;
   float* yb_ = y + (int64_t)b * HW * C;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int p = p0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (p < HW && c < C) ? to_f32(xb[(int64_t)p * C + c]) : 0.f;
+    float v = 0.f;
+    if (p < HW && c < C) {
+      v = to_f32(xb[(int64_t)p * PS + c]);
+      if (split) v += to_f32(xb[(int64_t)p * PS + C + c]);
+    }
+    tile[i][threadIdx.x] = v;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -151,12 +185,13 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
 }
 // NCHW fp32 [B, C, HW] -> NHWC(T) [B, HW, C]
 template <typename T>
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int HW, int C) {
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int HW, int C, int split) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int PS = split ? 2 * C : C;
   const float* xb = x + (int64_t)b * HW * C;
-  T* yb_ = y + (int64_t)b * HW * C;
+  T* yb_ = y + (int64_t)b * HW * PS;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int c = c0 + i, p = p0 + threadIdx.x;
     tile[i][threadIdx.x] = (p < HW && c < C) ? xb[(int64_t)c * HW + p] : 0.f;
@@ -164,7 +199,12 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int p = p0 + i, c = c0 + threadIdx.x;
-    if (c < C && p < HW) yb_[(int64_t)p * C + c] = from_f32<T>(tile[threadIdx.x][i]);
+    if (c < C && p < HW) {
+      const float v = tile[threadIdx.x][i];
+      const T hi = from_f32<T>(v);
+      yb_[(int64_t)p * PS + c] = hi;
+      if (split) yb_[(int64_t)p * PS + C + c] = from_f32<T>(fabsf(v) > 65504.f ? 0.f : v - to_f32(hi));
+    }
   }
 }
 
@@ -203,63 +243,65 @@ inline int grid_for(int64_t total, int block) {
 
 template <typename T>
 void launch_maxpool3x3s2(const T* x, T* y, int B, int H, int W, int C, int Ho, int Wo,
-                         cudaStream_t stream, LaunchCounter* lc) {
+                         cudaStream_t stream, LaunchCounter* lc, int split) {
   YB_REQUIRE(C % DType<T>::kVec == 0, "maxpool: C must be a multiple of the vector width");
+  YB_REQUIRE(!split || sizeof(T) == 2, "split activations are fp16 pairs");
   int64_t total = (int64_t)B * Ho * Wo * (C / DType<T>::kVec);
-  maxpool3x3s2_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>(x, y, B, H, W, C, Ho, Wo);
+  maxpool3x3s2_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>(x, y, B, H, W, C, Ho, Wo, split);
   YB_CHECK_LAUNCH();
   if (lc) lc->n++;
 }
 template void launch_maxpool3x3s2<float>(const float*, float*, int, int, int, int, int, int,
-                                         cudaStream_t, LaunchCounter*);
+                                         cudaStream_t, LaunchCounter*, int);
 template void launch_maxpool3x3s2<__half>(const __half*, __half*, int, int, int, int, int, int,
-                                          cudaStream_t, LaunchCounter*);
+                                          cudaStream_t, LaunchCounter*, int);
 
 template <typename T>
 void launch_upsample_bilinear(const T* x, const T* add, T* y, int B, int H, int W, int C, int Ho,
                               int Wo, float scale_h, float scale_w, int relu, cudaStream_t stream,
-                              LaunchCounter* lc) {
+                              LaunchCounter* lc, int split) {
   YB_REQUIRE(C % DType<T>::kVec == 0, "upsample: C must be a multiple of the vector width");
+  YB_REQUIRE(!split || sizeof(T) == 2, "split activations are fp16 pairs");
   int64_t total = (int64_t)B * Ho * Wo * (C / DType<T>::kVec);
   upsample_bilinear_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>(x, add, y, B, H, W, C, Ho, Wo,
-                                                                       scale_h, scale_w, relu);
+                                                                       scale_h, scale_w, relu, split);
   YB_CHECK_LAUNCH();
   if (lc) lc->n++;
 }
 template void launch_upsample_bilinear<float>(const float*, const float*, float*, int, int, int, int,
                                               int, int, float, float, int, cudaStream_t,
-                                              LaunchCounter*);
+                                              LaunchCounter*, int);
 template void launch_upsample_bilinear<__half>(const __half*, const __half*, __half*, int, int, int,
                                                int, int, int, float, float, int, cudaStream_t,
-                                               LaunchCounter*);
+                                               LaunchCounter*, int);
 
 template <typename T>
 void launch_nhwc_to_nchw_f32(const T* x, float* y, int B, int H, int W, int C, cudaStream_t stream,
-                             LaunchCounter* lc) {
+                             LaunchCounter* lc, int split) {
   int HW = H * W;
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B), block(32, 8);
-  nhwc_to_nchw_kernel<T><<<grid, block, 0, stream>>>(x, y, HW, C);
+  nhwc_to_nchw_kernel<T><<<grid, block, 0, stream>>>(x, y, HW, C, split);
   YB_CHECK_LAUNCH();
   if (lc) lc->n++;
 }
 template void launch_nhwc_to_nchw_f32<float>(const float*, float*, int, int, int, int, cudaStream_t,
-                                             LaunchCounter*);
+                                             LaunchCounter*, int);
 template void launch_nhwc_to_nchw_f32<__half>(const __half*, float*, int, int, int, int,
-                                              cudaStream_t, LaunchCounter*);
+                                              cudaStream_t, LaunchCounter*, int);
 
 template <typename T>
 void launch_nchw_f32_to_nhwc(const float* x, T* y, int B, int C, int H, int W, cudaStream_t stream,
-                             LaunchCounter* lc) {
+                             LaunchCounter* lc, int split) {
   int HW = H * W;
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B), block(32, 8);
-  nchw_to_nhwc_kernel<T><<<grid, block, 0, stream>>>(x, y, HW, C);
+  nchw_to_nhwc_kernel<T><<<grid, block, 0, stream>>>(x, y, HW, C, split);
   YB_CHECK_LAUNCH();
   if (lc) lc->n++;
 }
 template void launch_nchw_f32_to_nhwc<float>(const float*, float*, int, int, int, int, cudaStream_t,
-                                             LaunchCounter*);
+                                             LaunchCounter*, int);
 template void launch_nchw_f32_to_nhwc<__half>(const float*, __half*, int, int, int, int,
-                                              cudaStream_t, LaunchCounter*);
+                                              cudaStream_t, LaunchCounter*, int);
 
 void launch_softmax_rows(const float* in, float* out, int64_t rows, int cols, cudaStream_t stream,
                          LaunchCounter* lc) {

@@ -32,15 +32,19 @@ struct alignas(64) StemParams {
   long long M;
   uint32_t idesc;
   int act;
+  float out_scale;   // split: weights are pre-multiplied by 1 / out_scale (a power of two)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int KS, int STRIDE, int PAD, int COUT, int WG>
+// SPLIT (YB_PREC_F16X3): the patch is written as a hi and a lo fp16 tile, the weights come as [Cout][hi(Kpad) | lo(Kpad)],
+// three MMA passes (hi*hi + lo*hi + hi*lo) accumulate in one fp32 tile and the output pixel is [hi(COUT) | lo(COUT)].
+template <int KS, int STRIDE, int PAD, int COUT, int WG, bool SPLIT>
 __global__ void __launch_bounds__(128 * WG + 32)
 stem_tc_kernel(const __grid_constant__ StemParams p) {
+  constexpr int NPL = SPLIT ? 2 : 1;
   constexpr int MMA_WARP = 4 * WG;
   constexpr int K = 3 * KS * KS;
   constexpr int ATOMS = (K + 63) / 64;
@@ -52,8 +56,8 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
   __shared__ uint64_t a_full, b_full, tmem_full;
   __shared__ uint32_t s_tmem;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + ATOMS * A_ATOM_BYTES;
+  uint8_t* sA = smem;                               // [plane][atom]
+  uint8_t* sB = smem + NPL * ATOMS * A_ATOM_BYTES;  // [plane][atom]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -71,17 +75,23 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
 
   if (warp == MMA_WARP) {
     if (lane == 0) {
-      mbar_expect_tx(&b_full, ATOMS * B_ATOM_BYTES);
-      for (int a = 0; a < ATOMS; ++a) tma_load_3d(sB + a * B_ATOM_BYTES, &p.tmW, &b_full, a * 64, 0, 0);
+      mbar_expect_tx(&b_full, NPL * ATOMS * B_ATOM_BYTES);
+      for (int pl = 0; pl < NPL; ++pl)
+        for (int a = 0; a < ATOMS; ++a)
+          tma_load_3d(sB + (pl * ATOMS + a) * B_ATOM_BYTES, &p.tmW, &b_full, pl * ATOMS * 64 + a * 64, 0, 0);
       mbar_wait(&b_full, 0);
       mbar_wait(&a_full, 0);
       tc_fence_after();
 #pragma unroll
-      for (int j = 0; j < KSTEPS; ++j) {
-        const int atom = j >> 2, kk = j & 3;
-        const uint64_t da = make_sw128_desc(smem_u32(sA + atom * A_ATOM_BYTES)) + (uint64_t)(2 * kk);
-        const uint64_t db = make_sw128_desc(smem_u32(sB + atom * B_ATOM_BYTES)) + (uint64_t)(2 * kk);
-        umma_f16(tmem_base, da, db, p.idesc, j > 0 ? 1u : 0u);
+      for (int pass = 0; pass < (SPLIT ? 3 : 1); ++pass) {
+        const int pa = (pass == 1) ? 1 : 0, pb = (pass == 2) ? 1 : 0;   // hi*hi, lo*hi, hi*lo
+#pragma unroll
+        for (int j = 0; j < KSTEPS; ++j) {
+          const int atom = j >> 2, kk = j & 3;
+          const uint64_t da = make_sw128_desc(smem_u32(sA + (pa * ATOMS + atom) * A_ATOM_BYTES)) + (uint64_t)(2 * kk);
+          const uint64_t db = make_sw128_desc(smem_u32(sB + (pb * ATOMS + atom) * B_ATOM_BYTES)) + (uint64_t)(2 * kk);
+          umma_f16(tmem_base, da, db, p.idesc, (pass > 0 || j > 0) ? 1u : 0u);
+        }
       }
       umma_commit(&tmem_full);
     }
@@ -110,8 +120,9 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
 #pragma unroll
     for (int kg = 0; kg < ATOMS * 8; ++kg) {
       if (WG > 1 && (kg % WG) != wg) continue;   // warp-uniform
-      uint4 pk;
+      uint4 pk, pkl;
       __half2* h2 = reinterpret_cast<__half2*>(&pk);
+      __half2* l2 = reinterpret_cast<__half2*>(&pkl);
 #pragma unroll
       for (int j2 = 0; j2 < 4; ++j2) {
         float v[2];
@@ -126,9 +137,15 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
           v[e] = val;
         }
         h2[j2] = __halves2half2(from_f32<__half>(v[0]), from_f32<__half>(v[1]));
+        if (SPLIT) {
+          const float2 hf = __half22float2(h2[j2]);
+          l2[j2] = __floats2half2_rn(fabsf(v[0]) > 65504.f ? 0.f : v[0] - hf.x, fabsf(v[1]) > 65504.f ? 0.f : v[1] - hf.y);
+        }
       }
       const int atom = kg >> 3;
-      *reinterpret_cast<uint4*>(sA + atom * A_ATOM_BYTES + row * 128 + ((((uint32_t)kg & 7u) ^ sw) << 4)) = pk;
+      const uint32_t aoff = row * 128 + ((((uint32_t)kg & 7u) ^ sw) << 4);
+      *reinterpret_cast<uint4*>(sA + atom * A_ATOM_BYTES + aoff) = pk;
+      if (SPLIT) *reinterpret_cast<uint4*>(sA + (ATOMS + atom) * A_ATOM_BYTES + aoff) = pkl;
     }
     fence_proxy_async();   // generic-proxy smem writes -> visible to tcgen05.mma (async proxy)
     mbar_arrive(&a_full);
@@ -136,7 +153,7 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
     // ---- epilogue: one accumulator row per thread -> bias -> activation -> one contiguous line
     mbar_wait(&tmem_full, 0);
     tc_fence_after();
-    __half* yrow = p.y + m * COUT;
+    __half* yrow = p.y + m * (COUT * NPL);
 #pragma unroll
     for (int c0 = 0; c0 < COUT; c0 += 32) {
       if (WG > 1 && ((c0 >> 5) % WG) != wg) continue;   // warp-uniform
@@ -145,16 +162,27 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
       if (!valid) continue;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint4 o;
+        uint4 o, ol;
         __half2* o2 = reinterpret_cast<__half2*>(&o);
+        __half2* ol2 = reinterpret_cast<__half2*>(&ol);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int col = c0 + q * 8 + 2 * j;
-          float v0 = __uint_as_float(r[q * 8 + 2 * j]) + (p.bias ? __ldg(p.bias + col) : 0.f);
-          float v1 = __uint_as_float(r[q * 8 + 2 * j + 1]) + (p.bias ? __ldg(p.bias + col + 1) : 0.f);
-          o2[j] = __halves2half2(from_f32<__half>(apply_act(v0, p.act)), from_f32<__half>(apply_act(v1, p.act)));
+          float v0 = __uint_as_float(r[q * 8 + 2 * j]), v1 = __uint_as_float(r[q * 8 + 2 * j + 1]);
+          if (SPLIT) {
+            v0 *= p.out_scale;
+            v1 *= p.out_scale;
+          }
+          v0 = apply_act(v0 + (p.bias ? __ldg(p.bias + col) : 0.f), p.act);
+          v1 = apply_act(v1 + (p.bias ? __ldg(p.bias + col + 1) : 0.f), p.act);
+          o2[j] = __halves2half2(from_f32<__half>(v0), from_f32<__half>(v1));
+          if (SPLIT) {
+            const float2 hf = __half22float2(o2[j]);
+            ol2[j] = __floats2half2_rn(fabsf(v0) > 65504.f ? 0.f : v0 - hf.x, fabsf(v1) > 65504.f ? 0.f : v1 - hf.y);
+          }
         }
         reinterpret_cast<uint4*>(yrow + c0)[q] = o;
+        if (SPLIT) reinterpret_cast<uint4*>(yrow + COUT + c0)[q] = ol;
       }
     }
   }
@@ -166,17 +194,17 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
   }
 }
 
-template <int KS, int STRIDE, int PAD, int COUT, int WG>
+template <int KS, int STRIDE, int PAD, int COUT, int WG, bool SPLIT>
 void launch_variant(const StemParams& prm, cudaStream_t stream) {
   constexpr int K = 3 * KS * KS;
   constexpr int ATOMS = (K + 63) / 64;
-  const size_t smem = (size_t)ATOMS * (ST_M * 128 + COUT * 128) + 1024;
+  const size_t smem = (size_t)(SPLIT ? 2 : 1) * ATOMS * (ST_M * 128 + COUT * 128) + 1024;
   static PerDeviceOnce attr;
   if (attr.first())
-    YB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<KS, STRIDE, PAD, COUT, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    YB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<KS, STRIDE, PAD, COUT, WG, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
   const unsigned grid = (unsigned)((prm.M + ST_M - 1) / ST_M);
-  stem_tc_kernel<KS, STRIDE, PAD, COUT, WG><<<grid, 128 * WG + 32, smem, stream>>>(prm);
+  stem_tc_kernel<KS, STRIDE, PAD, COUT, WG, SPLIT><<<grid, 128 * WG + 32, smem, stream>>>(prm);
 }
 
 }  // namespace
@@ -185,6 +213,7 @@ struct StemTcPlan {
   StemParams prm;
   int ks, stride, pad, cout;
   int wg = 1;   // worker groups (7x7 stem only)
+  int split = 0;
 };
 
 bool stem_tc_supported(int ks, int stride, int pad, int cin, int cout) {
@@ -194,7 +223,7 @@ bool stem_tc_supported(int ks, int stride, int pad, int cin, int cout) {
 int stem_tc_kpad(int ks) { return ((3 * ks * ks + 63) / 64) * 64; }
 
 StemTcPlan* stem_tc_plan_create(const float* x_nchw, const __half* w_packed, const float* bias, __half* y, int B, int H,
-                                int W, int ks, int stride, int pad, int cout, int act) {
+                                int W, int ks, int stride, int pad, int cout, int act, int split, float out_scale) {
   YB_REQUIRE(stem_tc_supported(ks, stride, pad, 3, cout), "stem_tc: unsupported stem shape");
   auto* plan = new StemTcPlan();
   StemParams& q = plan->prm;
@@ -213,10 +242,13 @@ StemTcPlan* stem_tc_plan_create(const float* x_nchw, const __half* w_packed, con
   q.Wo = (W + 2 * pad - ks) / stride + 1;
   q.M = (long long)B * q.Ho * q.Wo;
   q.act = act;
+  q.out_scale = split ? out_scale : 1.f;
+  plan->split = split ? 1 : 0;
   q.idesc = (1u << 4) | ((uint32_t)(cout >> 3) << 17) | ((uint32_t)(ST_M >> 4) << 24);
   const int kpad = stem_tc_kpad(ks);
-  uint64_t dims[3] = {(uint64_t)kpad, (uint64_t)cout, 1};
-  uint64_t str[2] = {(uint64_t)kpad * 2, (uint64_t)kpad * cout * 2};
+  const uint64_t kp = (uint64_t)kpad * (split ? 2 : 1);   // [cout][hi(kpad) | lo(kpad)]
+  uint64_t dims[3] = {kp, (uint64_t)cout, 1};
+  uint64_t str[2] = {kp * 2, kp * cout * 2};
   uint32_t box[3] = {64, (uint32_t)cout, 1};
   encode_map_f16(&q.tmW, w_packed, 3, dims, str, box);
   return plan;
@@ -226,13 +258,18 @@ void stem_tc_plan_destroy(StemTcPlan* plan) { delete plan; }
 void stem_tc_plan_set_worker_groups(StemTcPlan* plan, int wg) { plan->wg = (wg == 2 && plan->ks == 7) ? 2 : 1; }
 
 void launch_stem_tc(const StemTcPlan* plan, cudaStream_t stream, LaunchCounter* lc) {
-  if (plan->ks == 7) {
-    if (plan->wg == 2)
-      launch_variant<7, 2, 3, 64, 2>(plan->prm, stream);
+  if (plan->split) {
+    if (plan->ks == 7)
+      launch_variant<7, 2, 3, 64, 1, true>(plan->prm, stream);
     else
-      launch_variant<7, 2, 3, 64, 1>(plan->prm, stream);
+      launch_variant<3, 1, 1, 32, 1, true>(plan->prm, stream);
+  } else if (plan->ks == 7) {
+    if (plan->wg == 2)
+      launch_variant<7, 2, 3, 64, 2, false>(plan->prm, stream);
+    else
+      launch_variant<7, 2, 3, 64, 1, false>(plan->prm, stream);
   } else {
-    launch_variant<3, 1, 1, 32, 1>(plan->prm, stream);
+    launch_variant<3, 1, 1, 32, 1, false>(plan->prm, stream);
   }
   YB_CHECK_LAUNCH();
   if (lc) lc->n++;

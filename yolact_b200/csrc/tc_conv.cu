@@ -75,6 +75,11 @@ struct alignas(64) TcParams {
   int act;
   int vec_ok;
   int res_after_act;
+  // split precision (SPLIT kernels): activations are [hi(C) | lo(C)] fp16 pairs per pixel, weights [.. hi(Cin) | lo(Cin)]
+  // scaled by a power of two; the accumulator is multiplied by out_scale (its exact inverse) before the bias
+  int split;
+  int cin;              // logical input channels: the lo plane starts at channel `cin` of the A / B tensor maps
+  float out_scale;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -126,11 +131,13 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// One 64-channel chunk of one accumulator row: +bias (smem, broadcast), +residual (swizzled smem tile),
-// activation, fp16 pack, swizzled 16-byte stores into the output staging tile.
-template <int ACT, bool RES_AFTER>
+// One 64-channel chunk of one accumulator row: (* out_scale) +bias (smem, broadcast), +residual (swizzled smem
+// tile), activation, fp16 pack, swizzled 16-byte stores into the output staging tile.  SPLIT: the residual is
+// hi + lo from two tiles and the result is written as hi / lo = rn(v - hi) into two staging tiles.
+template <int ACT, bool RES_AFTER, bool SPLIT>
 __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1, const float* sbias,
-                                          const uint8_t* res_tile, uint8_t* out_tile, uint32_t row, uint32_t sw) {
+                                          const uint8_t* res_tile, uint8_t* out_tile, uint32_t row, uint32_t sw,
+                                          float out_scale) {
 #pragma unroll
   for (int j8 = 0; j8 < 8; ++j8) {
     const float4 b0 = *reinterpret_cast<const float4*>(sbias + j8 * 8);
@@ -140,7 +147,8 @@ __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int col = j8 * 8 + j;
-      v[j] = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + bb[j];
+      const float a = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]);
+      v[j] = SPLIT ? __fmaf_rn(a, out_scale, bb[j]) : a + bb[j];
       if (RES_AFTER) v[j] = act_t<ACT>(v[j]);
     }
     const uint32_t off = row * 128u + (((uint32_t)j8 ^ sw) << 4);
@@ -153,6 +161,16 @@ __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1
         v[2 * j] += f.x;
         v[2 * j + 1] += f.y;
       }
+      if (SPLIT) {
+        const uint4 rawl = *reinterpret_cast<const uint4*>(res_tile + A_STAGE_BYTES + off);
+        const __half2* l2 = reinterpret_cast<const __half2*>(&rawl);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(l2[j]);
+          v[2 * j] += f.x;
+          v[2 * j + 1] += f.y;
+        }
+      }
     }
     if (!RES_AFTER) {
 #pragma unroll
@@ -163,6 +181,19 @@ __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1
 #pragma unroll
     for (int j = 0; j < 4; ++j) o2[j] = pack_sat(v[2 * j], v[2 * j + 1]);
     *reinterpret_cast<uint4*>(out_tile + off) = o;
+    if (SPLIT) {
+      uint4 ol;
+      __half2* l2 = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 hf = __half22float2(o2[j]);
+        // hi saturates at +-65504; the residual of a saturated value is dropped (lo = 0 keeps hi + lo finite)
+        const float l0 = fabsf(v[2 * j]) > 65504.f ? 0.f : v[2 * j] - hf.x;
+        const float l1 = fabsf(v[2 * j + 1]) > 65504.f ? 0.f : v[2 * j + 1] - hf.y;
+        l2[j] = __floats2half2_rn(l0, l1);
+      }
+      *reinterpret_cast<uint4*>(out_tile + A_STAGE_BYTES + off) = ol;
+    }
   }
 }
 
@@ -190,11 +221,16 @@ __device__ __forceinline__ TileCoord decode_unit(const TcParams& p, int u, int r
   return decode_mn(p, PAIR ? 2 * mg + rank : mg, nt, BN);
 }
 
-template <int BN, bool PAIR, int H>
+template <int BN, bool PAIR, int H, bool SPLIT>
 __global__ void __launch_bounds__(64 + 128 * H)
 tc_conv_kernel(const __grid_constant__ TcParams p) {
-  constexpr int B_STAGE_BYTES = (PAIR ? BN / 2 : BN) * BLOCK_K * 2;   // a pair CTA stages half of the weight tile
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  // SPLIT (YB_PREC_F16X3): every operand has a hi and a lo fp16 plane; a k-block stages A_hi, A_lo, W_hi, W_lo and
+  // issues A_hi*W_hi + A_lo*W_hi + A_hi*W_lo into ONE fp32 accumulator (the lo*lo term is below fp32 resolution).
+  constexpr int NPL = SPLIT ? 2 : 1;
+  constexpr int B_PLANE_BYTES = (PAIR ? BN / 2 : BN) * BLOCK_K * 2;   // a pair CTA stages half of the weight tile
+  constexpr int A_BYTES = NPL * A_STAGE_BYTES;
+  constexpr int B_STAGE_BYTES = NPL * B_PLANE_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
 
   extern __shared__ uint8_t smem_dyn[];
   __shared__ uint64_t full_bar[MAX_STAGES];
@@ -207,8 +243,8 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 
   // 1024-byte alignment required by SWIZZLE_128B (host adds 1024 bytes of slack)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  uint8_t* out_base = smem + p.out_off;   // 2 x 16 KB epilogue staging tiles
-  uint8_t* res_base = smem + p.res_off;   // 2 x 16 KB residual tiles (only when residual && epi_tma)
+  uint8_t* out_base = smem + p.out_off;   // epilogue staging tiles: [buffer][plane] x 16 KB
+  uint8_t* res_base = smem + p.res_off;   // residual tiles, same layout (only when residual && epi_tma)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -249,14 +285,14 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   uint32_t pre = 0;   // producer thread only: k-blocks whose weight tile is already in flight
   if (p.pdl) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (!PAIR && warp == 0 && lane == 0 && unit0 < num_units) {
+    if (!PAIR && !SPLIT && warp == 0 && lane == 0 && unit0 < num_units) {
       const TileCoord t0 = decode_unit<PAIR>(p, unit0, rank, BN);
       const int npre = min(stages, num_kb);
       for (int kb = 0; kb < npre; ++kb) {
         const int tap = kb / p.kchunks;
         const int kc = kb - tap * p.kchunks;
         mbar_expect_tx(&full_bar[kb], (uint32_t)p.a_box_bytes + (uint32_t)B_STAGE_BYTES);
-        tma_load_3d(smem + (size_t)kb * STAGE_BYTES + A_STAGE_BYTES, &p.tmB, &full_bar[kb], kc * BLOCK_K, t0.n0, tap);
+        tma_load_3d(smem + (size_t)kb * STAGE_BYTES + A_BYTES, &p.tmB, &full_bar[kb], kc * BLOCK_K, t0.n0, tap);
       }
       pre = (uint32_t)npre;
     }
@@ -266,8 +302,8 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      // a pair's leader expects the bytes of BOTH CTAs (each: its A tile + its half of the weight tile)
-      const uint32_t tx_bytes = ((uint32_t)p.a_box_bytes + (uint32_t)B_STAGE_BYTES) * (PAIR ? 2u : 1u);
+      // a pair's leader expects the bytes of BOTH CTAs (each: its A tile + its half of the weight tile, per plane)
+      const uint32_t tx_bytes = ((uint32_t)p.a_box_bytes + (uint32_t)B_PLANE_BYTES) * (uint32_t)NPL * (PAIR ? 2u : 1u);
       const uint32_t leader_full = PAIR ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0u;
       uint32_t kbg = 0;
       for (int u = unit0; u < num_units; u += ustep) {
@@ -279,22 +315,27 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           const int tap = kb / p.kchunks;
           const int kc = kb - tap * p.kchunks;
           uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
-          uint8_t* sb = sa + A_STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          const CUtensorMap* ma = &p.tmA[p.tap_map[tap]];
+          const int ax = tc_.x0 + p.tap_dx[tap], ay = tc_.y0 + p.tap_dy[tap];
           if (PAIR) {
             if (rank == 0) mbar_expect_tx(&full_bar[s], tx_bytes);
             const uint32_t fb = leader_full + s * (uint32_t)sizeof(uint64_t);
-            tma_load_4d_pair(sa, &p.tmA[p.tap_map[tap]], fb, kc * BLOCK_K, tc_.x0 + p.tap_dx[tap],
-                             tc_.y0 + p.tap_dy[tap], tc_.b);
-            tma_load_3d_pair(sb, &p.tmB, fb, kc * BLOCK_K, tc_.n0 + rank * (BN / 2), tap);
-          } else if (kbg < pre) {
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl) {
+              tma_load_4d_pair(sa + pl * A_STAGE_BYTES, ma, fb, kc * BLOCK_K + pl * p.cin, ax, ay, tc_.b);
+              tma_load_3d_pair(sb + pl * B_PLANE_BYTES, &p.tmB, fb, kc * BLOCK_K + pl * p.cin, tc_.n0 + rank * (BN / 2), tap);
+            }
+          } else if (!SPLIT && kbg < pre) {
             // PDL: this stage was armed and its weight tile requested before the dependency wait
-            tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[s], kc * BLOCK_K, tc_.x0 + p.tap_dx[tap],
-                        tc_.y0 + p.tap_dy[tap], tc_.b);
+            tma_load_4d(sa, ma, &full_bar[s], kc * BLOCK_K, ax, ay, tc_.b);
           } else {
             mbar_expect_tx(&full_bar[s], tx_bytes);
-            tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[s], kc * BLOCK_K, tc_.x0 + p.tap_dx[tap],
-                        tc_.y0 + p.tap_dy[tap], tc_.b);
-            tma_load_3d(sb, &p.tmB, &full_bar[s], kc * BLOCK_K, tc_.n0, tap);
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl) {
+              tma_load_4d(sa + pl * A_STAGE_BYTES, ma, &full_bar[s], kc * BLOCK_K + pl * p.cin, ax, ay, tc_.b);
+              tma_load_3d(sb + pl * B_PLANE_BYTES, &p.tmB, &full_bar[s], kc * BLOCK_K + pl * p.cin, tc_.n0, tap);
+            }
           }
         }
       }
@@ -315,16 +356,24 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           mbar_wait(&full_bar[s], it & 1u);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
           const uint64_t da = make_sw128_desc(sa);
           const uint64_t db = make_sw128_desc(sb);
+          auto mma = [&](uint64_t a, uint64_t b, uint32_t accum) {
+            if (PAIR) umma_f16_pair(tmem_d, a, b, p.idesc, accum); else umma_f16(tmem_d, a, b, p.idesc, accum);
+          };
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 field
-            if (PAIR)
-              umma_f16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            else
-              umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            mma(da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          if (SPLIT) {
+            const uint64_t dal = make_sw128_desc(sa + A_STAGE_BYTES);
+            const uint64_t dbl = make_sw128_desc(sb + B_PLANE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) mma(dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), 1u);   // A_lo * W_hi
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) mma(da + (uint64_t)(2 * k), dbl + (uint64_t)(2 * k), 1u);   // A_hi * W_lo
           }
           // frees this smem slot (in both CTAs of a pair) once the MMAs above have read it
           if (PAIR) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
@@ -346,7 +395,8 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
     const bool has_res = (p.residual != nullptr);
     const uint32_t sw = (uint32_t)(row & 7);
     float* my_bias = sbias + hgrp * BN;
-    constexpr int NBUF = (H == 2) ? 1 : 2;                    // staging / residual tiles per group
+    constexpr int NBUF = (H == 2 || SPLIT) ? 1 : 2;           // staging / residual buffers per group (a buffer = NPL tiles)
+    constexpr int BUF_BYTES = NPL * A_STAGE_BYTES;
     auto group_sync = [&]() {                                 // the 128 threads of this group
       if (hgrp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
       else asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -373,9 +423,12 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           pf_tile += ustep;
           continue;
         }
-        const uint32_t buf = (H == 2) ? (uint32_t)hgrp : (pf_g & 1u);
-        mbar_expect_tx(&res_full_bar[buf], (uint32_t)p.a_box_bytes);
-        tma_load_4d(res_base + buf * A_STAGE_BYTES, &p.tmR, &res_full_bar[buf], tcp.n0 + pf_c * 64, tcp.x0, tcp.y0, tcp.b);
+        const uint32_t buf = (NBUF == 1) ? (uint32_t)hgrp : (pf_g & 1u);
+        mbar_expect_tx(&res_full_bar[buf], (uint32_t)p.a_box_bytes * (uint32_t)NPL);
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl)
+          tma_load_4d(res_base + buf * BUF_BYTES + pl * A_STAGE_BYTES, &p.tmR, &res_full_bar[buf],
+                      tcp.n0 + pf_c * 64 + pl * p.Cout, tcp.x0, tcp.y0, tcp.b);
         ++pf_g;
         pf_c += H;
         return;
@@ -412,9 +465,9 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
         }
 #pragma unroll 1
         for (int c = hgrp; c < nchunks; c += H, ++g) {
-          const uint32_t buf = (H == 2) ? (uint32_t)hgrp : (g & 1u);
-          uint8_t* out_tile = out_base + buf * A_STAGE_BYTES;
-          uint8_t* res_tile = res_base + buf * A_STAGE_BYTES;
+          const uint32_t buf = (NBUF == 1) ? (uint32_t)hgrp : (g & 1u);
+          uint8_t* out_tile = out_base + buf * BUF_BYTES;
+          uint8_t* res_tile = res_base + buf * BUF_BYTES;
           if (g >= (uint32_t)NBUF) {
             if (issuer) bulk_wait_read<NBUF - 1>();  // the store that last used this staging tile has read it
             group_sync();
@@ -423,20 +476,20 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           tmem_ld32_nowait(tmem_acc + (uint32_t)(c * 64), r0);
           tmem_ld32_nowait(tmem_acc + (uint32_t)(c * 64 + 32), r1);
           tmem_ld_wait();
-          if (has_res) mbar_wait(&res_full_bar[buf], (H == 2) ? (g & 1u) : ((g >> 1) & 1u));
+          if (has_res) mbar_wait(&res_full_bar[buf], (NBUF == 1) ? (g & 1u) : ((g >> 1) & 1u));
           const int nbase = n0 + c * 64;
           const float* sb = my_bias + c * 64;
           const uint8_t* rt = has_res ? res_tile : nullptr;
           switch (p.act) {
-            case ACT_RELU: epi_chunk<ACT_RELU, false>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw); break;
+            case ACT_RELU: epi_chunk<ACT_RELU, false, SPLIT>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw, p.out_scale); break;
             case ACT_LEAKY:
               if (p.res_after_act)
-                epi_chunk<ACT_LEAKY, true>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw);
+                epi_chunk<ACT_LEAKY, true, SPLIT>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw, p.out_scale);
               else
-                epi_chunk<ACT_LEAKY, false>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw);
+                epi_chunk<ACT_LEAKY, false, SPLIT>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw, p.out_scale);
               break;
-            case ACT_TANH: epi_chunk<ACT_TANH, false>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw); break;
-            default: epi_chunk<ACT_NONE, false>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw); break;
+            case ACT_TANH: epi_chunk<ACT_TANH, false, SPLIT>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw, p.out_scale); break;
+            default: epi_chunk<ACT_NONE, false, SPLIT>(r0, r1, sb, rt, out_tile, (uint32_t)row, sw, p.out_scale); break;
           }
           fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
           if (c == c_last) tc_fence_before();
@@ -444,6 +497,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           if (issuer) {
             if (c == c_last) release_acc(acc);  // all 128 threads of the group have read their rows
             tma_store_4d(&p.tmY, out_tile, nbase, x0, y0, b);
+            if (SPLIT) tma_store_4d(&p.tmY, out_tile + A_STAGE_BYTES, nbase + p.Cout, x0, y0, b);
             bulk_commit();
             if (has_res) prefetch_res();   // the group is done reading res_tile[buf]: refill it
           }
@@ -490,8 +544,13 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             if (trow >= p.tw * p.th || oy >= p.Ho || ox >= p.Wo || b >= p.nb) continue;   // warp-uniform
             if (lane >= nvalid) continue;
             const long long pix = (long long)oy * p.Wo + ox;
-            float v = tbuf[rr * 33 + lane] + bias_l;
-            const float rsd = has_res ? __half2float(p.residual[(long long)b * p.res_batch_stride + pix * p.Cout + nbase + lane]) : 0.f;
+            float v = SPLIT ? __fmaf_rn(tbuf[rr * 33 + lane], p.out_scale, bias_l) : tbuf[rr * 33 + lane] + bias_l;
+            float rsd = 0.f;
+            if (has_res) {
+              const __half* rp = p.residual + ((long long)b * p.res_batch_stride + pix * p.Cout) * NPL + nbase + lane;
+              rsd = __half2float(rp[0]);
+              if (SPLIT) rsd += __half2float(rp[p.Cout]);
+            }
             if (!raa) v += rsd;
             v = (act == ACT_RELU) ? fmaxf(v, 0.f) : (act == ACT_TANH) ? tanhf(v) : (act == ACT_LEAKY) ? (v > 0.f ? v : 0.1f * v) : v;
             if (raa) v += rsd;
@@ -500,10 +559,16 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
               continue;
             }
             const long long o = (long long)b * p.y_batch_stride + pix * p.y_pix_stride + nbase + lane;
-            if (p.y_f32)
+            if (p.y_f32) {
               reinterpret_cast<float*>(p.y)[o] = v;
-            else
+            } else if (SPLIT) {   // y_pix_stride counts halfs and already includes both planes
+              __half hi, lo;
+              split_f32(v, hi, lo);
+              reinterpret_cast<__half*>(p.y)[o] = hi;
+              reinterpret_cast<__half*>(p.y)[o + p.Cout] = lo;
+            } else {
               reinterpret_cast<__half*>(p.y)[o] = from_f32<__half>(v);
+            }
           }
         }
         tc_fence_before();
@@ -577,6 +642,7 @@ void tc::encode_map_f16(CUtensorMap* map, const void* base, int rank, const uint
 
 struct TcConvPlan {
   TcParams prm;
+  int split = 0;
   int BN = 128;
   int pair = 0;
   int epi_groups = 1;   // H: 4-warp epilogue groups per CTA
@@ -605,9 +671,16 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   const int s = p.stride;
   q.ntaps = p.KH * p.KW;
   q.kchunks = p.Cin / BLOCK_K;
+  const int split = p.split ? 1 : 0;
+  const int npl = split ? 2 : 1;       // fp16 planes per operand / activation
+  plan->split = split;
+  q.split = split;
+  q.cin = p.Cin;
+  q.out_scale = split ? p.out_scale : 1.f;
 
   // ---- geometry: can the whole problem be flattened into one pixel axis? (1x1, stride 1, dense out)
   const bool dense_out = (p.y_batch_stride == (int64_t)p.Ho * p.Wo * p.y_pix_stride);
+  YB_REQUIRE(!split || p.y_f32 || p.nseg > 0 || p.y_pix_stride >= 2 * p.Cout, "tc_conv: split outputs need 2*Cout halfs per pixel");
   const bool flat = (q.ntaps == 1 && s == 1 && p.pad == 0 && dense_out);
   int Bv = p.B, Hov = p.Ho, Wov = p.Wo;
   if (flat) {
@@ -648,6 +721,8 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   if (p.residual) vec_ok = vec_ok && (p.Cout % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
   q.vec_ok = vec_ok ? 1 : 0;
   q.epi_tma = (!p.y_f32 && vec_ok && p.Cout % 8 == 0 && p.nseg == 0) ? 1 : 0;
+  // split: a 64-channel hi box must not run into the lo plane of the same pixel (nothing clips it there)
+  if (split && q.epi_tma && p.Cout % 64 != 0) q.epi_tma = 0;
   // the staged epilogue moves 64-channel boxes: a CTA must own at least 64 output channels
   const int bn_min = q.epi_tma ? 64 : 32;
 
@@ -678,7 +753,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   plan->pair = pair;
   q.pair = pair;
   q.nb = Bv;
-  const int stage_bytes = A_STAGE_BYTES + (pair ? BN / 2 : BN) * BLOCK_K * 2;
+  const int stage_bytes = npl * (A_STAGE_BYTES + (pair ? BN / 2 : BN) * BLOCK_K * 2);
   // ---- persistent grid + shared-memory layout: [pipeline stages][2 x 16 KB out tiles][2 x 16 KB residual tiles]
   q.m_tiles = (int)m_tiles;
   q.n_tiles = ceil_div(p.Cout, BN);
@@ -696,7 +771,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   // two epilogue groups (8 warps) work on two 64-channel chunks at once; pointless for a single-chunk tile
   // PDL-friendly plan: <= ~108 KB of shared memory, one epilogue group (192 threads x 122 registers) and <= 256 TMEM
   // columns, so a CTA of the NEXT layer can become resident beside it and overlap its prologue + first weight tiles
-  const int pdlf = (pdl_override > 0 && !pair) ? 1 : 0;
+  const int pdlf = (pdl_override > 0 && !pair && !split) ? 1 : 0;
   plan->pdl_friendly = pdlf;
   if (pdlf && q.acc_stages * BN > 256) q.acc_stages = 1;
   if (pdlf) {
@@ -707,9 +782,12 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   plan->epi_groups = (epi_override == 2 && BN >= 64 && !pdlf) ? 2 : 1;
   // staging: 2 x 16 KB tiles (one per group when there are two); the direct (fp32) epilogue needs a padded
   // 32x33 float transpose buffer per epilogue warp
-  const int out_bytes = plan->epi_groups == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES;
-  const int res_bytes = (q.epi_tma && p.residual) ? 2 * A_STAGE_BYTES : 0;
-  int stages = std::min(MAX_STAGES, ((pdlf ? 108 : 200) * 1024 - out_bytes - res_bytes) / stage_bytes);
+  // (split: one buffer of two tiles per group)
+  const int epi_tiles = split ? 2 * plan->epi_groups : 2;
+  const int out_bytes = std::max(epi_tiles * A_STAGE_BYTES, plan->epi_groups == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES);
+  const int res_bytes = (q.epi_tma && p.residual) ? epi_tiles * A_STAGE_BYTES : 0;
+  int stages = std::min(MAX_STAGES, ((pdlf ? 108 : (split ? 221 : 200)) * 1024 - out_bytes - res_bytes) / stage_bytes);
+  YB_REQUIRE(stages >= 1, "tc_conv: tile does not fit in shared memory");
   if (stages_override > 0) stages = std::min(stages, stages_override);
   stages = std::max(1, std::min(stages, q.ntaps * q.kchunks * tiles_per_cta));
   q.stages = stages;
@@ -727,9 +805,11 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
 
   // ---- A tensor maps
   const __half* x = reinterpret_cast<const __half*>(p.x);
+  const uint64_t CinP = (uint64_t)npl * p.Cin;    // halfs per input pixel (both planes)
+  const uint64_t CoutP = (uint64_t)npl * p.Cout;  // halfs per residual pixel
   if (flat) {
-    uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)Wov, 1, 1};
-    uint64_t str[3] = {(uint64_t)p.Cin * 2, (uint64_t)Wov * p.Cin * 2, (uint64_t)Wov * p.Cin * 2};
+    uint64_t dims[4] = {CinP, (uint64_t)Wov, 1, 1};
+    uint64_t str[3] = {CinP * 2, (uint64_t)Wov * CinP * 2, (uint64_t)Wov * CinP * 2};
     uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)q.tw, (uint32_t)q.th, 1};
     encode_map_f16(&q.tmA[0], x, 4, dims, str, box);
     q.tap_map[0] = 0;
@@ -752,18 +832,18 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
         if (!used[py * s + px]) continue;
         int Hv = (p.H - py + s - 1) / s, Wv = (p.W - px + s - 1) / s;
         YB_REQUIRE(Hv >= 1 && Wv >= 1, "tc_conv: empty phase view");
-        const __half* base = x + ((size_t)py * p.W + px) * p.Cin;
-        uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)Wv, (uint64_t)Hv, (uint64_t)p.B};
-        uint64_t str[3] = {(uint64_t)s * p.Cin * 2, (uint64_t)s * p.W * p.Cin * 2,
-                           (uint64_t)p.H * p.W * p.Cin * 2};
+        const __half* base = x + ((size_t)py * p.W + px) * CinP;
+        uint64_t dims[4] = {CinP, (uint64_t)Wv, (uint64_t)Hv, (uint64_t)p.B};
+        uint64_t str[3] = {(uint64_t)s * CinP * 2, (uint64_t)s * p.W * CinP * 2,
+                           (uint64_t)p.H * p.W * CinP * 2};
         uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)q.tw, (uint32_t)q.th, 1};
         encode_map_f16(&q.tmA[py * s + px], base, 4, dims, str, box);
       }
   }
   // ---- B tensor map: [tap][Cout][Cin]
   {
-    uint64_t dims[3] = {(uint64_t)p.Cin, (uint64_t)p.Cout, (uint64_t)q.ntaps};
-    uint64_t str[2] = {(uint64_t)p.Cin * 2, (uint64_t)p.Cout * p.Cin * 2};
+    uint64_t dims[3] = {CinP, (uint64_t)p.Cout, (uint64_t)q.ntaps};
+    uint64_t str[2] = {CinP * 2, (uint64_t)p.Cout * CinP * 2};
     uint32_t box[3] = {(uint32_t)BLOCK_K, (uint32_t)(pair ? BN / 2 : BN), 1};   // a pair CTA loads half a weight tile
     encode_map_f16(&q.tmB, w_packed, 3, dims, str, box);
   }
@@ -789,25 +869,25 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
     q.res_batch_stride = 0;
   } else {
     q.y_batch_stride = p.y_batch_stride;
-    q.res_batch_stride = (long long)p.Ho * p.Wo * p.Cout;
+    q.res_batch_stride = (long long)p.Ho * p.Wo * p.Cout;   // pixels * Cout; the kernel scales by the plane count
   }
   if (q.epi_tma) {
     // output / residual tile maps: same geometry as the accumulator tile, 64-channel boxes
     uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)q.tw, (uint32_t)q.th, 1};
     if (flat) {
-      uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)Wov, 1, 1};
+      uint64_t dims[4] = {CoutP, (uint64_t)Wov, 1, 1};
       uint64_t ystr[3] = {(uint64_t)p.y_pix_stride * 2, (uint64_t)Wov * p.y_pix_stride * 2, (uint64_t)Wov * p.y_pix_stride * 2};
       encode_map_f16(&q.tmY, p.y, 4, dims, ystr, box);
       if (p.residual) {
-        uint64_t rstr[3] = {(uint64_t)p.Cout * 2, (uint64_t)Wov * p.Cout * 2, (uint64_t)Wov * p.Cout * 2};
+        uint64_t rstr[3] = {CoutP * 2, (uint64_t)Wov * CoutP * 2, (uint64_t)Wov * CoutP * 2};
         encode_map_f16(&q.tmR, p.residual, 4, dims, rstr, box);
       }
     } else {
-      uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.B};
+      uint64_t dims[4] = {CoutP, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.B};
       uint64_t ystr[3] = {(uint64_t)p.y_pix_stride * 2, (uint64_t)p.Wo * p.y_pix_stride * 2, (uint64_t)p.y_batch_stride * 2};
       encode_map_f16(&q.tmY, p.y, 4, dims, ystr, box);
       if (p.residual) {
-        uint64_t rstr[3] = {(uint64_t)p.Cout * 2, (uint64_t)p.Wo * p.Cout * 2, (uint64_t)p.Ho * p.Wo * p.Cout * 2};
+        uint64_t rstr[3] = {CoutP * 2, (uint64_t)p.Wo * CoutP * 2, (uint64_t)p.Ho * p.Wo * CoutP * 2};
         encode_map_f16(&q.tmR, p.residual, 4, dims, rstr, box);
       }
     }
@@ -824,12 +904,12 @@ int tc_conv_plan_pair(const TcConvPlan* plan) { return plan->pair; }
 int tc_conv_plan_epi_groups(const TcConvPlan* plan) { return plan->epi_groups; }
 int tc_conv_plan_pdl_friendly(const TcConvPlan* plan) { return plan->pdl_friendly; }
 
-template <int BN, bool PAIR, int H>
+template <int BN, bool PAIR, int H, bool SPLIT>
 static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
   static PerDeviceOnce attr;
   if (attr.first())
-    YB_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, PAIR, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(220 * 1024)));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, PAIR, H, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(224 * 1024)));
   constexpr int THREADS = 64 + 128 * H;
   if (plan->prm.pdl || PAIR) {
     cudaLaunchConfig_t cfg = {};
@@ -852,37 +932,42 @@ static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN, PAIR, H>, plan->prm));
+    YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN, PAIR, H, SPLIT>, plan->prm));
   } else {
-    tc_conv_kernel<BN, PAIR, H><<<plan->grid, THREADS, plan->smem_bytes, stream>>>(plan->prm);
+    tc_conv_kernel<BN, PAIR, H, SPLIT><<<plan->grid, THREADS, plan->smem_bytes, stream>>>(plan->prm);
   }
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool SPLIT>
 static void launch_h(const TcConvPlan* plan, cudaStream_t stream) {
   if (plan->epi_groups == 2)
-    launch_bn<BN, PAIR, (BN >= 64 ? 2 : 1)>(plan, stream);
+    launch_bn<BN, PAIR, (BN >= 64 ? 2 : 1), SPLIT>(plan, stream);
   else
-    launch_bn<BN, PAIR, 1>(plan, stream);
+    launch_bn<BN, PAIR, 1, SPLIT>(plan, stream);
 }
 
-void launch_tc_conv(const TcConvPlan* plan, cudaStream_t stream, LaunchCounter* lc) {
+template <bool SPLIT>
+static void launch_s(const TcConvPlan* plan, cudaStream_t stream) {
   if (plan->pair) {
     switch (plan->BN) {
-      case 256: launch_h<256, true>(plan, stream); break;
-      case 128: launch_h<128, true>(plan, stream); break;
-      case 64: launch_h<64, true>(plan, stream); break;
+      case 256: launch_h<256, true, SPLIT>(plan, stream); break;
+      case 128: launch_h<128, true, SPLIT>(plan, stream); break;
+      case 64: launch_h<64, true, SPLIT>(plan, stream); break;
       default: YB_REQUIRE(false, "tc_conv: bad BN for a CTA pair");
     }
   } else {
     switch (plan->BN) {
-      case 256: launch_h<256, false>(plan, stream); break;
-      case 128: launch_h<128, false>(plan, stream); break;
-      case 64: launch_h<64, false>(plan, stream); break;
-      case 32: launch_h<32, false>(plan, stream); break;
+      case 256: launch_h<256, false, SPLIT>(plan, stream); break;
+      case 128: launch_h<128, false, SPLIT>(plan, stream); break;
+      case 64: launch_h<64, false, SPLIT>(plan, stream); break;
+      case 32: launch_h<32, false, SPLIT>(plan, stream); break;
       default: YB_REQUIRE(false, "tc_conv: bad BN");
     }
   }
+}
+
+void launch_tc_conv(const TcConvPlan* plan, cudaStream_t stream, LaunchCounter* lc) {
+  if (plan->split) launch_s<true>(plan, stream); else launch_s<false>(plan, stream);
   YB_CHECK_LAUNCH();
   if (lc) lc->n++;
 }

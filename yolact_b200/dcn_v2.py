@@ -47,7 +47,7 @@ def dcn_v2_conv(input, offset, mask, weight, bias, stride, padding, dilation, de
     Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
     out = torch.empty(B, Co, Ho, Wo, device=input.device, dtype=torch.float32)
     args = [t.contiguous().float() for t in (input, weight, bias, offset, mask)]
-    prec = {"f32": _lib.YB_PREC_F32, "f16tc": _lib.YB_PREC_F16TC}[precision]
+    prec = _lib.PRECISIONS[precision]
     _lib.check(lib.yb_dcn_forward(_handle(input.device, prec), _lib.ptr(args[0]), _lib.ptr(args[1]), _lib.ptr(args[2]),
                                   _lib.ptr(args[3]), _lib.ptr(args[4]), _lib.ptr(out), B, C, H, W, Co, kh, kw, sh, sw,
                                   ph, pw, dh, dw, deformable_groups, _lib.current_stream(input.device)),

@@ -183,17 +183,21 @@ def make_yb_config(c, precision):
 
 
 class Yolact(nn.Module):
-    """See the module docstring.  `precision`: 'f16tc' (tcgen05 tensor cores, default) or 'f32'
-    (fp32 CUDA-core parity mode)."""
+    """See the module docstring.  `precision` (yb_precision in include/yolact_b200.h):
+      'f16x3' (default) split-precision tcgen05 -- fp16 hi+lo operand pairs, three MMA passes, fp32-equivalent results
+              (boxes / scores / masks within 1e-3 of the fp32 reference, identical class ids);
+      'f16tc' single-pass fp16 tcgen05 -- ~2x faster conv stack, head tensors within ~2e-3 of range;
+      'f32'   fp32 on CUDA cores (slow second opinion)."""
 
-    def __init__(self, cfg=None, precision="f16tc"):
+    def __init__(self, cfg=None, precision="f16x3"):
         super().__init__()
         c = (cfg or _config.cfg).copy()
         self.cfg = c
         # side effects the reference's constructor has on its global cfg (yolact.py:425,445)
         _config.cfg.mask_dim = c.mask_dim
         _config.cfg.num_heads = 5
-        self.precision = {"f32": _lib.YB_PREC_F32, "f16tc": _lib.YB_PREC_F16TC}[precision]
+        self.precision = _lib.PRECISIONS[precision]
+        self.precision_name = precision
 
         if c.backbone == "resnet":
             self.backbone = _ResNetParams(c.backbone_layers, c.dcn_layers, c.dcn_interval)
