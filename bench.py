@@ -300,6 +300,7 @@ def main():
 
     def make_net(precision):
         net = yolact_b200.Yolact(cfg, precision=precision)
+        net.detect.use_fast_nms = True   # what eval.py does from --fast_nms (default True, eval.py:50,871)
         net.load_state_dict(deterministic_state_dict(net.state_dict(), 0))
         net.eval()
         return net

@@ -79,6 +79,9 @@ typedef enum { YB_PREC_F32 = 0, YB_PREC_F16TC = 1, YB_PREC_F16X3 = 2 } yb_precis
  *   YB_NMS_CROSS_CLASS : cc_fast_nms       (detection.py:111-135; --cross_class_nms)
  *   YB_NMS_TRADITIONAL : traditional_nms   (detection.py:182-228 + utils/cython_nms.pyx; --fast_nms=False) */
 typedef enum { YB_NMS_FAST = 0, YB_NMS_CROSS_CLASS = 1, YB_NMS_TRADITIONAL = 2 } yb_nms_mode;
+/* OR-ed into the nms mode: fast_nms(second_threshold=True), i.e. a kept detection must also have its OWN class score
+ * above conf_thresh (detection.py:155-161; the reference leaves it off, "+0.2 mAP for 34 -> 33 fps"). YB_NMS_FAST only. */
+#define YB_NMS_FLAG_SECOND_THRESHOLD 0x100
 
 /* cfg.backbone.transform of FastBaseTransform (utils/augmentations.py:645-650) */
 typedef enum {
@@ -173,6 +176,11 @@ YB_API int yb_detect(yb_handle* h, const float* d_loc, const float* d_conf, cons
               const float* d_priors, int B, int64_t P, int conf_is_logits, int cross_class,
               int max_out, float* d_box, float* d_coef_out, int64_t* d_cls, float* d_score,
               int32_t* d_count, void* stream);
+
+/* Detect's parameters (Detect.top_k / conf_thresh / nms_thresh and cfg.max_num_detections, detection.py:17-31) are taken
+ * from yb_config at yb_create; the reference lets callers change the attributes of net.detect afterwards, this is the
+ * C-side of that.  Changing them synchronises the device and drops the captured yb_infer graphs. */
+YB_API int yb_set_detect_params(yb_handle* h, int top_k, float conf_thresh, float nms_thresh, int max_num_detections);
 
 /* Fused eval-mode path: yb_forward + yb_detect on the library's internal head buffers (no copy-out
  * of loc/conf/coef).  This is Yolact.forward() in eval mode (yolact.py:649-676).  d_proto

@@ -324,7 +324,7 @@ def traditional_nms(boxes, masks, scores, iou_threshold, conf_thresh, max_size, 
 
 
 def detect_one(loc, conf, mask, priors, conf_thresh=0.05, nms_thresh=0.5, top_k=200, max_dets=100,
-               cross_class=False, traditional=False, max_size=550):
+               cross_class=False, traditional=False, max_size=550, second_threshold=False):
     """One image.  conf [P,C] softmaxed.  Returns dict(box, mask, class, score) or None
     (Detect.detect + fast_nms / cc_fast_nms / traditional_nms, detection.py:81-228)."""
     conf = np.asarray(conf, np.float32)
@@ -361,6 +361,8 @@ def detect_one(loc, conf, mask, priors, conf_thresh=0.05, nms_thresh=0.5, top_k=
     iou = np.triu(iou, k=1)                                # triu_ on the last two dims (:149)
     iou_max = iou.max(axis=1)                              # column max (:150); NaN propagates like torch.max
     keepm = iou_max <= np.float32(nms_thresh)              # :153
+    if second_threshold:
+        keepm = keepm & (s > np.float32(conf_thresh))      # :160-161
     classes = np.broadcast_to(np.arange(C)[:, None], keepm.shape)[keepm]
     b, m, s = b[keepm], m[keepm], s[keepm]
     o = _stable_desc_order(s)[:max_dets]                   # :172-174

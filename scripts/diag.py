@@ -10,7 +10,7 @@ cfgname = sys.argv[1] if len(sys.argv) > 1 else "yolact_resnet50_config"
 size = int(sys.argv[2]) if len(sys.argv) > 2 else 160
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 cfg = CONFIGS[cfgname].copy(); yolact_b200.cfg.replace(cfg.copy())
-net = yolact_b200.Yolact(cfg); net.load_state_dict(deterministic_state_dict(net.state_dict(), 0)); net.eval()
+net = yolact_b200.Yolact(cfg); net.load_state_dict(deterministic_state_dict(net.state_dict(), 0)); net.eval(); net.detect.use_fast_nms = True
 print("net built %.1fs" % (time.time() - t0), flush=True)
 x = deterministic_input(B, size, size, 1).cuda()
 torch.cuda.synchronize()

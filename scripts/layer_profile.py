@@ -9,7 +9,7 @@ ap.add_argument("--config", default="yolact_base_config"); ap.add_argument("--ba
 ap.add_argument("--precision", default="f16x3")
 a = ap.parse_args()
 cfg = CONFIGS[a.config].copy(); yolact_b200.cfg.replace(cfg.copy())
-net = yolact_b200.Yolact(cfg, precision=a.precision); net.load_state_dict(deterministic_state_dict(net.state_dict(), 0)); net.eval()
+net = yolact_b200.Yolact(cfg, precision=a.precision); net.load_state_dict(deterministic_state_dict(net.state_dict(), 0)); net.eval(); net.detect.use_fast_nms = True
 x = deterministic_input(a.batch, cfg.max_size, cfg.max_size, 1).cuda()
 net.profile_conv_stack(x)
 prof = net.profile_conv_stack(x)

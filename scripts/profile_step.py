@@ -21,7 +21,7 @@ args = ap.parse_args()
 cfg = CONFIGS[args.config].copy()
 size = args.size or cfg.max_size
 yolact_b200.cfg.replace(cfg.copy())
-net = yolact_b200.Yolact(cfg)
+net = yolact_b200.Yolact(cfg, precision=os.environ.get("YB_PRECISION", "f16x3")); net.detect.use_fast_nms = True
 net.load_state_dict(deterministic_state_dict(net.state_dict(), 0))
 net.eval()
 x = deterministic_input(args.batch, size, size, 1234).cuda()

@@ -120,6 +120,7 @@ def measure(cfg, precision, batch, size, out_hw=None, seed_w=0, seed_x=99, net=N
     own = net is None
     if own:
         net = yolact_b200.Yolact(cfg, precision=precision)
+        net.detect.use_fast_nms = True   # what eval.py does from --fast_nms (default True, eval.py:50,871)
         sd = deterministic_state_dict(net.state_dict(), seed_w)
         net.load_state_dict(sd)
     else:

@@ -104,7 +104,12 @@ def test_no_cpu_fallback_for_the_row_ops():
 def test_detect_nms_mode_follows_the_eval_flags():
     from yolact_b200.detection import Detect
     d = Detect(81, 0, 200, 0.05, 0.5)
-    assert d.nms_mode() == _lib.YB_NMS_FAST                      # eval.py defaults
+    assert d.nms_mode() == _lib.YB_NMS_TRADITIONAL               # the reference class default (detection.py:30)
+    d.use_fast_nms = True                                        # eval.py:871 with --fast_nms's default
+    assert d.nms_mode() == _lib.YB_NMS_FAST
+    d.second_threshold = True                                    # fast_nms(second_threshold=True), detection.py:160
+    assert d.nms_mode() == (_lib.YB_NMS_FAST | _lib.YB_NMS_FLAG_SECOND_THRESHOLD)
+    d.second_threshold = False
     d.use_cross_class_nms = True
     assert d.nms_mode() == _lib.YB_NMS_CROSS_CLASS
     d.use_fast_nms = False                                       # --fast_nms=False wins (detection.py:100-106)

@@ -36,9 +36,46 @@ def test_detect_unit_golden():
             assert np.array_equal(coef[b, :n], g["%s%d_mask" % (tag, b)])
 
 
+def _sparse_fixture(seed=5, P=3000, C=81):
+    """Few confident priors: fast_nms then returns sub-threshold rows unless second_threshold is on."""
+    r = np.random.RandomState(seed)
+    priors = np.concatenate([r.uniform(0.1, 0.9, (P, 2)), r.uniform(0.05, 0.3, (P, 2))], 1).astype(np.float32)
+    loc = (r.standard_normal((P, 4)) * 0.5).astype(np.float32)
+    logits = r.standard_normal((P, C)).astype(np.float32)
+    logits[:, 0] += 4.0
+    hot = r.choice(P, 40, replace=False)
+    logits[hot, r.randint(1, C, 40)] += 7.0
+    return loc, O.softmax_rows(logits), r.standard_normal((P, 32)).astype(np.float32), priors
+
+
+@pytest.mark.parametrize("thresh", [0.05, 0.2])
+def test_fast_nms_second_threshold_matches_oracle(thresh):
+    """fast_nms(second_threshold=True) (detection.py:137,160-161): a kept row must also have its own class score above
+    conf_thresh.  Candidates are selected on the max over classes, so the class rows hold many sub-threshold scores;
+    at thresh = 0.2 the plain result carries 42 of them and the flag removes exactly those."""
+    loc, conf, mask, priors = _sparse_fixture()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    res = {}
+    for flag in (False, True):
+        d = Detect(81, bkg_label=0, top_k=200, conf_thresh=thresh, nms_thresh=0.5)
+        d.use_fast_nms, d.second_threshold = True, flag
+        box, coef, cls, score, count = [x.cpu().numpy() for x in
+                                        d.detect_padded(t(loc[None]), t(conf[None]), t(mask[None]), t(priors))]
+        want = O.detect_one(loc, conf, mask, priors, conf_thresh=thresh, second_threshold=flag)
+        n = int(count[0])
+        assert n == want["score"].shape[0]
+        assert np.array_equal(cls[0, :n], want["class"]) and np.array_equal(score[0, :n], want["score"])
+        np.testing.assert_allclose(box[0, :n], want["box"], rtol=0, atol=2e-6)
+        res[flag] = score[0, :n]
+    assert (res[True] > thresh).all()
+    if thresh == 0.2:
+        assert (res[False] <= thresh).sum() > 0 and len(res[True]) < len(res[False])
+
+
 def test_detect_api_object():
     g = load_golden("detect_unit")
     d = Detect(81, 0, 200, 0.05, 0.5)
+    d.use_fast_nms = True   # eval.py:871
     t = lambda a: torch.from_numpy(a).cuda()
     out = d({"loc": t(g["loc"]), "conf": t(g["conf"]), "mask": t(g["mask"]), "priors": t(g["priors"])}, "NET")
     assert len(out) == 2 and out[0]["net"] == "NET"

@@ -32,6 +32,7 @@ def build(case, precision):
         cfg = cfg_for(str(g["config"]))
         yolact_b200.cfg.replace(cfg.copy())
         net = yolact_b200.Yolact(cfg, precision=precision)
+        net.detect.use_fast_nms = True   # what eval.py does from --fast_nms (default True, eval.py:50,871)
         net.load_state_dict(deterministic_state_dict(net.state_dict(), int(g["seed"])))
         _cache[key] = (g, cfg, net)
     g, cfg, net = _cache[key]
@@ -158,6 +159,7 @@ def test_full_size_yolact_base_f16tc_vs_f32_and_oracle():
     outs = {}
     for prec in ("f32", "f16tc", "f16x3"):
         net = yolact_b200.Yolact(cfg, precision=prec)
+        net.detect.use_fast_nms = True   # what eval.py does from --fast_nms (default True, eval.py:50,871)
         sd = deterministic_state_dict(net.state_dict(), 1)
         net.load_state_dict(sd)
         net.train()

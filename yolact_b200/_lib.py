@@ -43,6 +43,7 @@ YB_PREC_F32, YB_PREC_F16TC, YB_PREC_F16X3 = 0, 1, 2
 PRECISIONS = {"f32": YB_PREC_F32, "f16tc": YB_PREC_F16TC, "f16x3": YB_PREC_F16X3}
 YB_MASK_F32, YB_MASK_U8, YB_MASK_BITS = 0, 1, 2
 YB_NMS_FAST, YB_NMS_CROSS_CLASS, YB_NMS_TRADITIONAL = 0, 1, 2
+YB_NMS_FLAG_SECOND_THRESHOLD = 0x100
 YB_XFORM_NORMALIZE, YB_XFORM_SUBTRACT_MEANS, YB_XFORM_TO_FLOAT, YB_XFORM_NONE = 0, 1, 2, 3
 
 # name -> (restype, argtypes); kept in one table so tests can check that every symbol the header
@@ -63,6 +64,7 @@ SIGNATURES = {
     "yb_softmax": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "yb_detect": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "yb_set_detect_params": (c_int, [c_void_p, c_int, c_float, c_float, c_int]),
     "yb_infer": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_void_p]),
     "yb_postprocess": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,

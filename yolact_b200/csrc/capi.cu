@@ -92,6 +92,42 @@ __global__ void pack_om_kernel(const float* __restrict__ off, const float* __res
   }
 }
 
+// Every entry point that takes a handle holds its mutex while it enqueues work (the handle's plans, launch counter
+// and lazily grown workspaces are not thread-safe by themselves).  Entry points that run on the handle's SHARED device
+// buffers (executor activations, Detect workspace, scratch) additionally order themselves on the device behind the
+// previous such call when it was issued on a different stream -- eval.py's ThreadPool callers (eval.py:793-827) may
+// drive one net from several threads / streams; results are then serialised, never corrupted.
+struct CallGuard {
+  yb_handle* h;
+  DeviceGuard dg;
+  std::unique_lock<std::recursive_mutex> lk;
+  cudaStream_t stream = nullptr;
+  bool chain = false;
+  explicit CallGuard(yb_handle* h_) : h(h_), dg(h_->device), lk(h_->mu) {}
+  CallGuard(yb_handle* h_, cudaStream_t s) : h(h_), dg(h_->device), lk(h_->mu), stream(s), chain(true) {
+    if (h->ev_last && h->has_last && h->last_stream != s) cudaStreamWaitEvent(s, h->ev_last, 0);
+  }
+  ~CallGuard() {
+    if (!chain) return;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return;   // the caller is capturing this stream itself: ordering is the caller's graph
+    }
+    if (!h->ev_last && cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      h->ev_last = nullptr;
+      return;
+    }
+    if (cudaEventRecord(h->ev_last, stream) == cudaSuccess) {
+      h->last_stream = stream;
+      h->has_last = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
+};
+
 struct TempPool {  // RAII device temporaries for the op-level hooks
   std::vector<void*> v;
   void* get(size_t bytes) {
@@ -169,7 +205,7 @@ int yb_create(const yb_config* cfg, int device, yb_handle** out) {
 int yb_destroy(yb_handle* h) {
   YB_API_BEGIN
   if (h) {
-    DeviceGuard g(h->device);
+    DeviceGuard dg(h->device);
     cudaDeviceSynchronize();
     delete h;
   }
@@ -196,7 +232,7 @@ int yb_load_weight(yb_handle* h, const char* name, const float* h_data, const in
 int yb_finalize_weights(yb_handle* h) {
   YB_API_BEGIN
   YB_REQUIRE(h, "null handle");
-  DeviceGuard g(h->device);
+  CallGuard g(h);
   h->finalize();
   YB_API_END
 }
@@ -221,7 +257,7 @@ int yb_num_priors(yb_handle* h, int img_h, int img_w, int64_t* num_priors, int32
 int yb_priors(yb_handle* h, int img_h, int img_w, float* d_priors, void* stream) {
   YB_API_BEGIN
   YB_REQUIRE(h && !h->ops_only && d_priors, "yb_priors: bad argument");
-  DeviceGuard g(h->device);
+  CallGuard g(h);
   int lhw[5][2];
   compute_level_sizes(h->cfg, img_h, img_w, lhw, nullptr, nullptr);
   std::vector<float> pri = make_priors_host(h->cfg, lhw);
@@ -245,7 +281,7 @@ int yb_forward(yb_handle* h, const float* d_x, int B, int H, int W, float* d_loc
   YB_API_BEGIN
   YB_REQUIRE(h && d_x && B > 0 && H > 0 && W > 0, "yb_forward: bad argument");
   YB_REQUIRE(!h->ops_only, "yb_forward: handle has no network");
-  DeviceGuard g(h->device);
+  CallGuard g(h, (cudaStream_t)stream);   // shared workspaces: ordered behind the previous call
   h->forward(d_x, B, H, W, d_loc, d_conf, d_coef, d_proto, (cudaStream_t)stream);
   YB_API_END
 }
@@ -256,7 +292,7 @@ int yb_infer(yb_handle* h, const float* d_x, int B, int H, int W, int cross_clas
   YB_REQUIRE(h && d_x && B > 0 && H > 0 && W > 0, "yb_infer: bad argument");
   YB_REQUIRE(!h->ops_only, "yb_infer: handle has no network");
   YB_REQUIRE(d_box && d_coef_out && d_cls && d_score && d_count, "yb_infer: null output");
-  DeviceGuard g(h->device);
+  CallGuard g(h, (cudaStream_t)stream);   // shared workspaces: ordered behind the previous call
   h->infer(d_x, B, H, W, cross_class, max_out, d_box, d_coef_out, d_cls, d_score, d_count, d_proto,
            (cudaStream_t)stream);
   YB_API_END
@@ -265,7 +301,7 @@ int yb_infer(yb_handle* h, const float* d_x, int B, int H, int W, int cross_clas
 int yb_debug_feature(yb_handle* h, int which, float* d_out, int32_t* chw, void* stream) {
   YB_API_BEGIN
   YB_REQUIRE(h && h->last_exec && which >= 0 && which < 9, "yb_debug_feature: no forward has run / bad index");
-  DeviceGuard g(h->device);
+  CallGuard g(h, (cudaStream_t)stream);   // shared workspaces: ordered behind the previous call
   const Act& a = h->last_exec->feats[which];
   YB_REQUIRE(a.ptr != nullptr, "yb_debug_feature: feature not available for this backbone");
   if (chw) {
@@ -286,8 +322,28 @@ int yb_debug_feature(yb_handle* h, int which, float* d_out, int32_t* chw, void* 
 int yb_softmax(yb_handle* h, const float* d_in, float* d_out, int64_t rows, int cols, void* stream) {
   YB_API_BEGIN
   YB_REQUIRE(h && d_in && d_out && rows >= 0 && cols > 0, "yb_softmax: bad argument");
-  DeviceGuard g(h->device);
+  CallGuard g(h);
   launch_softmax_rows(d_in, d_out, rows, cols, (cudaStream_t)stream, &h->lc);
+  YB_API_END
+}
+
+int yb_set_detect_params(yb_handle* h, int top_k, float conf_thresh, float nms_thresh, int max_num_detections) {
+  YB_API_BEGIN
+  YB_REQUIRE(h, "yb_set_detect_params: null handle");
+  YB_REQUIRE(top_k >= 1 && top_k <= 256, "yb_set_detect_params: top_k must be in [1, 256] (one CTA sorts a class)");
+  YB_REQUIRE(max_num_detections >= 1 && max_num_detections <= 256, "yb_set_detect_params: max_num_detections must be in [1, 256]");
+  YB_REQUIRE(nms_thresh > 0.f, "nms_threshold must be non negative.");   // detection.py:25-26
+  CallGuard g(h);
+  yb_config& c = h->cfg;
+  if (c.nms_top_k == top_k && c.nms_conf_thresh == conf_thresh && c.nms_thresh == nms_thresh &&
+      c.max_num_detections == max_num_detections)
+    return YB_OK;
+  YB_CHECK_CUDA(cudaDeviceSynchronize());
+  c.nms_top_k = top_k;
+  c.nms_conf_thresh = conf_thresh;
+  c.nms_thresh = nms_thresh;
+  c.max_num_detections = max_num_detections;
+  for (auto& kv : h->execs) kv.second->drop_detect_state();   // workspace sizes and captured graphs depend on them
   YB_API_END
 }
 
@@ -298,7 +354,7 @@ int yb_detect(yb_handle* h, const float* d_loc, const float* d_conf, const float
   YB_REQUIRE(h && d_loc && d_conf && d_coef && d_priors && d_box && d_coef_out && d_cls && d_score && d_count,
              "yb_detect: null argument");
   YB_REQUIRE(B > 0 && P > 0, "yb_detect: empty input");
-  DeviceGuard g(h->device);
+  CallGuard g(h, (cudaStream_t)stream);   // shared workspaces: ordered behind the previous call
   DetectParams dp;
   dp.B = B;
   dp.P = P;
@@ -309,7 +365,8 @@ int yb_detect(yb_handle* h, const float* d_loc, const float* d_conf, const float
   dp.nms_thresh = h->cfg.nms_thresh;
   dp.max_dets = h->cfg.max_num_detections;
   dp.conf_is_logits = conf_is_logits;
-  dp.cross_class = cross_class;
+  dp.cross_class = cross_class & 0xFF;
+  dp.second_threshold = (cross_class & YB_NMS_FLAG_SECOND_THRESHOLD) ? 1 : 0;
   dp.max_size = (float)h->cfg.max_size;
   dp.max_out = max_out;
   YB_REQUIRE(dp.nms_thresh > 0.f, "nms_threshold must be non negative.");  // detection.py:25-26
@@ -327,7 +384,7 @@ int yb_postprocess(yb_handle* h, const float* d_proto, int ph, int pw, int k, co
   YB_API_BEGIN
   YB_REQUIRE(h && d_proto && d_coef && d_box, "yb_postprocess: null argument");
   YB_REQUIRE(n >= 0, "yb_postprocess: negative detection count");
-  DeviceGuard g(h->device);
+  CallGuard g(h);
   launch_mask_assembly(d_proto, ph, pw, k, d_coef, d_box, n, out_h, out_w, crop_masks, mask_format, d_masks,
                        d_boxes_px, d_proto_masks, (cudaStream_t)stream, &h->lc);
   YB_API_END
@@ -339,7 +396,7 @@ int yb_postprocess_batch(yb_handle* h, const float* d_proto, int ph, int pw, int
   YB_API_BEGIN
   YB_REQUIRE(h && d_proto && d_coef && d_box, "yb_postprocess_batch: null argument");
   YB_REQUIRE(n >= 0 && batch >= 0, "yb_postprocess_batch: negative count");
-  DeviceGuard g(h->device);
+  CallGuard g(h);
   launch_mask_assembly(d_proto, ph, pw, k, d_coef, d_box, n, out_h, out_w, crop_masks, mask_format, d_masks,
                        d_boxes_px, nullptr, (cudaStream_t)stream, &h->lc, batch);
   YB_API_END
@@ -351,7 +408,7 @@ int yb_maskiou(yb_handle* h, const float* d_proto_masks, int n, int ph, int pw, 
   YB_REQUIRE(h && d_proto_masks && d_maskiou, "yb_maskiou: null argument");
   YB_REQUIRE(h->cfg.use_maskiou && h->finalized, "yb_maskiou: network has no maskiou_net / weights not finalized");
   if (n <= 0) return YB_OK;
-  DeviceGuard g(h->device);
+  CallGuard g(h, (cudaStream_t)stream);   // shared workspaces: ordered behind the previous call
   cudaStream_t s = (cudaStream_t)stream;
   // FastMaskIoUNet (yolact.py:363-375, config.py:785-789): 5x (3x3 s2 p0 + ReLU), 1x1 + ReLU, global max
   const char* idx[6] = {"0", "2", "4", "6", "8", "10"};
@@ -413,7 +470,7 @@ int yb_fast_base_transform(yb_handle* h, const void* d_img, int img_is_u8, int B
   // data/config.py:28-29 (BGR order)
   static const float kMeans[3] = {103.94f, 116.78f, 123.68f};
   static const float kStd[3] = {57.38f, 57.12f, 58.40f};
-  DeviceGuard g(h->device);
+  CallGuard g(h);
   launch_fast_base_transform(d_img, img_is_u8, B, H, W, out_h, out_w, mode, h_mean_bgr ? h_mean_bgr : kMeans,
                              h_std_bgr ? h_std_bgr : kStd, d_out, (cudaStream_t)stream, &h->lc);
   YB_API_END
@@ -423,7 +480,7 @@ int yb_pack_mask_bits(yb_handle* h, const void* d_in, int in_format, int64_t row
                       void* stream) {
   YB_API_BEGIN
   YB_REQUIRE(h && rows >= 0 && w > 0 && (rows == 0 || (d_in && d_bits)), "yb_pack_mask_bits: bad argument");
-  DeviceGuard g(h->device);
+  CallGuard g(h);
   launch_pack_mask_bits(d_in, in_format, rows, w, d_bits, (cudaStream_t)stream, &h->lc);
   YB_API_END
 }
@@ -433,7 +490,7 @@ int yb_mask_iou(yb_handle* h, const uint32_t* d_a, int n, const uint32_t* d_b, i
   YB_API_BEGIN
   YB_REQUIRE(h && n >= 0 && m >= 0 && words >= 0, "yb_mask_iou: bad argument");
   YB_REQUIRE(n == 0 || m == 0 || (d_a && d_b && d_iou), "yb_mask_iou: null argument");
-  DeviceGuard g(h->device);
+  CallGuard g(h);
   launch_mask_iou_bits(d_a, n, d_b, m, words, iscrowd, d_iou, (cudaStream_t)stream, &h->lc);
   YB_API_END
 }
@@ -443,7 +500,7 @@ int yb_box_iou(yb_handle* h, const float* d_a, int n, const float* d_b, int m, i
   YB_API_BEGIN
   YB_REQUIRE(h && n >= 0 && m >= 0, "yb_box_iou: bad argument");
   YB_REQUIRE(n == 0 || m == 0 || (d_a && d_b && d_iou), "yb_box_iou: null argument");
-  DeviceGuard g(h->device);
+  CallGuard g(h);
   launch_box_iou(d_a, n, d_b, m, iscrowd, d_iou, (cudaStream_t)stream, &h->lc);
   YB_API_END
 }
@@ -453,7 +510,7 @@ int yb_mask_rle(yb_handle* h, const void* d_masks, int mask_format, int n, int m
   YB_API_BEGIN
   YB_REQUIRE(h && n >= 0, "yb_mask_rle: bad argument");
   YB_REQUIRE(n == 0 || (d_masks && d_counts && d_nruns), "yb_mask_rle: null argument");
-  DeviceGuard g(h->device);
+  CallGuard g(h);
   launch_mask_rle(d_masks, mask_format, n, mask_h, mask_w, d_counts, cap, d_nruns, (cudaStream_t)stream, &h->lc);
   YB_API_END
 }
@@ -463,7 +520,7 @@ int yb_display_blend(yb_handle* h, const float* d_img, int img_is_255, const voi
   YB_API_BEGIN
   YB_REQUIRE(h && d_img && d_out, "yb_display_blend: null argument");
   YB_REQUIRE(n == 0 || (d_masks && d_colors), "yb_display_blend: null masks / colors");
-  DeviceGuard g(h->device);
+  CallGuard g(h);
   launch_display_blend(d_img, img_is_255, d_masks, mask_format, n, img_h, img_w, d_colors, alpha, d_out,
                        (cudaStream_t)stream, &h->lc);
   YB_API_END
@@ -479,7 +536,7 @@ int yb_dcn_forward(yb_handle* h, const float* d_input, const float* d_weight, co
   YB_REQUIRE(stride_h == stride_w && pad_h == pad_w && dilation_h == dilation_w, "yb_dcn_forward: anisotropic params");
   YB_REQUIRE(deformable_group == 1, "yb_dcn_forward: deformable_group must be 1");
   YB_REQUIRE(C % 16 == 0, "yb_dcn_forward: C must be a multiple of 16");
-  DeviceGuard g(h->device);
+  CallGuard g(h);
   cudaStream_t s = (cudaStream_t)stream;
   const int Ho = (H + 2 * pad_h - (dilation_h * 2 + 1)) / stride_h + 1;
   const int Wo = (W + 2 * pad_w - (dilation_w * 2 + 1)) / stride_w + 1;
@@ -571,7 +628,7 @@ int yb_conv2d(yb_handle* h, const float* d_x, const float* h_w, const float* h_b
   YB_REQUIRE(precision >= 0 && precision <= 3,
              "yb_conv2d: precision must be 0 (f32 simt), 1 (f16 tcgen05), 2 (f16 simt), 3 (split-precision tcgen05)");
   const int sp = (precision == 3) ? 1 : 0;
-  DeviceGuard g(h->device);
+  CallGuard g(h);
   cudaStream_t s = (cudaStream_t)stream;
   const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
   YB_REQUIRE(Ho >= 1 && Wo >= 1, "yb_conv2d: empty output");

@@ -269,6 +269,7 @@ class_nms_kernel(const float* __restrict__ scoresT, const int32_t* __restrict__ 
                  const float* __restrict__ loc, const float* __restrict__ priors,
                  const float* __restrict__ coef, int64_t P, int C, int mask_dim, int top_k,
                  float nms_thresh,
+                 float second_thresh,   // fast_nms(second_threshold=True): keep only score > conf_thresh; -inf = off
                  // per-class pool (not CC)
                  float* __restrict__ pool_score, int32_t* __restrict__ pool_prior,
                  float* __restrict__ pool_box, int32_t* __restrict__ pool_n,
@@ -321,7 +322,8 @@ class_nms_kernel(const float* __restrict__ scoresT, const int32_t* __restrict__ 
   if (valid) {
     for (int i = 0; i < tid; ++i) m = nan_max(m, box_iou(sbox[i], bx));
   }
-  const bool keep = valid && (m <= nms_thresh);
+  // detection.py:153,160-161: keep = (iou_max <= thresh) [* (scores > conf_thresh)]
+  const bool keep = valid && (m <= nms_thresh) && (score > second_thresh);
 
   int total;
   const int pos = block_excl_scan(keep ? 1 : 0, s_warp, &total);
@@ -569,6 +571,7 @@ void launch_detect(const DetectParams& dp, const float* loc, const float* conf, 
   YB_REQUIRE(dp.num_classes >= 2 && dp.num_classes - 1 <= 128, "detect: num_classes out of range");
   YB_REQUIRE(dp.max_out <= SORT_N, "detect: max_out must be <= 256");
   YB_REQUIRE(dp.cross_class >= YB_NMS_FAST && dp.cross_class <= YB_NMS_TRADITIONAL, "detect: unknown nms mode");
+  YB_REQUIRE(!dp.second_threshold || dp.cross_class == YB_NMS_FAST, "detect: second_threshold exists for fast_nms only");
   YB_REQUIRE(dp.cross_class == YB_NMS_CROSS_CLASS ? dp.max_out >= 1 : dp.max_out >= dp.max_dets,
              "detect: max_out too small");
   YB_REQUIRE(dp.P < (1ll << 31), "detect: too many priors");
@@ -589,7 +592,7 @@ void launch_detect(const DetectParams& dp, const float* loc, const float* conf, 
     dim3 grid(1, B);
     class_nms_kernel<true><<<grid, NT2, 0, stream>>>(
         ws.scoresT, ws.cand_prior, ws.cand_cls, ws.cand_count, loc, priors, coef, dp.P, C,
-        dp.mask_dim, dp.top_k, dp.nms_thresh, nullptr, nullptr, nullptr, nullptr, dp.max_out, box,
+        dp.mask_dim, dp.top_k, dp.nms_thresh, -INFINITY, nullptr, nullptr, nullptr, nullptr, dp.max_out, box,
         coef_out, cls, score, count);
     YB_CHECK_LAUNCH();
     if (lc) lc->n++;
@@ -604,7 +607,8 @@ void launch_detect(const DetectParams& dp, const float* loc, const float* conf, 
     } else {
       class_nms_kernel<false><<<grid, NT2, 0, stream>>>(
           ws.scoresT, ws.cand_prior, ws.cand_cls, ws.cand_count, loc, priors, coef, dp.P, C,
-          dp.mask_dim, dp.top_k, dp.nms_thresh, ws.pool_score, ws.pool_prior, ws.pool_box, ws.pool_n,
+          dp.mask_dim, dp.top_k, dp.nms_thresh, dp.second_threshold ? dp.conf_thresh : -INFINITY, ws.pool_score,
+          ws.pool_prior, ws.pool_box, ws.pool_n,
           dp.max_out, nullptr, nullptr, nullptr, nullptr, nullptr);
     }
     YB_CHECK_LAUNCH();

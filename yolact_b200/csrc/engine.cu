@@ -23,9 +23,28 @@ static void* dmalloc(std::vector<void*>& pool, size_t bytes) {
   return p;
 }
 
+void Executor::drop_detect_state() {
+  for (auto& kv : infer_graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  infer_graphs.clear();
+  void* bufs[6] = {det_ws, det_box, det_coef, det_cls, det_score, det_count};
+  for (void* b : bufs) {
+    if (!b) continue;
+    auto it = std::find(allocs.begin(), allocs.end(), b);
+    if (it != allocs.end()) allocs.erase(it);
+    cudaFree(b);
+  }
+  det_ws = nullptr;
+  det_box = det_coef = det_score = nullptr;
+  det_cls = nullptr;
+  det_count = nullptr;
+  det_cap = 0;
+}
+
 Executor::~Executor() {
   if (graph_fwd) cudaGraphExecDestroy(graph_fwd);
-  if (graph_infer) cudaGraphExecDestroy(graph_infer);
+  for (auto& kv : infer_graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (auto* p : plans) tc_conv_plan_destroy(p);
   for (auto* p : stem_plans) stem_tc_plan_destroy(p);
   for (void* p : allocs) cudaFree(p);
@@ -691,6 +710,7 @@ yb_handle::~yb_handle() {
   for (auto s : lane_streams)
     if (s) cudaStreamDestroy(s);
   if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_last) cudaEventDestroy(ev_last);
   for (auto e : ev_join)
     if (e) cudaEventDestroy(e);
 }
@@ -1088,29 +1108,25 @@ void yb_handle::infer(const float* d_x, int B, int H, int W, int cross_class, in
   dp.nms_thresh = cfg.nms_thresh;
   dp.max_dets = cfg.max_num_detections;
   dp.conf_is_logits = 1;
-  dp.cross_class = cross_class;
+  dp.cross_class = cross_class & 0xFF;
+  dp.second_threshold = (cross_class & YB_NMS_FLAG_SECOND_THRESHOLD) ? 1 : 0;
   dp.max_size = (float)cfg.max_size;
   dp.max_out = max_out;
-  if (!ex->det_ws || ex->det_max_out != max_out || ex->det_cross_class != cross_class) {
-    // (re)build the fused-detect buffers; invalidates the captured graph
-    YB_CHECK_CUDA(cudaDeviceSynchronize());
-    if (ex->graph_infer) {
-      cudaGraphExecDestroy(ex->graph_infer);
-      ex->graph_infer = nullptr;
-    }
-    ex->infer_calls = 0;
-    if (!ex->det_ws) {
-      ex->det_ws = dmalloc(ex->allocs, detect_workspace_bytes(B, ex->P, cfg.num_classes, cfg.nms_top_k));
-      detect_workspace_bind(&ex->dws, ex->det_ws, B, ex->P, cfg.num_classes, cfg.nms_top_k);
-    }
-    ex->det_box = (float*)dmalloc(ex->allocs, (size_t)B * max_out * 4 * 4);
-    ex->det_coef = (float*)dmalloc(ex->allocs, (size_t)B * max_out * cfg.mask_dim * 4);
-    ex->det_cls = (int64_t*)dmalloc(ex->allocs, (size_t)B * max_out * 8);
-    ex->det_score = (float*)dmalloc(ex->allocs, (size_t)B * max_out * 4);
+  // Detect buffers: allocated once per executor at the largest row count any NMS mode can ask for, so toggling
+  // net.detect.use_cross_class_nms / use_fast_nms between calls neither re-allocates nor leaks
+  const int cap = std::max(cfg.nms_top_k, cfg.max_num_detections);
+  YB_REQUIRE(max_out >= 1 && max_out <= cap, "yb_infer: max_out must be in [1, max(nms_top_k, max_num_detections)]");
+  if (!ex->det_ws) {
+    ex->det_ws = dmalloc(ex->allocs, detect_workspace_bytes(B, ex->P, cfg.num_classes, cfg.nms_top_k));
+    detect_workspace_bind(&ex->dws, ex->det_ws, B, ex->P, cfg.num_classes, cfg.nms_top_k);
+    ex->det_box = (float*)dmalloc(ex->allocs, (size_t)B * cap * 4 * 4);
+    ex->det_coef = (float*)dmalloc(ex->allocs, (size_t)B * cap * cfg.mask_dim * 4);
+    ex->det_cls = (int64_t*)dmalloc(ex->allocs, (size_t)B * cap * 8);
+    ex->det_score = (float*)dmalloc(ex->allocs, (size_t)B * cap * 4);
     ex->det_count = (int32_t*)dmalloc(ex->allocs, (size_t)B * 4);
-    ex->det_max_out = max_out;
-    ex->det_cross_class = cross_class;
+    ex->det_cap = cap;
   }
+  Executor::InferGraph& ig = ex->infer_graphs[(cross_class & 0xFFF) | (max_out << 12)];
   auto run_all = [&](cudaStream_t s, bool branches) {
     run_ops(this, ex, s, branches);
     launch_detect(dp, ex->loc, ex->conf, ex->coef, ex->priors, ex->dws, ex->det_box, ex->det_coef, ex->det_cls,
@@ -1118,10 +1134,10 @@ void yb_handle::infer(const float* d_x, int B, int H, int W, int cross_class, in
   };
   YB_CHECK_CUDA(cudaMemcpyAsync(ex->d_in, d_x, (size_t)B * 3 * H * W * 4, cudaMemcpyDeviceToDevice, stream));
   last_exec = ex;
-  if (!use_graphs || ex->infer_calls == 0) {
-    run_all(stream, false);
+  if (!use_graphs || ig.calls == 0) {
+    run_all(stream, false);   // first call of this mode eager: validates launches, sets function attributes
   } else {
-    if (!ex->graph_infer) {
+    if (!ig.exec) {
       cudaGraph_t g = nullptr;
       const int64_t before = lc.n;
       cudaStream_t cs = capture_stream();
@@ -1135,13 +1151,13 @@ void yb_handle::infer(const float* d_x, int B, int H, int W, int cross_class, in
       }
       YB_CHECK_CUDA(cudaStreamEndCapture(cs, &g));
       lc.n = before;
-      YB_CHECK_CUDA(cudaGraphInstantiate(&ex->graph_infer, g, 0));
+      YB_CHECK_CUDA(cudaGraphInstantiate(&ig.exec, g, 0));
       cudaGraphDestroy(g);
     }
-    YB_CHECK_CUDA(cudaGraphLaunch(ex->graph_infer, stream));
-    lc.n += (int64_t)ex->ops.size() + (cross_class == YB_NMS_CROSS_CLASS ? 2 : 3);
+    YB_CHECK_CUDA(cudaGraphLaunch(ig.exec, stream));
+    lc.n += (int64_t)ex->ops.size() + (dp.cross_class == YB_NMS_CROSS_CLASS ? 2 : 3);
   }
-  ex->infer_calls++;
+  ig.calls++;
   const void* src[6] = {ex->det_box, ex->det_coef, ex->det_cls, ex->det_score, ex->det_count, ex->proto};
   void* dst[6] = {d_box, d_coef_out, d_cls, d_score, d_count, d_proto};
   size_t bytes[6] = {(size_t)B * max_out * 16, (size_t)B * max_out * cfg.mask_dim * 4, (size_t)B * max_out * 8,

@@ -5,6 +5,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -78,12 +79,16 @@ struct Executor {
   int64_t* det_cls = nullptr;
   float* det_score = nullptr;
   int32_t* det_count = nullptr;
-  int det_max_out = 0;
-  int det_cross_class = -1;
-  // graphs
+  int det_cap = 0;               // rows per image the det_* buffers hold: max(nms_top_k, max_num_detections)
+  // graphs: one captured yb_infer graph per (nms mode + flags, max_out); the first call of a key runs eagerly
+  struct InferGraph {
+    cudaGraphExec_t exec = nullptr;
+    int calls = 0;
+  };
   cudaGraphExec_t graph_fwd = nullptr;
-  cudaGraphExec_t graph_infer = nullptr;
-  int fwd_calls = 0, infer_calls = 0;
+  std::map<int, InferGraph> infer_graphs;
+  int fwd_calls = 0;
+  void drop_detect_state();      // frees the Detect buffers and every captured yb_infer graph (Detect parameters changed)
   ~Executor();
 };
 
@@ -121,6 +126,11 @@ struct yb_handle {
   cudaStream_t lane_streams[8] = {};  // branch streams joined into the capture (parallel graph branches)
   cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
   bool multi_stream = true;           // YB_BRANCHES=0: capture a linear graph
+  // call serialisation (capi.cu CallGuard): host-side mutex + device-side ordering across caller streams
+  std::recursive_mutex mu;
+  cudaEvent_t ev_last = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool has_last = false;
   cudaStream_t capture_stream();
   ~yb_handle();
 

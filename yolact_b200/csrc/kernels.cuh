@@ -131,6 +131,7 @@ struct DetectParams {
   int max_dets = 100;
   int conf_is_logits = 0;
   int cross_class = 0;          // yb_nms_mode
+  int second_threshold = 0;     // fast_nms(second_threshold=True), detection.py:160-161
   float max_size = 550.f;       // cfg.max_size: box scale of traditional_nms (detection.py:194)
   int max_out = 100;
 };

@@ -747,9 +747,26 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
     if (bn_override == 32 || bn_override == 64 || bn_override == 128 || bn_override == 256)
       plan->BN = std::max(bn_override, bn_min);
   }
-  const int BN = plan->BN;
   // ---- CTA pairs: two adjacent M tiles per (cluster of 2), each CTA stages half of the weight tile
-  const int pair = (pair_override > 0 && m_tiles >= 2 && BN >= 64) ? 1 : 0;
+  const int pair = (pair_override > 0 && m_tiles >= 2 && plan->BN >= 64) ? 1 : 0;
+  int epi_req = (epi_override == 2 && plan->BN >= 64) ? 2 : 1;
+  if (split) {
+    // every stage and every epilogue buffer is twice as large: step down (second epilogue group first, then the
+    // N tile) until at least two pipeline stages fit
+    auto stages_for = [&](int bn, int hg) {
+      const int sb = 2 * (A_STAGE_BYTES + (pair ? bn / 2 : bn) * BLOCK_K * 2);
+      const int tiles = 2 * hg;
+      const int ob = std::max(tiles * A_STAGE_BYTES, hg == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES);
+      const int rb = (q.epi_tma && p.residual) ? tiles * A_STAGE_BYTES : 0;
+      return (221 * 1024 - ob - rb) / sb;
+    };
+    while (stages_for(plan->BN, epi_req) < 2) {
+      if (epi_req == 2) epi_req = 1;
+      else if (plan->BN > std::max(bn_min, pair ? 64 : 32)) plan->BN /= 2;
+      else break;
+    }
+  }
+  const int BN = plan->BN;
   plan->pair = pair;
   q.pair = pair;
   q.nb = Bv;
@@ -779,7 +796,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
     while (tc < q.acc_stages * BN) tc *= 2;
     q.tmem_cols = tc;
   }
-  plan->epi_groups = (epi_override == 2 && BN >= 64 && !pdlf) ? 2 : 1;
+  plan->epi_groups = (epi_req == 2 && !pdlf) ? 2 : 1;
   // staging: 2 x 16 KB tiles (one per group when there are two); the direct (fp32) epilogue needs a padded
   // 32x33 float transpose buffer per epilogue warp
   // (split: one buffer of two tiles per group)

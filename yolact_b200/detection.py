@@ -25,7 +25,11 @@ class Detect(object):
             raise ValueError('nms_threshold must be non negative.')  # detection.py:25-26
         self.conf_thresh = conf_thresh
         self.use_cross_class_nms = False
-        self.use_fast_nms = True   # eval.py:50,871 default; False -> traditional_nms (detection.py:182-228)
+        # The reference's attribute default is False (detection.py:30) but every caller sets it from --fast_nms, whose
+        # default is True (eval.py:50,871).  Same default as the reference class: a caller that bypasses eval.py gets
+        # traditional_nms, exactly as it would there.
+        self.use_fast_nms = False
+        self.second_threshold = False   # fast_nms(second_threshold=...) (detection.py:137,160-161); never set by eval.py
         self.max_num_detections = getattr(cfg, "max_num_detections", 100) if cfg is not None else 100
         self.mask_dim = getattr(cfg, "mask_dim", 32) if cfg is not None else 32
         self.max_size = getattr(cfg, "max_size", 550) if cfg is not None else 550   # traditional_nms box scale
@@ -61,7 +65,9 @@ class Detect(object):
             if self.use_cross_class_nms:
                 print('Warning: Cross Class Traditional NMS is not implemented.')
             return _lib.YB_NMS_TRADITIONAL
-        return _lib.YB_NMS_CROSS_CLASS if self.use_cross_class_nms else _lib.YB_NMS_FAST
+        if self.use_cross_class_nms:
+            return _lib.YB_NMS_CROSS_CLASS
+        return _lib.YB_NMS_FAST | (_lib.YB_NMS_FLAG_SECOND_THRESHOLD if self.second_threshold else 0)
 
     def detect_padded(self, loc, conf, mask, priors, conf_is_logits=False):
         """Fixed-size outputs, no host sync: (box [B,M,4], coef [B,M,k], cls [B,M] int64, score [B,M], count [B])."""
@@ -75,7 +81,7 @@ class Detect(object):
         mask = mask.contiguous().float()
         priors = priors.contiguous().float()
         mode = self.nms_mode()
-        cc = mode == _lib.YB_NMS_CROSS_CLASS
+        cc = (mode & 0xFF) == _lib.YB_NMS_CROSS_CLASS
         M = self.top_k if cc else self.max_num_detections
         box = torch.empty(B, M, 4, dtype=torch.float32, device=dev)
         coef = torch.empty(B, M, mask.shape[-1], dtype=torch.float32, device=dev)

@@ -222,6 +222,7 @@ class Yolact(nn.Module):
         self._handles = {}      # device index -> yb_handle
         self._version = 1       # bumped whenever the parameters may have changed
         self._pushed = {}       # device index -> version of the weights that handle holds
+        self._detect_pushed = {}  # device index -> (top_k, conf_thresh, nms_thresh, max_num_detections) the handle uses
 
     # ---- weights ---------------------------------------------------------------------------------
     def save_weights(self, path):
@@ -378,7 +379,14 @@ class Yolact(nn.Module):
             mode = self.detect.nms_mode()   # fast_nms | cc_fast_nms | traditional_nms (--fast_nms=False)
         else:
             mode = _lib.YB_NMS_CROSS_CLASS if cross_class else _lib.YB_NMS_FAST
-        M = c.nms_top_k if mode == _lib.YB_NMS_CROSS_CLASS else c.max_num_detections
+        # net.detect's attributes are live in the reference (detection.py:17-31): push them when they changed
+        d = self.detect
+        dkey = (int(d.top_k), float(d.conf_thresh), float(d.nms_thresh), int(d.max_num_detections))
+        idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+        if self._detect_pushed.get(idx) != dkey:
+            _lib.check(lib.yb_set_detect_params(h, *dkey), "yb_set_detect_params")
+            self._detect_pushed[idx] = dkey
+        M = dkey[0] if (mode & 0xFF) == _lib.YB_NMS_CROSS_CLASS else dkey[3]
         ph, pw = ctypes.c_int32(), ctypes.c_int32()
         _lib.check(lib.yb_proto_size(h, H, W, ctypes.byref(ph), ctypes.byref(pw)), "yb_proto_size")
         o = dict(device=x.device)
