@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define YB_ABI_VERSION 1
+#define YB_ABI_VERSION 2   /* 2: yb_config gained scales_f64 / ars_f64, YB_PREC_F16X3, yb_set_detect_params */
 
 #if defined(__GNUC__)
 #define YB_API __attribute__((visibility("default")))
@@ -122,6 +122,11 @@ typedef struct {
   float   nms_conf_thresh;     /* 0.05 */
   float   nms_thresh;          /* 0.5  */
   int32_t max_num_detections;  /* 100  */
+  /* The reference evaluates the anchors in Python doubles from the un-rounded config values and rounds to fp32 once at
+   * the end (yolact.py:224-246); YOLACT++'s scales 24 * 2^(j/3) are not fp32 numbers.  Non-zero entries here take
+   * precedence over scales[][] / ars[] so that the priors are bit-identical to the reference's for every config. */
+  double  scales_f64[5][4];
+  double  ars_f64[4];
 } yb_config;
 
 typedef struct yb_handle yb_handle;

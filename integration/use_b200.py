@@ -41,14 +41,26 @@ def install(reference_root, mask_iou_on_gpu=True):
         def __init__(self):
             super().__init__(from_reference_cfg(ref_data.cfg))
 
+    # cfg keys the reference's callers flip on the GLOBAL cfg between calls (prep_display sets rescore_bbox = True around
+    # postprocess, eval.py:147-151; --detect clears eval_mask_branch, eval.py:1074): the package snapshot would go stale,
+    # so they are re-read from the live reference cfg on every postprocess call.
+    live_keys = ("rescore_bbox", "rescore_mask", "eval_mask_branch", "mask_proto_debug")
+
+    def postprocess(*args, **kwargs):
+        for key in live_keys:
+            if hasattr(ref_data.cfg, key):
+                setattr(yolact_b200.cfg, key, getattr(ref_data.cfg, key))
+        return yolact_b200.postprocess(*args, **kwargs)
+    postprocess.__doc__ = yolact_b200.postprocess.__doc__
+
     ref_yolact.ReferenceYolact = ref_yolact.Yolact          # the PyTorch graph stays reachable
     ref_yolact.Yolact = Yolact
-    ref_output_utils.postprocess = yolact_b200.postprocess
+    ref_output_utils.postprocess = postprocess
     ref_aug.FastBaseTransform = FastBaseTransform
     if mask_iou_on_gpu:
         ref_box_utils.mask_iou = eval_utils.mask_iou
         ref_box_utils.jaccard = eval_utils.jaccard
-    return {"Yolact": Yolact, "postprocess": yolact_b200.postprocess, "FastBaseTransform": FastBaseTransform}
+    return {"Yolact": Yolact, "postprocess": postprocess, "FastBaseTransform": FastBaseTransform}
 
 
 if __name__ == "__main__":

@@ -168,6 +168,68 @@ def gen_network_case(tag, config_name, B, H, W, post_hw, seed=0, row_stride=1):
     npz_save(tag, **out)
 
 
+def gen_fullsize_case(tag, config_name, size, post_hw, seed=0, seed_x=99, head_stride=97, proto_stride=5):
+    """One FULL-SIZE image of a BASELINE.json config through the real reference: eval-mode `net(x)` (Detect with
+    fast_nms) + `postprocess` at `post_hw` (eval.py:949,266).  Kept small: the input is rebuilt from its seed, the raw
+    head tensors are row-subsampled, the prototypes spatially subsampled; the 100 detections and their bit-packed
+    masks are complete."""
+    from data.config import cfg, set_cfg
+    import yolact as ref_yolact
+    from layers.output_utils import postprocess
+    from oracle.weights import deterministic_state_dict, deterministic_input
+
+    set_cfg(config_name)
+    cfg.mask_proto_debug = False
+    net = ref_yolact.Yolact()
+    net.load_state_dict(deterministic_state_dict(net.state_dict(), seed))
+    net.detect.use_fast_nms = True
+    net.detect.use_cross_class_nms = False
+    x = deterministic_input(1, size, size, seed_x)
+    out = {"config": np.array(config_name), "seed": np.array(seed), "seed_x": np.array(seed_x), "size": np.array(size),
+           "post_hw": np.array(post_hw), "head_stride": np.array(head_stride), "proto_stride": np.array(proto_stride)}
+    with torch.no_grad():
+        net.train()
+        net.freeze_bn()
+        raw = net(x)
+        for k in ("loc", "conf", "mask"):
+            out["raw_" + k] = to_np(raw[k]).astype(np.float32)[:, ::head_stride]
+            out["raw_%s_absmax" % k] = np.array(float(raw[k].abs().max()))
+        out["raw_proto"] = to_np(raw["proto"]).astype(np.float32)[:, ::proto_stride, ::proto_stride]
+        out["raw_proto_absmax"] = np.array(float(raw["proto"].abs().max()))
+        out["raw_priors"] = to_np(raw["priors"]).astype(np.float32)
+        net.eval()
+        preds = net(x)
+    det = preds[0]["detection"]
+    assert det is not None
+    for k in ("box", "mask", "class", "score"):
+        out["det_" + k] = to_np(det[k])
+    ph, pw = post_hw
+    p2 = copy.deepcopy([{"detection": {k: v.clone() for k, v in det.items()}, "net": net}])
+    with torch.no_grad():
+        classes, scores, boxes, masks = postprocess(p2, pw, ph, batch_idx=0, crop_masks=True, score_threshold=0)
+    out["post_classes"] = to_np(classes)
+    if isinstance(scores, list):
+        out["post_scores"] = to_np(scores[0])
+        out["post_scores_maskiou"] = to_np(scores[1])
+    else:
+        out["post_scores"] = to_np(scores)
+    out["post_boxes"] = to_np(boxes)
+    out["post_masks_packed"] = np.packbits(to_np(masks).astype(np.uint8), axis=-1)
+    s = out["det_score"]
+    print(tag, config_name, "P =", raw["loc"].shape[1], "detections:", len(s), "scores %.4f .. %.4f" % (s[0], s[-1]),
+          "min gap between consecutive scores %.2e" % float(np.min(-np.diff(s))) if len(s) > 1 else "")
+    npz_save(tag, **out)
+
+
+FULL_CASES = [  # BASELINE.json configs 2-5 (+ the 640x480 postprocess target of eval.py:266)
+    ("full_base_550", "yolact_base_config", 550, (550, 550)),
+    ("full_base_550_to_480x640", "yolact_base_config", 550, (480, 640)),
+    ("full_plus_resnet50_550", "yolact_plus_resnet50_config", 550, (550, 550)),
+    ("full_im700_700", "yolact_im700_config", 700, (700, 700)),
+    ("full_plus_base_550", "yolact_plus_base_config", 550, (550, 550)),
+]
+
+
 def gen_detect_unit(seed=3):
     """Synthetic pred_outs straight into the reference Detect (fast_nms and cc_fast_nms)."""
     from data.config import cfg, set_cfg
@@ -419,6 +481,9 @@ if __name__ == "__main__":
         gen_dcn_unit()
     if "units" in which or "eval" in which:
         gen_eval_unit()
+    if "full" in which:
+        for tag, name, size, post in FULL_CASES:
+            gen_fullsize_case(tag, name, size, post)
     if "nets" in which:
         gen_network_case("net_resnet50_160", "yolact_resnet50_config", 1, 160, 160, (120, 150))
         gen_network_case("net_base_192x160_b2", "yolact_base_config", 2, 192, 160, (100, 100))

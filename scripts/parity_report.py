@@ -37,7 +37,7 @@ def main():
     from yolact_b200.config import CONFIGS
     rows = []
     sel = [int(i) for i in a.cases.split(",")] if a.cases else range(len(CASES))
-    print("| config | size | B | out | mode | raw loc | raw conf | raw coef | raw proto | cls ids equal | keep-set | max dbox | max dscore | mask flips |")
+    print("| config | size | B | out | mode | raw loc | raw conf | raw coef | raw proto | cls ids equal (strict / mod ties<2e-5) | keep-set | max dbox | max dscore | mask flips |")
     print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
     for ci in sel:
         name, size, batch, out_hw = CASES[ci]
@@ -50,7 +50,7 @@ def main():
             f = lambda v: "-" if v is None else ("%.2e" % v)
             print("| %s | %d | %d | %dx%d | %s | %s | %s | %s | %s | %s (%d/%d) | %s | %s | %s | %s |" % (
                 cfg.name, size, batch, out_hw[0], out_hw[1], prec, f(r["raw_loc"]), f(r["raw_conf"]), f(r["raw_mask"]),
-                f(r["raw_proto"]), r["class_ids_equal"], r["class_ids_equal_images"], r["images"],
+                f(r["raw_proto"]), "%s / %s" % (r["class_ids_equal_strict"], r["class_ids_equal"]), r["class_ids_equal_images"], r["images"],
                 f(r["keep_set_agreement_min"]), f(r["max_abs_dbox"]), f(r["max_abs_dscore"]),
                 f(r["mask_pixel_mismatch_max"])), flush=True)
     if a.out:

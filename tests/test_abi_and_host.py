@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), "library does not export %s" % s
     # and the ctypes table covers exactly the header
     assert sorted(_lib.SIGNATURES) == syms
-    assert _lib.load().yb_abi_version() == 1
+    assert _lib.load().yb_abi_version() == 2
 
 
 def test_config_struct_matches_header_layout():
@@ -97,8 +97,7 @@ def test_no_cpu_fallback_for_the_row_ops():
                  lambda: E.display_blend(torch.zeros(4, 4, 3), m, [[0, 0, 0]] * 2)):
         with pytest.raises(_lib.YbError):
             call()
-    with pytest.raises(NotImplementedError):
-        E.prep_display([], torch.zeros(4, 4, 3), 4, 4, undo_transform=True)
+    assert not hasattr(E, "prep_display")   # caller code (eval.py:135-262) is not rebuilt; only its blend is
 
 
 def test_detect_nms_mode_follows_the_eval_flags():

@@ -53,6 +53,41 @@ def test_detect_and_postprocess_match_reference(case):
         assert (masks != ref).mean() < 1e-4                                   # binarised: a few ulp-level flips at most
 
 
+@pytest.mark.parametrize("tag", ["full_base_550_to_480x640", "full_plus_resnet50_550", "full_im700_700"])
+def test_oracle_matches_reference_at_full_size(tag):
+    """BASELINE.json configs at FULL resolution (550 / 700 px, DCN at C = 128..512, 640x480 postprocess target): the
+    oracle's whole pipeline against the real reference's outputs.  Ranks may swap only between scores closer than
+    2e-5 (fp32 summation order decides those in any implementation; torch's own CPU conv is not bit-reproducible
+    across thread counts)."""
+    from oracle import torch_port as T
+    from oracle.weights import deterministic_input
+    from tests.fullsize_golden import load_case, raw_errors
+    from tests.parity_utils import align
+    import yolact_b200
+    g, cfg, ref, (ph, pw) = load_case(tag)
+    sd = deterministic_state_dict(yolact_b200.Yolact(cfg).state_dict(), int(g["seed"]))
+    orc = O.ConvStackOracle(cfg, sd)
+    x = deterministic_input(1, int(g["size"]), int(g["size"]), int(g["seed_x"]))
+    raw = orc.forward(x)
+    e = raw_errors({k: v.numpy() for k, v in raw.items()}, g)
+    assert e["priors_equal"]
+    for k in ("loc", "conf", "mask", "proto"):
+        assert e[k] < 5e-5, (k, e[k])
+    det = T.detect_one(raw["loc"][0], torch.softmax(raw["conf"], -1)[0], raw["mask"][0], raw["priors"],
+                       cfg.nms_conf_thresh, cfg.nms_thresh, cfg.nms_top_k, cfg.max_num_detections)
+    det["proto"] = raw["proto"][0]
+    box_rel = det["box"].clone().numpy()
+    classes, scores, boxes, masks = T.postprocess_one(det, pw, ph, maskiou_fn=orc.maskiou if cfg.use_maskiou else None)
+    got = {"class": classes.numpy(), "score": (scores[0] if isinstance(scores, list) else scores).numpy(), "box": box_rel}
+    perm, ok = align(got, ref)
+    assert ok, "class ids differ beyond score ties"
+    assert np.abs(got["box"][perm] - ref["box"]).max() < 1e-5 and np.abs(got["score"][perm] - ref["score"]).max() < 1e-5
+    assert np.abs(boxes.numpy()[perm] - ref["box_px"]).max() <= 1
+    assert ((masks.numpy()[perm] > 0.5) != ref["masks"]).mean() < 1e-4
+    if ref["score_maskiou"] is not None:
+        np.testing.assert_allclose(scores[1].numpy()[perm], ref["score_maskiou"], rtol=1e-3, atol=1e-5)
+
+
 def test_detect_unit_fast_and_cross_class():
     g = load_golden("detect_unit")
     for b in range(2):

@@ -35,6 +35,8 @@ class YbConfig(ctypes.Structure):
         ("nms_conf_thresh", c_float),
         ("nms_thresh", c_float),
         ("max_num_detections", c_int32),
+        ("scales_f64", (ctypes.c_double * 4) * 5),
+        ("ars_f64", ctypes.c_double * 4),
     ]
 
 
@@ -112,7 +114,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.yb_abi_version() != 1:
+    if lib.yb_abi_version() != 2:
         raise YbError("yolact_b200: ABI version mismatch")
     _lib = lib
     return lib

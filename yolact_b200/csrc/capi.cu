@@ -74,7 +74,7 @@ __global__ void pack_w_dcn_tc_split_kernel(const float* __restrict__ w, __half* 
     int c = (int)(r % Ci);
     int o = (int)(r / Ci);
     __half hi, lo;
-    split_f32(w[i] * up, hi, lo);
+    split_w_f32(w[i] * up, hi, lo);
     out[(int64_t)o * 2 * K + (int64_t)t * Ci + c] = hi;
     out[(int64_t)o * 2 * K + K + (int64_t)t * Ci + c] = lo;
   }

@@ -150,8 +150,8 @@ std::vector<float> make_priors_host(const yb_config& cfg, const int level_hw[5][
         const double y = (j + 0.5) / ch;
         for (int s = 0; s < cfg.num_scales; ++s)
           for (int a = 0; a < cfg.num_ars; ++a) {
-            const double scale = (double)cfg.scales[l][s];
-            const double ar = sqrt((double)cfg.ars[a]);  // preapply_sqrt == False
+            const double scale = cfg.scales_f64[l][s] != 0.0 ? cfg.scales_f64[l][s] : (double)cfg.scales[l][s];
+            const double ar = sqrt(cfg.ars_f64[a] != 0.0 ? cfg.ars_f64[a] : (double)cfg.ars[a]);  // preapply_sqrt == False
             const double w = scale * ar / cfg.max_size;  // use_pixel_scales
             double hgt = scale / ar / cfg.max_size;
             if (cfg.use_square_anchors) hgt = w;

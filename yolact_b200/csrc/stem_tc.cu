@@ -90,7 +90,8 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
           const int atom = j >> 2, kk = j & 3;
           const uint64_t da = make_sw128_desc(smem_u32(sA + (pa * ATOMS + atom) * A_ATOM_BYTES)) + (uint64_t)(2 * kk);
           const uint64_t db = make_sw128_desc(smem_u32(sB + (pb * ATOMS + atom) * B_ATOM_BYTES)) + (uint64_t)(2 * kk);
-          umma_f16(tmem_base, da, db, p.idesc, (pass > 0 || j > 0) ? 1u : 0u);
+          // the lo plane of the patch is bf16 (common.cuh): a_format = 1 for the lo * hi pass
+          umma_f16(tmem_base, da, db, pa ? (p.idesc | (1u << 7)) : p.idesc, (pass > 0 || j > 0) ? 1u : 0u);
         }
       }
       umma_commit(&tmem_full);
@@ -139,7 +140,7 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
         h2[j2] = __halves2half2(from_f32<__half>(v[0]), from_f32<__half>(v[1]));
         if (SPLIT) {
           const float2 hf = __half22float2(h2[j2]);
-          l2[j2] = __floats2half2_rn(fabsf(v[0]) > 65504.f ? 0.f : v[0] - hf.x, fabsf(v[1]) > 65504.f ? 0.f : v[1] - hf.y);
+          l2[j2] = lo2_from_f32(fabsf(v[0]) > 65504.f ? 0.f : v[0] - hf.x, fabsf(v[1]) > 65504.f ? 0.f : v[1] - hf.y);   // bf16
         }
       }
       const int atom = kg >> 3;
@@ -178,7 +179,7 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
           o2[j] = __halves2half2(from_f32<__half>(v0), from_f32<__half>(v1));
           if (SPLIT) {
             const float2 hf = __half22float2(o2[j]);
-            ol2[j] = __floats2half2_rn(fabsf(v0) > 65504.f ? 0.f : v0 - hf.x, fabsf(v1) > 65504.f ? 0.f : v1 - hf.y);
+            ol2[j] = lo2_from_f32(fabsf(v0) > 65504.f ? 0.f : v0 - hf.x, fabsf(v1) > 65504.f ? 0.f : v1 - hf.y);   // bf16
           }
         }
         reinterpret_cast<uint4*>(yrow + c0)[q] = o;

@@ -166,7 +166,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1
         const __half2* l2 = reinterpret_cast<const __half2*>(&rawl);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(l2[j]);
+          const float2 f = lo2_to_f32(l2[j]);   // lo plane: bf16
           v[2 * j] += f.x;
           v[2 * j + 1] += f.y;
         }
@@ -190,7 +190,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1
         // hi saturates at +-65504; the residual of a saturated value is dropped (lo = 0 keeps hi + lo finite)
         const float l0 = fabsf(v[2 * j]) > 65504.f ? 0.f : v[2 * j] - hf.x;
         const float l1 = fabsf(v[2 * j + 1]) > 65504.f ? 0.f : v[2 * j + 1] - hf.y;
-        l2[j] = __floats2half2_rn(l0, l1);
+        l2[j] = lo2_from_f32(l0, l1);          // lo plane: bf16 (see common.cuh)
       }
       *reinterpret_cast<uint4*>(out_tile + A_STAGE_BYTES + off) = ol;
     }
@@ -371,7 +371,9 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             const uint64_t dal = make_sw128_desc(sa + A_STAGE_BYTES);
             const uint64_t dbl = make_sw128_desc(sb + B_PLANE_BYTES);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) mma(dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), 1u);   // A_lo * W_hi
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // A_lo (bf16) * W_hi (fp16): a_format = 1 in the instruction descriptor
+              if (PAIR) umma_f16_pair(tmem_d, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc | (1u << 7), 1u);
+              else umma_f16(tmem_d, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc | (1u << 7), 1u);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) mma(da + (uint64_t)(2 * k), dbl + (uint64_t)(2 * k), 1u);   // A_hi * W_lo
           }
@@ -549,7 +551,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             if (has_res) {
               const __half* rp = p.residual + ((long long)b * p.res_batch_stride + pix * p.Cout) * NPL + nbase + lane;
               rsd = __half2float(rp[0]);
-              if (SPLIT) rsd += __half2float(rp[p.Cout]);
+              if (SPLIT) rsd += lo_to_f32(rp[p.Cout]);
             }
             if (!raa) v += rsd;
             v = (act == ACT_RELU) ? fmaxf(v, 0.f) : (act == ACT_TANH) ? tanhf(v) : (act == ACT_LEAKY) ? (v > 0.f ? v : 0.1f * v) : v;
@@ -804,6 +806,10 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   const int out_bytes = std::max(epi_tiles * A_STAGE_BYTES, plan->epi_groups == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES);
   const int res_bytes = (q.epi_tma && p.residual) ? epi_tiles * A_STAGE_BYTES : 0;
   int stages = std::min(MAX_STAGES, ((pdlf ? 108 : (split ? 221 : 200)) * 1024 - out_bytes - res_bytes) / stage_bytes);
+  if (stages < 1 && pdlf) {   // does not fit in half an SM: an ordinary plan
+    plan->pdl_friendly = 0;
+    stages = std::min(MAX_STAGES, (200 * 1024 - out_bytes - res_bytes) / stage_bytes);
+  }
   YB_REQUIRE(stages >= 1, "tc_conv: tile does not fit in shared memory");
   if (stages_override > 0) stages = std::min(stages, stages_override);
   stages = std::max(1, std::min(stages, q.ntaps * q.kchunks * tiles_per_cta));
@@ -811,7 +817,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   q.out_off = stages * stage_bytes;
   q.res_off = q.out_off + out_bytes;
   plan->smem_bytes = (size_t)q.res_off + res_bytes + 1024;
-  if (pdlf && plan->smem_bytes > (size_t)112 * 1024) plan->pdl_friendly = 0;   // does not fit twice: plain plan
+  if (plan->pdl_friendly && plan->smem_bytes > (size_t)112 * 1024) plan->pdl_friendly = 0;   // does not fit twice: plain plan
   q.pdl = plan->pdl_friendly;
   if (pair) plan->smem_bytes = std::max(plan->smem_bytes, (size_t)120 * 1024);   // at most one pair CTA per SM
   plan->grid = dim3((unsigned)(pair ? 2 * grid : grid), 1, 1);

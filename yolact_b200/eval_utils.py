@@ -3,7 +3,11 @@
     mask_iou(masks_a, masks_b, iscrowd=False)      <- layers/box_utils.py:98-113  (eval.py:435 _mask_iou)
     jaccard(box_a, box_b, iscrowd=False)           <- layers/box_utils.py:54-79   (eval.py:442 _bbox_iou)
     encode_masks(masks)                            <- pycocotools.mask.encode in Detections.add_mask (eval.py:320-330)
-    prep_display(dets_out, img, h, w, undo_transform=False, ...)   <- eval.py:135-262
+    display_blend(img, masks, colors, alpha)       <- the GPU mask blend inside prep_display (eval.py:186-209,226)
+    get_color(j, classes, class_color)             <- prep_display's palette lookup (eval.py:169-183)
+
+prep_display itself (top-k selection, OpenCV text and boxes, eval.py:135-262) is caller code and is NOT rebuilt: the
+caller keeps its own loop and replaces the ten ATen ops of the blend by `display_blend`.
 
 The reference multiplies two dense float matrices for the mask IoU and ships fp32 masks over PCIe for the RLE;
 here masks are 1 bit per pixel on the GPU (32x fewer bytes), the IoU is AND + popcount, and only the run
@@ -143,9 +147,9 @@ def encode_masks(masks, mask_format=None, w=None):
     return [{"size": [h, int(w)], "counts": rle_to_string(r)} for r in runs]
 
 
-# ---- prep_display ------------------------------------------------------------------------------------------
-def _get_color(j, classes, class_color, bgr):
-    # eval.py:169-183
+# ---- the mask blend of prep_display ------------------------------------------------------------------------
+def get_color(j, classes, class_color=False, bgr=True):
+    """eval.py:169-183: colour of the j-th drawn detection, as 0..255 ints (BGR like the frame unless bgr=False)."""
     colors = _config.COLORS
     idx = (int(classes[j]) * 5 if class_color else j * 5) % len(colors)
     c = colors[idx]
@@ -173,60 +177,3 @@ def display_blend(img, masks, colors, mask_alpha=0.45, img_is_255=True, mask_for
                                     wi, _lib.ptr(col), float(mask_alpha), _lib.ptr(out), _lib.current_stream(img.device)),
                "yb_display_blend")
     return out
-
-
-def prep_display(dets_out, img, h, w, undo_transform=False, class_color=False, mask_alpha=0.45, fps_str='',
-                 top_k=5, score_threshold=0, display_masks=True, display_text=True, display_bboxes=True,
-                 display_scores=True, crop=True, class_names=None):
-    """eval.py:135-262 for the production callers (evalimage :600, evalvideo :712: undo_transform=False,
-    img = the BGR frame [h,w,3] float 0..255 on the GPU).  The keyword defaults are eval.py's argparse defaults.
-    Masks are drawn by one kernel; text and boxes, like the reference, on the CPU with OpenCV (skipped when cv2
-    is not importable)."""
-    if undo_transform:
-        raise NotImplementedError("prep_display(undo_transform=True) is the dataset-visualisation path "
-                                  "(CPU numpy + cv2.resize in the reference, eval.py:140-142); out of scope")
-    cfg = _config.cfg
-    h, w = int(img.shape[0]), int(img.shape[1])
-    save = cfg.rescore_bbox
-    cfg.rescore_bbox = True                                   # eval.py:148-149
-    try:
-        t = postprocess(dets_out, w, h, crop_masks=crop, score_threshold=score_threshold, mask_format="u8")
-    finally:
-        cfg.rescore_bbox = save
-    if t[0].numel() == 0:
-        n_consider, masks, classes, scores, boxes = 0, None, None, None, None
-    else:
-        idx = t[1].argsort(0, descending=True)[:top_k]        # eval.py:156
-        masks = t[3][idx] if cfg.eval_mask_branch else None
-        classes, scores, boxes = [x[idx].cpu().numpy() for x in t[:3]]
-        n_consider = min(top_k, classes.shape[0])
-        for j in range(n_consider):
-            if scores[j] < score_threshold:
-                n_consider = j
-                break
-    if display_masks and cfg.eval_mask_branch and n_consider > 0:
-        colors = [[c / 255.0 for c in _get_color(j, classes, class_color, bgr=True)] for j in range(n_consider)]
-        out = display_blend(img, masks[:n_consider], colors, mask_alpha)
-    else:
-        out = display_blend(img, None, None, mask_alpha)
-    img_numpy = out.cpu().numpy()
-    if n_consider == 0 or not (display_text or display_bboxes):
-        return img_numpy
-    try:
-        import cv2
-    except ImportError:
-        return img_numpy
-    names = class_names if class_names is not None else getattr(cfg, "class_names", None)
-    face, fscale, thick = cv2.FONT_HERSHEY_DUPLEX, 0.6, 1
-    for j in reversed(range(n_consider)):                     # eval.py:233-259
-        x1, y1, x2, y2 = (int(v) for v in boxes[j, :])
-        color = _get_color(j, classes, class_color, bgr=True)
-        if display_bboxes:
-            cv2.rectangle(img_numpy, (x1, y1), (x2, y2), color, 1)
-        if display_text:
-            name = names[classes[j]] if names is not None else str(int(classes[j]))
-            text = '%s: %.2f' % (name, scores[j]) if display_scores else name
-            tw, th = cv2.getTextSize(text, face, fscale, thick)[0]
-            cv2.rectangle(img_numpy, (x1, y1), (x1 + tw, y1 - th - 4), color, -1)
-            cv2.putText(img_numpy, text, (x1, y1 - 3), face, fscale, [255, 255, 255], thick, cv2.LINE_AA)
-    return img_numpy

@@ -169,9 +169,11 @@ def make_yb_config(c, precision):
     for l in range(5):
         for s, v in enumerate(c.pred_scales[l]):
             yc.scales[l][s] = float(v)
+            yc.scales_f64[l][s] = float(v)     # un-rounded: the reference computes the anchors in doubles
     yc.num_ars = len(c.pred_aspect_ratios)
     for i, v in enumerate(c.pred_aspect_ratios):
         yc.ars[i] = float(v)
+        yc.ars_f64[i] = float(v)
     yc.use_square_anchors = 1 if c.use_square_anchors else 0
     yc.use_maskiou = 1 if c.use_maskiou else 0
     yc.precision = precision
