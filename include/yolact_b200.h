@@ -247,6 +247,13 @@ YB_API int yb_box_iou(yb_handle* h, const float* d_a, int n, const float* d_b, i
 YB_API int yb_mask_rle(yb_handle* h, const void* d_masks, int mask_format, int n, int mask_h, int mask_w,
                        uint32_t* d_counts, int64_t cap, int32_t* d_nruns, void* stream);
 
+/* Multi-GPU detection gather (the analogue of CustomDataParallel.gather, eval.py:630-634): packs yb_infer / yb_detect's
+ * padded outputs of B images into one fp32 record per image, d_rec [B, 1 + M*(6+k)] =
+ * [count, cls[M], score[M], box[M*4], coef[M*k]], so that a global batch needs ONE all_gather (NCCL, by the caller). */
+YB_API int yb_pack_detections(yb_handle* h, const float* d_box, const float* d_coef, const int64_t* d_cls,
+                              const float* d_score, const int32_t* d_count, int B, int M, int k, float* d_rec,
+                              void* stream);
+
 /* prep_display's mask blend: d_img [h,w,3] fp32 (0..255 when img_is_255, else 0..1), n masks in
  * `mask_format` in drawing order, d_colors [n,3] fp32 0..1, alpha = mask_alpha ->
  * d_out [h,w,3] uint8 = (blend * 255).byte()  (eval.py:186-209,226). */

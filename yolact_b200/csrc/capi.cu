@@ -180,8 +180,9 @@ int yb_create(const yb_config* cfg, int device, yb_handle** out) {
   if (const char* at = getenv("YB_AUTOTUNE")) h->autotune = (atoi(at) != 0);
   if (const char* pc = getenv("YB_PAIR")) h->pair_candidates = (atoi(pc) != 0);
   if (const char* ec = getenv("YB_EPI2")) h->epi2_candidates = (atoi(ec) != 0);
-  if (const char* sw = getenv("YB_STEM_WG")) h->stem_wg = atoi(sw) == 2 ? 2 : 1;
+  if (const char* sw = getenv("YB_STEM_WG")) h->stem_wg = atoi(sw) == 2 ? 2 : 1;   // default 0: per precision mode
   if (const char* st = getenv("YB_STEM_TC")) h->stem_on_tc = (atoi(st) != 0);
+  if (const char* df = getenv("YB_DCN_FUSED")) h->dcn_fused = (atoi(df) != 0);
   if (const char* pd = getenv("YB_PDL")) h->pdl = (atoi(pd) != 0);
   if (const char* fh = getenv("YB_FUSE_HEADS")) h->fuse_heads = (atoi(fh) != 0);
   if (const char* br = getenv("YB_BRANCHES")) h->multi_stream = (atoi(br) != 0);
@@ -515,6 +516,16 @@ int yb_mask_rle(yb_handle* h, const void* d_masks, int mask_format, int n, int m
   YB_API_END
 }
 
+int yb_pack_detections(yb_handle* h, const float* d_box, const float* d_coef, const int64_t* d_cls, const float* d_score,
+                       const int32_t* d_count, int B, int M, int k, float* d_rec, void* stream) {
+  YB_API_BEGIN
+  YB_REQUIRE(h && d_box && d_coef && d_cls && d_score && d_count && d_rec, "yb_pack_detections: null argument");
+  YB_REQUIRE(B >= 0 && M >= 1 && k >= 1, "yb_pack_detections: bad sizes");
+  CallGuard g(h);
+  launch_pack_detections(d_box, d_coef, d_cls, d_score, d_count, B, M, k, d_rec, (cudaStream_t)stream, &h->lc);
+  YB_API_END
+}
+
 int yb_display_blend(yb_handle* h, const float* d_img, int img_is_255, const void* d_masks, int mask_format, int n,
                      int img_h, int img_w, const float* d_colors, float alpha, uint8_t* d_out, void* stream) {
   YB_API_BEGIN
@@ -583,6 +594,20 @@ int yb_dcn_forward(yb_handle* h, const float* d_input, const float* d_weight, co
         pack_w_dcn_tc_kernel<<<grid1d(wn), 256, 0, s>>>(d_weight, wk, Co, C, 9);
       }
       YB_CHECK_LAUNCH();
+      if (h->dcn_fused && dcn_tc_supported(C, Co)) {
+        DcnTcPlan* dp = dcn_tc_plan_create(x, om, wk, d_bias, y, B, H, W, C, Ho, Wo, Co, stride_h, pad_h, dilation_h,
+                                           ACT_NONE, 0, sp, out_scale);
+        try {
+          launch_dcn_tc(dp, s, &h->lc);
+        } catch (...) {
+          dcn_tc_plan_destroy(dp);
+          throw;
+        }
+        dcn_tc_plan_destroy(dp);
+        launch_nhwc_to_nchw_f32<__half>(y, d_output, B, Ho, Wo, Co, s, &h->lc, sp);
+        YB_CHECK_CUDA(cudaStreamSynchronize(s));
+        return YB_OK;
+      }
       launch_dcn_gather_f16(x, om, cols, B, H, W, C, Ho, Wo, stride_h, pad_h, dilation_h, 0, s, &h->lc, sp);
       ConvProblem p;
       p.B = B;

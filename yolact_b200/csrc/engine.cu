@@ -47,6 +47,7 @@ Executor::~Executor() {
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (auto* p : plans) tc_conv_plan_destroy(p);
   for (auto* p : stem_plans) stem_tc_plan_destroy(p);
+  for (auto* p : dcn_plans) dcn_tc_plan_destroy(p);
   for (void* p : allocs) cudaFree(p);
 }
 
@@ -265,9 +266,9 @@ struct NetBuilder {
     if (stem_tc) {
       StemTcPlan* sp = stem_tc_plan_create((const float*)in.ptr, w.w_tc, w.bias, (__half*)out.ptr, in.B, in.H, in.W, k,
                                            stride, pad, w.Cout, act, split ? 1 : 0, w.out_scale);
-      stem_tc_plan_set_worker_groups(sp, h->stem_wg);
+      stem_tc_plan_set_worker_groups(sp, h->stem_wg > 0 ? h->stem_wg : (split ? 2 : 1));
       ex->stem_plans.push_back(sp);
-      op.name += h->stem_wg == 2 ? " stem wg=2" : " stem";
+      op.name += (h->stem_wg > 0 ? h->stem_wg : (split ? 2 : 1)) == 2 ? " stem wg=2" : " stem";
       op.fn = [sp, lc](cudaStream_t s) { launch_stem_tc(sp, s, lc); };
       push(op);
       return out;
@@ -359,6 +360,18 @@ struct NetBuilder {
         launch_dcn_simt<float>((const float*)in.ptr, (const float*)om.ptr, wp, bias, (float*)out.ptr, in.B, in.H, in.W,
                                in.C, out.H, out.W, Cout, stride, 1, 1, ACT_RELU, 1, s, lc);
       };
+      push(op);
+    } else if (h->dcn_fused && dcn_tc_supported(in.C, w.Cout)) {
+      // one kernel: warp-shuffled tap geometry -> bilinear samples straight into the swizzled A stage -> tcgen05
+      const int sp = in.split ? 1 : 0;
+      DcnTcPlan* dp = dcn_tc_plan_create((const __half*)in.ptr, (const float*)om.ptr, w.w_tc, w.bias, (__half*)out.ptr, in.B,
+                                         in.H, in.W, in.C, Ho, Wo, w.Cout, stride, 1, 1, ACT_RELU, 1, sp, w.out_scale);
+      ex->dcn_plans.push_back(dp);
+      Op op;
+      op.is_conv = true;
+      op.name = key + " dcn_fused " + std::to_string(in.C) + "->" + std::to_string(w.Cout) + " k3s" + std::to_string(stride) +
+                " " + std::to_string(Ho) + "x" + std::to_string(Wo);
+      op.fn = [dp, lc](cudaStream_t s) { launch_dcn_tc(dp, s, lc); };
       push(op);
     } else {
       // gather -> fp16 columns [B,Ho,Wo,9C]; contraction = 1x1 conv with K = 9C on tcgen05

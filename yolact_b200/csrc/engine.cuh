@@ -59,6 +59,7 @@ struct Executor {
   std::vector<void*> allocs;
   std::vector<TcConvPlan*> plans;
   std::vector<StemTcPlan*> stem_plans;
+  std::vector<DcnTcPlan*> dcn_plans;
   std::vector<Op> ops;           // the conv stack (yb_forward)
   size_t fork_index = 0;         // ops[fork_index..] may run on their lanes concurrently (0 = no fork)
   float* d_in = nullptr;         // NCHW fp32 copy of the input (stable address for graph replay)
@@ -104,7 +105,8 @@ struct yb_handle {
   bool fuse_heads = true;   // YB_FUSE_HEADS=0: three separate head convs per level
   bool pdl = false;         // YB_PDL=1: programmatic dependent launch between consecutive tcgen05 convs
   bool stem_on_tc = true;   // YB_STEM_TC=0 falls back to the SIMT stem
-  int stem_wg = 1;          // YB_STEM_WG=2: two worker threads per output pixel in the 7x7 stem (measured slower: 0.176 vs 0.154 ms)
+  bool dcn_fused = true;    // YB_DCN_FUSED=0: separate gather kernel + fp16 column buffer + 1x1 tcgen05 contraction (round 1)
+  int stem_wg = 0;          // YB_STEM_WG=1|2: worker threads per output pixel in the 7x7 stem; 0 = 1 (f16: 2 measured slower, 0.176 vs 0.154 ms), 2 in the split mode
   bool autotune = true;     // YB_AUTOTUNE=0 disables plan-time autotuning of the tcgen05 tiles
   bool pair_candidates = true;    // YB_PAIR=0: the autotuner skips CTA-pair (cta_group::2) plans
   bool epi2_candidates = true;    // YB_EPI2=0: the autotuner skips plans with two epilogue groups (320 threads)

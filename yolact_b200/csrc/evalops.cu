@@ -393,6 +393,36 @@ void launch_mask_rle(const void* masks, int mask_format, int n, int h, int w, ui
   if (lc) lc->n++;
 }
 
+// ---- detection records for the multi-GPU gather (yolact_b200/parallel.py) ---------------------------------------------
+// rec[b] = [count, cls[M], score[M], box[M*4], coef[M*k]] as fp32 (class ids < 2^24 and counts are exact in fp32):
+// one fixed-size row per image, so that the only data-path collective of a global batch is ONE all_gather.
+__global__ void __launch_bounds__(256)
+pack_detections_kernel(const float* __restrict__ box, const float* __restrict__ coef, const int64_t* __restrict__ cls,
+                       const float* __restrict__ score, const int32_t* __restrict__ count, int M, int k,
+                       float* __restrict__ rec) {
+  const int b = blockIdx.x;
+  const int L = 1 + M * (6 + k);
+  float* r = rec + (int64_t)b * L;
+  const float* bb = box + (int64_t)b * M * 4;
+  const float* cc = coef + (int64_t)b * M * k;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    float v;
+    if (i == 0) v = (float)count[b];
+    else if (i < 1 + M) v = (float)cls[(int64_t)b * M + (i - 1)];
+    else if (i < 1 + 2 * M) v = score[(int64_t)b * M + (i - 1 - M)];
+    else if (i < 1 + 6 * M) v = bb[i - 1 - 2 * M];
+    else v = cc[i - 1 - 6 * M];
+    r[i] = v;
+  }
+}
+void launch_pack_detections(const float* box, const float* coef, const int64_t* cls, const float* score,
+                            const int32_t* count, int B, int M, int k, float* rec, cudaStream_t stream, LaunchCounter* lc) {
+  if (B <= 0) return;
+  pack_detections_kernel<<<B, 256, 0, stream>>>(box, coef, cls, score, count, M, k, rec);
+  YB_CHECK_LAUNCH();
+  if (lc) lc->n++;
+}
+
 void launch_display_blend(const float* img, int img_is_255, const void* masks, int mask_format, int n, int h, int w,
                           const float* colors, float alpha, uint8_t* out, cudaStream_t stream, LaunchCounter* lc) {
   YB_REQUIRE(h > 0 && w > 0 && h <= 65535, "display_blend: bad image size");

@@ -161,6 +161,8 @@ void launch_box_iou(const float* a, int n, const float* b, int m, int iscrowd, f
                     LaunchCounter* lc);
 void launch_mask_rle(const void* masks, int mask_format, int n, int h, int w, uint32_t* counts, int64_t cap,
                      int32_t* nruns, cudaStream_t stream, LaunchCounter* lc);
+void launch_pack_detections(const float* box, const float* coef, const int64_t* cls, const float* score,
+                            const int32_t* count, int B, int M, int k, float* rec, cudaStream_t stream, LaunchCounter* lc);
 void launch_display_blend(const float* img, int img_is_255, const void* masks, int mask_format, int n, int h, int w,
                           const float* colors, float alpha, uint8_t* out, cudaStream_t stream, LaunchCounter* lc);
 
@@ -177,5 +179,16 @@ void launch_dcn_simt(const T* x, const float* om, const T* w, const float* bias,
 void launch_dcn_gather_f16(const __half* x, const float* om, __half* cols, int B, int H, int W,
                            int C, int Ho, int Wo, int stride, int pad, int dil, int mask_logits,
                            cudaStream_t stream, LaunchCounter* lc, int split = 0);
+
+// ---- fused DCNv2 on tcgen05 (dcn_tc.cu): gather -> smem A stage -> MMA -> bias/act, no column buffer ----------------
+struct DcnTcPlan;
+bool dcn_tc_supported(int C, int Cout);
+// x NHWC half [B,H,W,C] (split: [.., hi(C) | lo(C)]), om fp32 [B,Ho,Wo,27], w_packed [Cout][9*C] half with k = tap*C + c
+// (split: [Cout][hi(9C) | lo(9C)] scaled by 1 / out_scale), y NHWC half [B,Ho,Wo,Cout] (split: pairs).
+DcnTcPlan* dcn_tc_plan_create(const __half* x, const float* om, const __half* w_packed, const float* bias, __half* y, int B,
+                              int H, int W, int C, int Ho, int Wo, int Cout, int stride, int pad, int dil, int act,
+                              int mask_logits, int split = 0, float out_scale = 1.f, int bn_override = 0);
+void dcn_tc_plan_destroy(DcnTcPlan* plan);
+void launch_dcn_tc(const DcnTcPlan* plan, cudaStream_t stream, LaunchCounter* lc);
 
 }  // namespace yb

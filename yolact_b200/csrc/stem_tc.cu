@@ -260,7 +260,11 @@ void stem_tc_plan_set_worker_groups(StemTcPlan* plan, int wg) { plan->wg = (wg =
 
 void launch_stem_tc(const StemTcPlan* plan, cudaStream_t stream, LaunchCounter* lc) {
   if (plan->split) {
-    if (plan->ks == 7)
+    // the split stem holds 144 KB of operand tiles (one CTA per SM): two worker threads per pixel double the warps
+    // that hide the gather's latency (YB_STEM_WG=1 selects one)
+    if (plan->ks == 7 && plan->wg == 2)
+      launch_variant<7, 2, 3, 64, 2, true>(plan->prm, stream);
+    else if (plan->ks == 7)
       launch_variant<7, 2, 3, 64, 1, true>(plan->prm, stream);
     else
       launch_variant<3, 1, 1, 32, 1, true>(plan->prm, stream);

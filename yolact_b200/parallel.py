@@ -15,11 +15,24 @@ def shard_range(global_batch, rank, world_size):
     return start, start + base + (1 if rank < rem else 0)
 
 
-def pack_records(box, coef, cls, score, count):
+def pack_records(box, coef, cls, score, count, out=None):
     """[b,M,4] f32, [b,M,k] f32, [b,M] i64, [b,M] f32, [b] i32 -> one float32 tensor [b, 1 + M*(6+k)].
-    Class ids (< 2^24) and counts are exactly representable in fp32."""
+    Class ids (< 2^24) and counts are exactly representable in fp32.  CUDA tensors: ONE kernel (yb_pack_detections);
+    CPU tensors (the gloo tests of the host logic): the same layout with torch ops."""
     b, M = score.shape
-    return torch.cat([count.view(b, 1).float(), cls.float(), score, box.reshape(b, M * 4), coef.reshape(b, -1)], 1)
+    k = coef.shape[2]
+    if not box.is_cuda:
+        return torch.cat([count.view(b, 1).float(), cls.float(), score, box.reshape(b, M * 4), coef.reshape(b, -1)], 1)
+    from . import _lib
+    from .output_utils import _ops_handle
+    lib = _lib.load()
+    rec = out if out is not None else torch.empty(b, 1 + M * (6 + k), dtype=torch.float32, device=box.device)
+    box, coef, score = box.contiguous().float(), coef.contiguous().float(), score.contiguous().float()
+    cls, count = cls.contiguous().long(), count.contiguous().int()
+    _lib.check(lib.yb_pack_detections(_ops_handle(box.device, k), _lib.ptr(box), _lib.ptr(coef), _lib.ptr(cls), _lib.ptr(score),
+                                      _lib.ptr(count), b, M, k, _lib.ptr(rec), _lib.current_stream(box.device)),
+               "yb_pack_detections")
+    return rec
 
 
 def unpack_records(rec, M, k):
@@ -41,10 +54,13 @@ def gather_detections(box, coef, cls, score, count, per_rank_batch, group=None):
     in original batch order on every rank.  ~16 KB per image: negligible on NVLink."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     M, k = score.shape[1], coef.shape[2]
-    rec = pack_records(box, coef, cls, score, count)
-    if rec.shape[0] < per_rank_batch:
-        pad = torch.zeros(per_rank_batch - rec.shape[0], rec.shape[1], dtype=rec.dtype, device=rec.device)
-        rec = torch.cat([rec, pad], 0)
+    b = int(score.shape[0])
+    if b < per_rank_batch:   # short last shard: zero rows (count 0)
+        rec = torch.zeros(per_rank_batch, 1 + M * (6 + k), dtype=torch.float32, device=box.device)
+        if b > 0:
+            rec[:b] = pack_records(box, coef, cls, score, count)
+    else:
+        rec = pack_records(box, coef, cls, score, count)
     if world == 1:
         return unpack_records(rec, M, k)
     out = torch.empty(world * per_rank_batch, rec.shape[1], dtype=rec.dtype, device=rec.device)
