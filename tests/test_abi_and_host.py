@@ -32,10 +32,22 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().yb_abi_version() == 2
 
 
-def test_config_struct_matches_header_layout():
-    # yb_config is plain int32/float fields: 4-byte packed, so sizeof must equal 4 * field count
+def test_config_struct_matches_header_layout(tmp_path):
+    # yb_config: 52 int32/float words (208 bytes, 8-byte aligned) followed by 24 doubles (ABI v2)
     n_words = 1 + 1 + 5 + 4 + 1 + 3 + 1 + 1 + 1 + 1 + 1 + 20 + 1 + 4 + 1 + 1 + 1 + 1 + 1 + 1 + 1
-    assert ctypes.sizeof(_lib.YbConfig) == 4 * n_words
+    assert ctypes.sizeof(_lib.YbConfig) == 4 * n_words + 8 * 24
+    assert _lib.YbConfig.scales_f64.offset == 4 * n_words and _lib.YbConfig.ars_f64.offset == 4 * n_words + 8 * 20
+    # the C compiler's view of the header must agree with the ctypes mirror
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "yolact_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu\\n", sizeof(yb_config), offsetof(yb_config, precision), '
+                   'offsetof(yb_config, scales_f64), offsetof(yb_config, ars_f64)); return 0; }\n')
+    exe = tmp_path / "layout"
+    import subprocess
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [ctypes.sizeof(_lib.YbConfig), _lib.YbConfig.precision.offset, _lib.YbConfig.scales_f64.offset,
+                   _lib.YbConfig.ars_f64.offset]
 
 
 @pytest.mark.parametrize("name", sorted(CONFIGS))
@@ -128,7 +140,7 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
                     os.path.join(ROOT, "examples", "c_abi_demo.c"), "-o", exe, os.path.join(libdir, "libyolact_b200.so"),
                     "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
-    assert "yolact_b200 ABI 1" in out
+    assert "yolact_b200 ABI 2" in out
     if not torch.cuda.is_available():
         assert "no CPU fallback" in out
 

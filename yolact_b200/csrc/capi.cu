@@ -74,7 +74,7 @@ __global__ void pack_w_dcn_tc_split_kernel(const float* __restrict__ w, __half* 
     int c = (int)(r % Ci);
     int o = (int)(r / Ci);
     __half hi, lo;
-    split_w_f32(w[i] * up, hi, lo);
+    split_f32(w[i] * up, hi, lo);   // same pair format as the activations
     out[(int64_t)o * 2 * K + (int64_t)t * Ci + c] = hi;
     out[(int64_t)o * 2 * K + K + (int64_t)t * Ci + c] = lo;
   }
@@ -717,7 +717,7 @@ int yb_conv2d(yb_handle* h, const float* d_x, const float* h_w, const float* h_b
             const __half hi = __float2half_rn(vs);
             const size_t idx = ((size_t)t * Co + o) * 2 * Ci + c;
             pk[idx] = hi;
-            pk[idx + Ci] = __float2half_rn(vs - __half2float(hi));
+            pk[idx + Ci] = __float2half_rn((vs - __half2float(hi)) * 2048.f);   // lo' = residual * 2^11 (common.cuh)
           }
     } else
     for (int o = 0; o < Co; ++o)

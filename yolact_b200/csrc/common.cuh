@@ -69,39 +69,31 @@ __device__ __forceinline__ __half from_f32<__half>(float v) {
   return __float2half_rn(v);
 }
 
-// Split-precision operands (YB_PREC_F16X3): a value is stored as a pair hi + lo.
-//   * activations: hi = rn_fp16(v), lo = rn_BF16(v - hi).  The lo plane is bfloat16 on purpose: lo is ~2^-12 |v|, which
-//     for |v| < 0.25 is an fp16 SUBNORMAL, and the tensor core flushes fp16 subnormal inputs to zero (measured: head
-//     tensors 5e-5 of range off with fp16 lo planes, the arithmetic's own bound is 1e-7).  bfloat16 has the exponent
-//     range of fp32; its 8 significand bits on top of hi's 11 give >= 19 bits.  tcgen05.mma kind::f16 takes the A and
-//     B formats independently, so the A_lo * W_hi pass runs as bf16 x fp16.
-//   * weights: w * 2^e = hi + lo, both fp16 (e puts the layer's largest weight just below 2^14, so lo is a normal
-//     fp16 number for every weight above 2^-17 of the maximum), see engine.cu split_exponent.
-// A pixel of a split NHWC tensor is [hi(C) | lo(C)], i.e. 2*C 16-bit elements; buffers are typed __half.
-__device__ __forceinline__ __half lo_from_f32(float r) {     // fp32 residual -> bf16 bits carried in a __half slot
-  const __nv_bfloat16 b = __float2bfloat16_rn(r);
-  return *reinterpret_cast<const __half*>(&b);
-}
-__device__ __forceinline__ float lo_to_f32(__half h) {
-  return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h));
-}
+// Split-precision operands (YB_PREC_F16X3): a value v is stored as a pair of fp16 numbers (hi, lo') with
+//     hi = rn(v),   lo' = rn((v - hi) * 2^11),   v ~= hi + lo' * 2^-11        (22 significand bits).
+// The lo plane is kept PRE-SCALED by 2^11: the unscaled residual (<= 2^-12 |v|) is an fp16 SUBNORMAL for every
+// |v| < 0.25 and the tensor core flushes fp16 subnormal inputs to zero (measured: head tensors 5e-5 of range off, the
+// arithmetic's own bound is 1e-7), and tcgen05.mma kind::f16 rejects a bf16 A with an fp16 B (illegal instruction), so
+// a wider-exponent lo format is not an option.  The kernels therefore accumulate the two cross terms
+// lo'_a * hi_w + hi_a * lo'_w in a SECOND fp32 TMEM accumulator and combine  acc_hi + 2^-11 * acc_lo  in the epilogue.
+// Weights are additionally multiplied by a per-layer power of two (engine.cu split_exponent) so that hi uses the upper
+// fp16 exponent range.  A pixel of a split NHWC tensor is [hi(C) | lo'(C)], i.e. 2*C halfs.
+#define YB_LO_SCALE 2048.f
+#define YB_LO_INV 4.8828125e-4f   /* 2^-11 */
+__device__ __forceinline__ __half lo_from_f32(float r) { return __float2half_rn(r * YB_LO_SCALE); }
+__device__ __forceinline__ float lo_to_f32(__half h) { return __half2float(h) * YB_LO_INV; }
 __device__ __forceinline__ __half2 lo2_from_f32(float r0, float r1) {
-  const __nv_bfloat162 b = __floats2bfloat162_rn(r0, r1);
-  return *reinterpret_cast<const __half2*>(&b);
+  return __floats2half2_rn(r0 * YB_LO_SCALE, r1 * YB_LO_SCALE);
 }
 __device__ __forceinline__ float2 lo2_to_f32(__half2 h) {
-  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h));
+  const float2 f = __half22float2(h);
+  return make_float2(f.x * YB_LO_INV, f.y * YB_LO_INV);
 }
-// activation split (hi saturates at +-65504; the residual of a saturated value is dropped)
+// (hi saturates at +-65504; the residual of a saturated value is dropped)
 __device__ __forceinline__ void split_f32(float v, __half& hi, __half& lo) {
   const float c = fminf(fmaxf(v, -65504.f), 65504.f);
   hi = __float2half_rn(c);
   lo = lo_from_f32(c - __half2float(hi));
-}
-// weight split: both halves fp16 (the caller pre-scales by a power of two)
-__device__ __forceinline__ void split_w_f32(float v, __half& hi, __half& lo) {
-  hi = __float2half_rn(v);
-  lo = __float2half_rn(v - __half2float(hi));
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {

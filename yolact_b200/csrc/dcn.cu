@@ -201,7 +201,7 @@ __global__ void dcn_gather_f16_kernel(const __half* __restrict__ x, const float*
         const __half2* l2 = reinterpret_cast<const __half2*>(&rawl);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float2 f = lo2_to_f32(l2[j]);   // lo plane: bf16
+          float2 f = lo2_to_f32(l2[j]);   // lo plane: residual * 2^11
           f8[2 * j] += f.x;
           f8[2 * j + 1] += f.y;
         }
@@ -222,7 +222,7 @@ __global__ void dcn_gather_f16_kernel(const __half* __restrict__ x, const float*
       o2[j] = __halves2half2(from_f32<__half>(v0), from_f32<__half>(v1));
       if (split) {
         const float2 hf = __half22float2(o2[j]);
-        ol2[j] = lo2_from_f32(fabsf(v0) > 65504.f ? 0.f : v0 - hf.x, fabsf(v1) > 65504.f ? 0.f : v1 - hf.y);   // bf16
+        ol2[j] = lo2_from_f32(fabsf(v0) > 65504.f ? 0.f : v0 - hf.x, fabsf(v1) > 65504.f ? 0.f : v1 - hf.y);   // lo' = residual * 2^11
       }
     }
     __half* cp = cols + (size_t)m * 9 * PS + (size_t)tap * C + cv * 8;

@@ -22,7 +22,7 @@
 //   epilogue    the same 8 warps: TMEM -> registers -> (* out_scale) + bias -> ReLU -> one full 128-byte line per
 //               thread and 64-channel chunk (even chunks: warps 2..5, odd chunks: warps 6..9).
 //   SPLIT       (YB_PREC_F16X3) x and y are [hi(C) | lo(C)] pairs, the sample is hi + lo, the A stage holds a hi (fp16)
-//               and a lo (bf16) tile, the weights [Cout][hi(9C) | lo(9C)], three MMA passes per k-block.
+//               and a lo (2^11-scaled fp16) tile, the weights [Cout][hi(9C) | lo(9C)], three MMA passes per k-block.
 #include "tc_common.cuh"
 
 namespace yb {
@@ -90,7 +90,7 @@ dcn_tc_kernel(const __grid_constant__ DcnParams p) {
     fence_barrier_init();
     tma_prefetch_desc(&p.tmW);
   }
-  if (warp == 1) tmem_alloc<BN>(&s_tmem);
+  if (warp == 1) tmem_alloc<NPL * BN>(&s_tmem);   // split: second accumulator for the lo cross terms (common.cuh)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -127,11 +127,11 @@ dcn_tc_kernel(const __grid_constant__ DcnParams p) {
         if (SPLIT) {
           const uint64_t dal = make_sw128_desc(sa + A_TILE), dbl = make_sw128_desc(sb + B_PLANE);
 #pragma unroll
-          for (int k = 0; k < DK / 16; ++k)   // A_lo (bf16) * W_hi (fp16)
-            umma_f16(tmem_base, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc | (1u << 7), 1u);
+          for (int k = 0; k < DK / 16; ++k)   // A_lo * W_hi -> second accumulator
+            umma_f16(tmem_base + BN, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < DK / 16; ++k)   // A_hi * W_lo
-            umma_f16(tmem_base, da + (uint64_t)(2 * k), dbl + (uint64_t)(2 * k), p.idesc, 1u);
+          for (int k = 0; k < DK / 16; ++k)   // A_hi * W_lo -> second accumulator
+            umma_f16(tmem_base + BN, da + (uint64_t)(2 * k), dbl + (uint64_t)(2 * k), p.idesc, 1u);
         }
         umma_commit(&empty_bar[s]);
       }
@@ -157,7 +157,11 @@ dcn_tc_kernel(const __grid_constant__ DcnParams p) {
     const int piece = lane & 7;
     const int src_sub = lane >> 3;                  // + 4*i = geometry owner lane
 
-    int o00 = -1, o01 = -1, o10 = -1, o11 = -1;
+    // Corner offsets are ALWAYS valid addresses (an out-of-range corner points at this image's pixel 0 and carries
+    // weight 0, which is what the reference's `if (h_low >= 0 && ...) v = ...` amounts to): the 16 corner loads of a
+    // k-block are then unconditional and the compiler issues them back to back -- with a branch per corner every load
+    // waited for the previous one (measured: 3.4 us per k-block, 124 us for a 35x35 layer).
+    int o00 = 0, o01 = 0, o10 = 0, o11 = 0;
     float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f, msk = 0.f;
     int cur_tap = -1;
     for (int kb = 0; kb < num_kb; ++kb) {
@@ -165,7 +169,7 @@ dcn_tc_kernel(const __grid_constant__ DcnParams p) {
       const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
       if (tap != cur_tap) {
         cur_tap = tap;
-        o00 = o01 = o10 = o11 = -1;
+        o00 = o01 = o10 = o11 = img_base;
         w00 = w01 = w10 = w11 = 0.f;
         msk = 0.f;
         if (gvalid) {
@@ -180,14 +184,22 @@ dcn_tc_kernel(const __grid_constant__ DcnParams p) {
             const int hhi = hl + 1, whi = wl + 1;
             const float lh = __fsub_rn(hh, (float)hl), lw = __fsub_rn(ww, (float)wl);
             const float uh = __fsub_rn(1.f, lh), uw = __fsub_rn(1.f, lw);
-            if (hl >= 0 && wl >= 0) o00 = img_base + hl * p.W + wl;
-            if (hl >= 0 && whi <= p.W - 1) o01 = img_base + hl * p.W + whi;
-            if (hhi <= p.H - 1 && wl >= 0) o10 = img_base + hhi * p.W + wl;
-            if (hhi <= p.H - 1 && whi <= p.W - 1) o11 = img_base + hhi * p.W + whi;
-            w00 = __fmul_rn(uh, uw);
-            w01 = __fmul_rn(uh, lw);
-            w10 = __fmul_rn(lh, uw);
-            w11 = __fmul_rn(lh, lw);
+            if (hl >= 0 && wl >= 0) {
+              o00 = img_base + hl * p.W + wl;
+              w00 = __fmul_rn(uh, uw);
+            }
+            if (hl >= 0 && whi <= p.W - 1) {
+              o01 = img_base + hl * p.W + whi;
+              w01 = __fmul_rn(uh, lw);
+            }
+            if (hhi <= p.H - 1 && wl >= 0) {
+              o10 = img_base + hhi * p.W + wl;
+              w10 = __fmul_rn(lh, uw);
+            }
+            if (hhi <= p.H - 1 && whi <= p.W - 1) {
+              o11 = img_base + hhi * p.W + whi;
+              w11 = __fmul_rn(lh, lw);
+            }
           }
         }
       }
@@ -204,9 +216,6 @@ dcn_tc_kernel(const __grid_constant__ DcnParams p) {
         const float mk = __shfl_sync(0xffffffffu, msk, src);
         float v1[8], v2[8], v3[8], v4[8];
         auto corner = [&](int o, float* v) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = 0.f;
-          if (o < 0) return;
           const __half* px = xc + (size_t)o * PS;
           const uint4 raw = ldg_nc16(px);
           const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
@@ -275,6 +284,15 @@ dcn_tc_kernel(const __grid_constant__ DcnParams p) {
       uint32_t r0[32], r1[32];
       tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 64), r0);
       tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 64 + 32), r1);
+      if (SPLIT) {
+        uint32_t q2[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(BN + c * 64), q2);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r0[j] = __float_as_uint(__fmaf_rn(__uint_as_float(q2[j]), YB_LO_INV, __uint_as_float(r0[j])));
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(BN + c * 64 + 32), q2);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r1[j] = __float_as_uint(__fmaf_rn(__uint_as_float(q2[j]), YB_LO_INV, __uint_as_float(r1[j])));
+      }
       if (m >= p.M) continue;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -312,7 +330,7 @@ dcn_tc_kernel(const __grid_constant__ DcnParams p) {
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_base);
+    tmem_dealloc<NPL * BN>(tmem_base);
   }
 }
 

@@ -778,7 +778,7 @@ static inline void split_pack(float v, float scale, __half* hi, __half* lo) {
   const float vs = v * scale;
   const __half h = __float2half_rn(vs);
   *hi = h;
-  *lo = __float2half_rn(vs - __half2float(h));
+  *lo = __float2half_rn((vs - __half2float(h)) * 2048.f);   // lo' = residual * 2^11 (common.cuh)
 }
 
 static const HostTensor& need(yb_handle* h, const std::string& name) {

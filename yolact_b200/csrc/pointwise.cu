@@ -66,7 +66,7 @@ template <typename T>
 __device__ __forceinline__ void load_vec(const T* px, int C, int cv, int split, float* f) {
   constexpr int V = DType<T>::kVec;
   unpack<T>(*reinterpret_cast<const uint4*>(px + cv * V), f);
-  if (sizeof(T) == 2 && split) {   // lo plane: bf16 pairs
+  if (sizeof(T) == 2 && split) {   // lo plane: residual * 2^11
     const uint4 rl = *reinterpret_cast<const uint4*>(px + C + cv * V);
     const __half2* l2 = reinterpret_cast<const __half2*>(&rl);
 #pragma unroll

@@ -67,7 +67,7 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
     fence_barrier_init();
     tma_prefetch_desc(&p.tmW);
   }
-  if (warp == MMA_WARP) tmem_alloc<COUT>(&s_tmem);
+  if (warp == MMA_WARP) tmem_alloc<NPL * COUT>(&s_tmem);   // split: second accumulator for the lo cross terms
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -90,8 +90,8 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
           const int atom = j >> 2, kk = j & 3;
           const uint64_t da = make_sw128_desc(smem_u32(sA + (pa * ATOMS + atom) * A_ATOM_BYTES)) + (uint64_t)(2 * kk);
           const uint64_t db = make_sw128_desc(smem_u32(sB + (pb * ATOMS + atom) * B_ATOM_BYTES)) + (uint64_t)(2 * kk);
-          // the lo plane of the patch is bf16 (common.cuh): a_format = 1 for the lo * hi pass
-          umma_f16(tmem_base, da, db, pa ? (p.idesc | (1u << 7)) : p.idesc, (pass > 0 || j > 0) ? 1u : 0u);
+          // hi*hi -> accumulator 0; lo*hi and hi*lo -> accumulator 1 (COUT columns further), see common.cuh
+          umma_f16(tmem_base + (pass > 0 ? COUT : 0), da, db, p.idesc, (pass == 2 || j > 0) ? 1u : 0u);
         }
       }
       umma_commit(&tmem_full);
@@ -140,7 +140,7 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
         h2[j2] = __halves2half2(from_f32<__half>(v[0]), from_f32<__half>(v[1]));
         if (SPLIT) {
           const float2 hf = __half22float2(h2[j2]);
-          l2[j2] = lo2_from_f32(fabsf(v[0]) > 65504.f ? 0.f : v[0] - hf.x, fabsf(v[1]) > 65504.f ? 0.f : v[1] - hf.y);   // bf16
+          l2[j2] = lo2_from_f32(fabsf(v[0]) > 65504.f ? 0.f : v[0] - hf.x, fabsf(v[1]) > 65504.f ? 0.f : v[1] - hf.y);   // lo' = residual * 2^11
         }
       }
       const int atom = kg >> 3;
@@ -160,6 +160,12 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
       if (WG > 1 && ((c0 >> 5) % WG) != wg) continue;   // warp-uniform
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, r);
+      if (SPLIT) {
+        uint32_t q2[32];
+        tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(COUT + c0), q2);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__fmaf_rn(__uint_as_float(q2[j]), YB_LO_INV, __uint_as_float(r[j])));
+      }
       if (!valid) continue;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -179,7 +185,7 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
           o2[j] = __halves2half2(from_f32<__half>(v0), from_f32<__half>(v1));
           if (SPLIT) {
             const float2 hf = __half22float2(o2[j]);
-            ol2[j] = lo2_from_f32(fabsf(v0) > 65504.f ? 0.f : v0 - hf.x, fabsf(v1) > 65504.f ? 0.f : v1 - hf.y);   // bf16
+            ol2[j] = lo2_from_f32(fabsf(v0) > 65504.f ? 0.f : v0 - hf.x, fabsf(v1) > 65504.f ? 0.f : v1 - hf.y);   // lo' = residual * 2^11
           }
         }
         reinterpret_cast<uint4*>(yrow + c0)[q] = o;
@@ -191,7 +197,7 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
   __syncthreads();
   if (warp == MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc<COUT>(tmem_base);
+    tmem_dealloc<NPL * COUT>(tmem_base);
   }
 }
 

@@ -166,7 +166,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1
         const __half2* l2 = reinterpret_cast<const __half2*>(&rawl);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 f = lo2_to_f32(l2[j]);   // lo plane: bf16
+          const float2 f = lo2_to_f32(l2[j]);   // lo plane: 2^11-scaled
           v[2 * j] += f.x;
           v[2 * j + 1] += f.y;
         }
@@ -190,7 +190,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1
         // hi saturates at +-65504; the residual of a saturated value is dropped (lo = 0 keeps hi + lo finite)
         const float l0 = fabsf(v[2 * j]) > 65504.f ? 0.f : v[2 * j] - hf.x;
         const float l1 = fabsf(v[2 * j + 1]) > 65504.f ? 0.f : v[2 * j + 1] - hf.y;
-        l2[j] = lo2_from_f32(l0, l1);          // lo plane: bf16 (see common.cuh)
+        l2[j] = lo2_from_f32(l0, l1);          // lo plane: residual * 2^11 (see common.cuh)
       }
       *reinterpret_cast<uint4*>(out_tile + A_STAGE_BYTES + off) = ol;
     }
@@ -224,8 +224,9 @@ __device__ __forceinline__ TileCoord decode_unit(const TcParams& p, int u, int r
 template <int BN, bool PAIR, int H, bool SPLIT>
 __global__ void __launch_bounds__(64 + 128 * H)
 tc_conv_kernel(const __grid_constant__ TcParams p) {
-  // SPLIT (YB_PREC_F16X3): every operand has a hi and a lo fp16 plane; a k-block stages A_hi, A_lo, W_hi, W_lo and
-  // issues A_hi*W_hi + A_lo*W_hi + A_hi*W_lo into ONE fp32 accumulator (the lo*lo term is below fp32 resolution).
+  // SPLIT (YB_PREC_F16X3): every operand has a hi and a (2^11-scaled) lo fp16 plane; a k-block stages A_hi, A_lo, W_hi,
+  // W_lo and issues A_hi*W_hi into the tile's first accumulator and A_lo*W_hi + A_hi*W_lo into its second one (BN TMEM
+  // columns further); the epilogue combines acc_hi + 2^-11 * acc_lo (the lo*lo term is below fp32 resolution).
   constexpr int NPL = SPLIT ? 2 : 1;
   constexpr int B_PLANE_BYTES = (PAIR ? BN / 2 : BN) * BLOCK_K * 2;   // a pair CTA stages half of the weight tile
   constexpr int A_BYTES = NPL * A_STAGE_BYTES;
@@ -349,7 +350,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
         const uint32_t use = t / (uint32_t)acc_stages;
         mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
+        const uint32_t tmem_d = tmem_base + acc * (uint32_t)(NPL * BN);
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)stages;
           const uint32_t it = kbg / (uint32_t)stages;
@@ -371,11 +372,13 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             const uint64_t dal = make_sw128_desc(sa + A_STAGE_BYTES);
             const uint64_t dbl = make_sw128_desc(sb + B_PLANE_BYTES);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // A_lo (bf16) * W_hi (fp16): a_format = 1 in the instruction descriptor
-              if (PAIR) umma_f16_pair(tmem_d, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc | (1u << 7), 1u);
-              else umma_f16(tmem_d, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc | (1u << 7), 1u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // A_lo * W_hi -> second accumulator
+              if (PAIR) umma_f16_pair(tmem_d + BN, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              else umma_f16(tmem_d + BN, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) mma(da + (uint64_t)(2 * k), dbl + (uint64_t)(2 * k), 1u);   // A_hi * W_lo
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // A_hi * W_lo -> second accumulator
+              if (PAIR) umma_f16_pair(tmem_d + BN, da + (uint64_t)(2 * k), dbl + (uint64_t)(2 * k), p.idesc, 1u);
+              else umma_f16(tmem_d + BN, da + (uint64_t)(2 * k), dbl + (uint64_t)(2 * k), p.idesc, 1u);
           }
           // frees this smem slot (in both CTAs of a pair) once the MMAs above have read it
           if (PAIR) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
@@ -446,7 +449,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       const int x0 = tc_.x0, y0 = tc_.y0, b = tc_.b, n0 = tc_.n0;
       const uint32_t acc = t % (uint32_t)acc_stages;
       const uint32_t use = t / (uint32_t)acc_stages;
-      const uint32_t tmem_acc = tmem_base + acc * (uint32_t)BN + ((uint32_t)(quad * 32) << 16);
+      const uint32_t tmem_acc = tmem_base + acc * (uint32_t)(NPL * BN) + ((uint32_t)(quad * 32) << 16);
       // bias of this tile's BN output channels -> this group's copy in shared memory (broadcast float4 reads)
       {
         const int et = (threadIdx.x - 64) & 127;   // 0..127 within the group
@@ -477,6 +480,17 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           uint32_t r0[32], r1[32];
           tmem_ld32_nowait(tmem_acc + (uint32_t)(c * 64), r0);
           tmem_ld32_nowait(tmem_acc + (uint32_t)(c * 64 + 32), r1);
+          if (SPLIT) {   // + 2^-11 * (A_lo*W_hi + A_hi*W_lo), from the tile's second accumulator
+            uint32_t q[32];
+            tmem_ld32_nowait(tmem_acc + (uint32_t)(BN + c * 64), q);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r0[j] = __float_as_uint(__fmaf_rn(__uint_as_float(q[j]), YB_LO_INV, __uint_as_float(r0[j])));
+            tmem_ld32_nowait(tmem_acc + (uint32_t)(BN + c * 64 + 32), q);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r1[j] = __float_as_uint(__fmaf_rn(__uint_as_float(q[j]), YB_LO_INV, __uint_as_float(r1[j])));
+          }
           tmem_ld_wait();
           if (has_res) mbar_wait(&res_full_bar[buf], (NBUF == 1) ? (g & 1u) : ((g >> 1) & 1u));
           const int nbase = n0 + c * 64;
@@ -514,6 +528,12 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
         for (int c0 = hgrp * 32; c0 < ncols; c0 += 32 * H) {
           uint32_t r[32];
           tmem_ld32(tmem_acc + (uint32_t)c0, r);
+          if (SPLIT) {
+            uint32_t q[32];
+            tmem_ld32(tmem_acc + (uint32_t)(BN + c0), q);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__fmaf_rn(__uint_as_float(q[j]), YB_LO_INV, __uint_as_float(r[j])));
+          }
           const int nbase = n0 + c0;
           const int nvalid = min(32, p.Cout - nbase);
           __syncwarp();
@@ -780,8 +800,9 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   int grid = std::min(num_tiles, grid_override > 0 ? (pair ? std::max(1, grid_override / 2) : grid_override) : (pair ? 74 : 148));
   if (pair) grid = std::min(grid, 74);   // one cluster per TPC: 148 SMs = 74 CTA pairs, one CTA per SM
   q.acc_stages = (grid < num_tiles) ? 2 : 1;
+  if (q.acc_stages * npl * BN > 512) q.acc_stages = 1;   // split: two accumulators per tile (2 * BN columns)
   int tmem_cols = 32;
-  while (tmem_cols < q.acc_stages * BN) tmem_cols *= 2;
+  while (tmem_cols < q.acc_stages * npl * BN) tmem_cols *= 2;
   // Pairs allocate all of TMEM (and > half of the shared memory, below): one CTA per SM, so both CTAs of a pair
   // get the SAME accumulator address, which the single cta_group::2 MMA requires.
   if (pair) tmem_cols = 512;
@@ -793,7 +814,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   const int pdlf = (pdl_override > 0 && !pair && !split) ? 1 : 0;
   plan->pdl_friendly = pdlf;
   if (pdlf && q.acc_stages * BN > 256) q.acc_stages = 1;
-  if (pdlf) {
+  if (pdlf) {   // (never a split plan)
     int tc = 32;
     while (tc < q.acc_stages * BN) tc *= 2;
     q.tmem_cols = tc;
