@@ -125,12 +125,17 @@ TC_MODES = {
     "epi2": {"YB_CONV2D_EPI": "2"},
     "epi2_grid3_bn256": {"YB_CONV2D_EPI": "2", "YB_CONV2D_GRID": "3", "YB_CONV2D_BN": "256"},
     "pair_epi2": {"YB_CONV2D_PAIR": "1", "YB_CONV2D_EPI": "2"},
+    # PDL-friendly plans (<= half an SM, weight tiles requested before griddepcontrol.wait)
+    "pdl_friendly": {"YB_CONV2D_PDL": "1"},
+    "pdl_friendly_bn64_grid3": {"YB_CONV2D_PDL": "1", "YB_CONV2D_BN": "64", "YB_CONV2D_GRID": "3"},
+    # stream-K: equal shares of the k-block iterations per CTA / cluster, fp32 partial tiles through a workspace; few
+    # CTAs give every CTA a tail, whole units and a head
+    "sk": {"YB_CONV2D_SK": "1"},
+    "sk_grid5": {"YB_CONV2D_SK": "1", "YB_CONV2D_GRID": "5"},
+    "sk_grid7_bn64": {"YB_CONV2D_SK": "1", "YB_CONV2D_GRID": "7", "YB_CONV2D_BN": "64"},
+    "sk_pair": {"YB_CONV2D_SK": "1", "YB_CONV2D_PAIR": "1"},
+    "sk_pair_grid6_epi2": {"YB_CONV2D_SK": "1", "YB_CONV2D_PAIR": "1", "YB_CONV2D_GRID": "6", "YB_CONV2D_EPI": "2"},
 }
-if os.environ.get("YB_TEST_EXPERIMENTAL"):
-    # not validated on hardware yet (written after the round-1 GPU budget was spent): PDL-friendly plans with the
-    # weight tiles requested before griddepcontrol.wait; yb_conv2d(iters > 1) launches the kernel back to back
-    TC_MODES["pdl_friendly"] = {"YB_CONV2D_PDL": "1"}
-    TC_MODES["pdl_friendly_bn64_grid3"] = {"YB_CONV2D_PDL": "1", "YB_CONV2D_BN": "64", "YB_CONV2D_GRID": "3"}
 if os.environ.get("YB_TEST_NO_PAIR"):   # escape hatch while the pair kernel is being brought up
     TC_MODES = {k: v for k, v in TC_MODES.items() if not k.startswith("pair")}
 
@@ -165,6 +170,10 @@ SPLIT_MODES = {
     "pair_bn256": {"YB_CONV2D_PAIR": "1", "YB_CONV2D_BN": "256"},
     "epi2": {"YB_CONV2D_EPI": "2"},
     "pair_epi2": {"YB_CONV2D_PAIR": "1", "YB_CONV2D_EPI": "2"},
+    "sk": {"YB_CONV2D_SK": "1"},
+    "sk_grid5": {"YB_CONV2D_SK": "1", "YB_CONV2D_GRID": "5"},
+    "sk_pair": {"YB_CONV2D_SK": "1", "YB_CONV2D_PAIR": "1"},
+    "sk_pair_grid6": {"YB_CONV2D_SK": "1", "YB_CONV2D_PAIR": "1", "YB_CONV2D_GRID": "6"},
 }
 
 

@@ -180,6 +180,7 @@ int yb_create(const yb_config* cfg, int device, yb_handle** out) {
   if (const char* at = getenv("YB_AUTOTUNE")) h->autotune = (atoi(at) != 0);
   if (const char* pc = getenv("YB_PAIR")) h->pair_candidates = (atoi(pc) != 0);
   if (const char* ec = getenv("YB_EPI2")) h->epi2_candidates = (atoi(ec) != 0);
+  if (const char* sk = getenv("YB_SK")) h->sk_candidates = (atoi(sk) != 0);
   if (const char* sw = getenv("YB_STEM_WG")) h->stem_wg = atoi(sw) == 2 ? 2 : 1;   // default 0: per precision mode
   if (const char* st = getenv("YB_STEM_TC")) h->stem_on_tc = (atoi(st) != 0);
   if (const char* df = getenv("YB_DCN_FUSED")) h->dcn_fused = (atoi(df) != 0);
@@ -731,10 +732,16 @@ int yb_conv2d(yb_handle* h, const float* d_x, const float* h_w, const float* h_b
       const char* ge = getenv("YB_CONV2D_GRID");
       const char* pe = getenv("YB_CONV2D_PAIR");
       const char* ee = getenv("YB_CONV2D_EPI");
-      const char* de = getenv("YB_CONV2D_PDL");   // experimental: PDL-friendly plan + programmatic dependent launch
+      const char* de = getenv("YB_CONV2D_PDL");   // PDL-friendly plan + programmatic dependent launch
+      const char* ke = getenv("YB_CONV2D_SK");    // stream-K
       plan = tc_conv_plan_create(p, wd, be ? atoi(be) : 0, 0, ge ? atoi(ge) : 0, pe ? atoi(pe) : 0, ee ? atoi(ee) : 0,
-                                 de ? atoi(de) : 0);
+                                 de ? atoi(de) : 0, ke ? atoi(ke) : 0);
       if (de && atoi(de)) tc_conv_plan_set_pdl(plan, 1);
+      if (tc_conv_plan_sk(plan)) {
+        void* ws = tp.get(tc_conv_sk_workspace_bytes());
+        YB_CHECK_CUDA(cudaMemsetAsync(ws, 0, tc_conv_sk_workspace_bytes(), s));
+        tc_conv_plan_set_sk_workspace(plan, ws);
+      }
     }
     run = [&]() { launch_tc_conv(plan, s, &h->lc); };
   } else if (precision == 2) {

@@ -16,7 +16,7 @@
 //               row (4 corner offsets, 4 bilinear weights, the modulation mask) from the 27 offset/mask channels; for
 //               every 64-channel chunk the geometry reaches the lanes that need it by WARP SHUFFLE (8 lanes share a
 //               row: one 16-byte vector of 8 channels each), the four corners are fetched with 16-byte loads, blended
-//               in fp32 and written as one swizzled 16-byte piece of the K-major SWIZZLE_128B A tile -- the layout
+//               (fp32 in the split mode, packed half2 in the fp16 mode) and written as one swizzled 16-byte piece of the K-major SWIZZLE_128B A tile -- the layout
 //               tcgen05.mma consumes directly.  Geometry is computed once per (pixel, tap) instead of once per
 //               (pixel, tap, 8 channels) as in the per-thread gather.
 //   epilogue    the same 8 warps: TMEM -> registers -> (* out_scale) + bias -> ReLU -> one full 128-byte line per
@@ -158,27 +158,29 @@ dcn_tc_kernel(const __grid_constant__ DcnParams p) {
     const int src_sub = lane >> 3;                  // + 4*i = geometry owner lane
 
     // Corner offsets are ALWAYS valid addresses (an out-of-range corner points at this image's pixel 0 and carries
-    // weight 0, which is what the reference's `if (h_low >= 0 && ...) v = ...` amounts to): the 16 corner loads of a
+    // weight 0, which is what the reference's `if (h_low >= 0 && ...) v = ...` amounts to): the corner loads of a
     // k-block are then unconditional and the compiler issues them back to back -- with a branch per corner every load
     // waited for the previous one (measured: 3.4 us per k-block, 124 us for a 35x35 layer).
-    int o00 = 0, o01 = 0, o10 = 0, o11 = 0;
-    float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f, msk = 0.f;
+    // The modulation mask is folded into the four bilinear weights (one rounding of difference to the reference's
+    // (sum) * mask, far below the fp16 / split resolution).
+    int ao[4][4];        // [item][corner] pixel offsets of this lane's 4 rows, refreshed once per tap by shuffle
+    float aw[4][4];      // [item][corner] weight * mask (split mode)
+    __half2 hw[4][4];    // the same as broadcast half2 pairs (fp16 mode)
     int cur_tap = -1;
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % stages, it = kb / stages;
       const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
       if (tap != cur_tap) {
         cur_tap = tap;
-        o00 = o01 = o10 = o11 = img_base;
-        w00 = w01 = w10 = w11 = 0.f;
-        msk = 0.f;
+        int o00 = img_base, o01 = img_base, o10 = img_base, o11 = img_base;
+        float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
         if (gvalid) {
           // dcn_v2_im2col_cuda.cu:151-189: h_im = h_in + i*dil + offset_h, w_im likewise; inside test (-1, H) x (-1, W)
           const int i = tap / 3, j = tap - i * 3;
           const float hh = __fadd_rn((float)(gho * p.stride - p.pad + i * p.dil), __ldg(gom + 2 * tap));
           const float ww = __fadd_rn((float)(gwo * p.stride - p.pad + j * p.dil), __ldg(gom + 2 * tap + 1));
           const float mv = __ldg(gom + 18 + tap);
-          msk = p.mask_logits ? __fdiv_rn(1.f, __fadd_rn(1.f, expf(-mv))) : mv;
+          const float msk = p.mask_logits ? __fdiv_rn(1.f, __fadd_rn(1.f, expf(-mv))) : mv;
           if (hh > -1.f && ww > -1.f && hh < (float)p.H && ww < (float)p.W) {
             const int hl = (int)floorf(hh), wl = (int)floorf(ww);
             const int hhi = hl + 1, whi = wl + 1;
@@ -186,85 +188,97 @@ dcn_tc_kernel(const __grid_constant__ DcnParams p) {
             const float uh = __fsub_rn(1.f, lh), uw = __fsub_rn(1.f, lw);
             if (hl >= 0 && wl >= 0) {
               o00 = img_base + hl * p.W + wl;
-              w00 = __fmul_rn(uh, uw);
+              w00 = __fmul_rn(__fmul_rn(uh, uw), msk);
             }
             if (hl >= 0 && whi <= p.W - 1) {
               o01 = img_base + hl * p.W + whi;
-              w01 = __fmul_rn(uh, lw);
+              w01 = __fmul_rn(__fmul_rn(uh, lw), msk);
             }
             if (hhi <= p.H - 1 && wl >= 0) {
               o10 = img_base + hhi * p.W + wl;
-              w10 = __fmul_rn(lh, uw);
+              w10 = __fmul_rn(__fmul_rn(lh, uw), msk);
             }
             if (hhi <= p.H - 1 && whi <= p.W - 1) {
               o11 = img_base + hhi * p.W + whi;
-              w11 = __fmul_rn(lh, lw);
+              w11 = __fmul_rn(__fmul_rn(lh, lw), msk);
             }
+          }
+        }
+        // geometry owner lane -> the 8 lanes that gather that row (item i: row 16*gw + 4*i + (lane >> 3))
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int src = 4 * i + src_sub;
+          ao[i][0] = __shfl_sync(0xffffffffu, o00, src);
+          ao[i][1] = __shfl_sync(0xffffffffu, o01, src);
+          ao[i][2] = __shfl_sync(0xffffffffu, o10, src);
+          ao[i][3] = __shfl_sync(0xffffffffu, o11, src);
+          aw[i][0] = __shfl_sync(0xffffffffu, w00, src);
+          aw[i][1] = __shfl_sync(0xffffffffu, w01, src);
+          aw[i][2] = __shfl_sync(0xffffffffu, w10, src);
+          aw[i][3] = __shfl_sync(0xffffffffu, w11, src);
+          if (!SPLIT) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) hw[i][c] = __float2half2_rn(aw[i][c]);
           }
         }
       }
       mbar_wait(&empty_bar[s], (uint32_t)(it & 1) ^ 1u);   // the MMAs that read this stage have completed
       uint8_t* sa = smem + (size_t)s * STAGE;
       const __half* xc = p.x + kc * DK + piece * 8;
+      if (!SPLIT) {
+        // fp16 mode: the samples are rounded to fp16 anyway -- blend in packed half2 arithmetic (4 HFMA2 per corner)
+        uint4 raw[4][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int src = 4 * i + src_sub;
-        const int a00 = __shfl_sync(0xffffffffu, o00, src), a01 = __shfl_sync(0xffffffffu, o01, src);
-        const int a10 = __shfl_sync(0xffffffffu, o10, src), a11 = __shfl_sync(0xffffffffu, o11, src);
-        const float b00 = __shfl_sync(0xffffffffu, w00, src), b01 = __shfl_sync(0xffffffffu, w01, src);
-        const float b10 = __shfl_sync(0xffffffffu, w10, src), b11 = __shfl_sync(0xffffffffu, w11, src);
-        const float mk = __shfl_sync(0xffffffffu, msk, src);
-        float v1[8], v2[8], v3[8], v4[8];
-        auto corner = [&](int o, float* v) {
-          const __half* px = xc + (size_t)o * PS;
-          const uint4 raw = ldg_nc16(px);
-          const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) raw[i][c] = ldg_nc16(xc + (size_t)ao[i][c] * PS);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 oh;
+          __half2* o2 = reinterpret_cast<__half2*>(&oh);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const __half2 w2 = hw[i][c];
+            const __half2* v2 = reinterpret_cast<const __half2*>(&raw[i][c]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o2[j] = (c == 0) ? __hmul2(w2, v2[j]) : __hfma2(w2, v2[j], o2[j]);
+          }
+          const int row = gw * 16 + 4 * i + src_sub;
+          const uint32_t off = (uint32_t)row * 128u + (((uint32_t)piece ^ ((uint32_t)row & 7u)) << 4);
+          *reinterpret_cast<uint4*>(sa + off) = oh;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 rh[4], rl[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const __half* px = xc + (size_t)ao[i][c] * PS;
+            rh[c] = ldg_nc16(px);
+            rl[c] = ldg_nc16(px + p.C);
+          }
+          uint4 oh, ol;
+          __half2* oh2 = reinterpret_cast<__half2*>(&oh);
+          __half2* ol2 = reinterpret_cast<__half2*>(&ol);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(h2[j]);
-            v[2 * j] = f.x;
-            v[2 * j + 1] = f.y;
-          }
-          if (SPLIT) {
-            const uint4 rawl = ldg_nc16(px + p.C);
-            const __half2* l2 = reinterpret_cast<const __half2*>(&rawl);
+            float r0 = 0.f, r1 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = lo2_to_f32(l2[j]);
-              v[2 * j] += f.x;
-              v[2 * j + 1] += f.y;
+            for (int c = 0; c < 4; ++c) {
+              const float2 fh = __half22float2(reinterpret_cast<const __half2*>(&rh[c])[j]);
+              const float2 fl = lo2_to_f32(reinterpret_cast<const __half2*>(&rl[c])[j]);
+              r0 = __fmaf_rn(aw[i][c], fh.x + fl.x, r0);
+              r1 = __fmaf_rn(aw[i][c], fh.y + fl.y, r1);
             }
-          }
-        };
-        corner(a00, v1);
-        corner(a01, v2);
-        corner(a10, v3);
-        corner(a11, v4);
-        uint4 oh, ol;
-        __half2* oh2 = reinterpret_cast<__half2*>(&oh);
-        __half2* ol2 = reinterpret_cast<__half2*>(&ol);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float r[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int q = 2 * j + e;
-            // (w1*v1 + w2*v2 + w3*v3 + w4*v4) * mask, left to right (dcn_v2_im2col_cuda.cu:50-53,189)
-            const float val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(b00, v1[q]), __fmul_rn(b01, v2[q])), __fmul_rn(b10, v3[q])),
-                                        __fmul_rn(b11, v4[q]));
-            r[e] = __fmul_rn(val, mk);
-          }
-          const float c0 = fminf(fmaxf(r[0], -65504.f), 65504.f), c1 = fminf(fmaxf(r[1], -65504.f), 65504.f);
-          oh2[j] = __floats2half2_rn(c0, c1);
-          if (SPLIT) {
+            oh2[j] = __floats2half2_rn(r0, r1);   // |sample| <= max |x|: no saturation needed
             const float2 hf = __half22float2(oh2[j]);
-            ol2[j] = lo2_from_f32(c0 - hf.x, c1 - hf.y);
+            ol2[j] = lo2_from_f32(r0 - hf.x, r1 - hf.y);
           }
+          const int row = gw * 16 + 4 * i + src_sub;
+          const uint32_t off = (uint32_t)row * 128u + (((uint32_t)piece ^ ((uint32_t)row & 7u)) << 4);
+          *reinterpret_cast<uint4*>(sa + off) = oh;
+          *reinterpret_cast<uint4*>(sa + A_TILE + off) = ol;
         }
-        const int row = gw * 16 + src;
-        const uint32_t off = (uint32_t)row * 128u + (((uint32_t)piece ^ ((uint32_t)row & 7u)) << 4);
-        *reinterpret_cast<uint4*>(sa + off) = oh;
-        if (SPLIT) *reinterpret_cast<uint4*>(sa + A_TILE + off) = ol;
       }
       fence_proxy_async();   // generic-proxy smem writes -> visible to tcgen05.mma (async proxy)
       __syncwarp();

@@ -220,14 +220,17 @@ struct NetBuilder {
     p.x = in.ptr;
     p.x_nchw_f32 = in_nchw ? 1 : 0;
     p.split = in.split ? 1 : 0;
+    // in.C may be a zero-padded channel count (the tcgen05 stem pads a 32-channel output to 64, see stem_tc)
     const bool tc = f16 && !in_nchw && (in.C % 64 == 0) && !in.f32;
     YB_REQUIRE(!split || tc || in_nchw, ("conv " + key + ": the split-precision mode has tensor-core kernels only").c_str());
     const bool simt_half = f16 && !tc && !in.f32;
     const bool stem_tc = f16 && in_nchw && !ospec && !out_f32 && !residual && h->stem_on_tc &&
                          stem_tc_supported(k, stride, pad, in.C, h->peek_cout(key));
     ConvW& w = stem_tc ? h->get_conv(key, bn, /*want_tc=*/true, false, false, /*pack=*/2)
-                       : h->get_conv(key, bn, /*want_tc=*/tc, /*want_f32=*/!tc && !simt_half, /*want_f16=*/simt_half);
-    YB_REQUIRE(w.Cin == in.C && w.KH == k && w.KW == k, ("conv " + key + ": weight shape mismatch").c_str());
+                       : h->get_conv(key, bn, /*want_tc=*/tc, /*want_f32=*/!tc && !simt_half, /*want_f16=*/simt_half, 0,
+                                     /*cin_pad=*/tc ? in.C : 0);
+    YB_REQUIRE((w.Cin == in.C || (tc && w.cin_pad == in.C)) && w.KH == k && w.KW == k,
+               ("conv " + key + ": weight shape mismatch").c_str());
     p.Cout = w.Cout;
     p.bias = w.bias;
     p.out_scale = w.out_scale;
@@ -244,7 +247,9 @@ struct NetBuilder {
       p.y_batch_stride = ospec->batch_stride;
       p.y_pix_stride = ospec->pix_stride;
     } else {
-      out = alloc_act(in.B, p.Ho, p.Wo, w.Cout, out_f32);
+      // the tcgen05 stem zero-pads its pixels to a multiple of 64 channels for the tensor-core conv that follows
+      const int out_c = stem_tc ? ((w.Cout + 63) / 64) * 64 : w.Cout;
+      out = alloc_act(in.B, p.Ho, p.Wo, out_c, out_f32);
       p.y = out.ptr;
       p.y_f32 = (f16 && out.f32) ? 1 : 0;
       const int ps = out.split ? 2 * w.Cout : w.Cout;
@@ -265,7 +270,7 @@ struct NetBuilder {
               std::to_string(stride) + " " + std::to_string(p.Ho) + "x" + std::to_string(p.Wo);
     if (stem_tc) {
       StemTcPlan* sp = stem_tc_plan_create((const float*)in.ptr, w.w_tc, w.bias, (__half*)out.ptr, in.B, in.H, in.W, k,
-                                           stride, pad, w.Cout, act, split ? 1 : 0, w.out_scale);
+                                           stride, pad, w.Cout, act, split ? 1 : 0, w.out_scale, out.C);
       stem_tc_plan_set_worker_groups(sp, h->stem_wg > 0 ? h->stem_wg : (split ? 2 : 1));
       ex->stem_plans.push_back(sp);
       op.name += (h->stem_wg > 0 ? h->stem_wg : (split ? 2 : 1)) == 2 ? " stem wg=2" : " stem";
@@ -279,7 +284,7 @@ struct NetBuilder {
       ex->plans.push_back(plan);
       op.name += " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) + " st=" + std::to_string(tc_conv_plan_stages(plan)) +
                  " g=" + std::to_string(tc_conv_plan_grid(plan)) + (tc_conv_plan_pair(plan) ? " pair" : "") + (tc_conv_plan_epi_groups(plan) == 2 ? " epi2" : "") +
-              (tc_conv_plan_pdl_friendly(plan) ? " pdlf" : "");
+              (tc_conv_plan_pdl_friendly(plan) ? " pdlf" : "") + (tc_conv_plan_sk(plan) ? " sk" : "");
       tc_conv_plan_set_pdl(plan, h->pdl ? 1 : 0);
       op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
     } else {
@@ -464,9 +469,19 @@ struct NetBuilder {
               std::to_string(in.H) + "x" + std::to_string(in.W) + " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) +
               " st=" + std::to_string(tc_conv_plan_stages(plan)) + " g=" + std::to_string(tc_conv_plan_grid(plan)) +
               (tc_conv_plan_pair(plan) ? " pair" : "") + (tc_conv_plan_epi_groups(plan) == 2 ? " epi2" : "") +
-              (tc_conv_plan_pdl_friendly(plan) ? " pdlf" : "");
+              (tc_conv_plan_pdl_friendly(plan) ? " pdlf" : "") + (tc_conv_plan_sk(plan) ? " sk" : "");
     op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
     push(op);
+  }
+
+  // stream-K workspace of the current lane (allocated on first use; the flags at its end start out zero)
+  void* sk_workspace() {
+    void*& ws = ex->sk_ws[lane & 7];
+    if (!ws) {
+      ws = dmalloc(ex->allocs, tc_conv_sk_workspace_bytes());
+      YB_CHECK_CUDA(cudaMemset(ws, 0, tc_conv_sk_workspace_bytes()));
+    }
+    return ws;
   }
 
   // Plan-time autotuning of the tcgen05 kernel's N tile and pipeline depth: each candidate is timed on the
@@ -480,9 +495,12 @@ struct NetBuilder {
                              std::to_string(p.stride) + "," + std::to_string(p.pad) + "," + (p.residual ? "r" : "-") +
                              (p.y_f32 ? "f" : "h") + (p.split ? "s" : "") + std::to_string(p.nseg) + "," + std::to_string(p.y_pix_stride) + "," + std::to_string((long long)p.y_batch_stride);
     auto it = h->tune_cache.find(tkey);
-    if (it != h->tune_cache.end())
-      return tc_conv_plan_create(p, w, it->second[0], it->second[1], it->second[2], it->second[3], it->second[4],
-                                 it->second[5]);
+    if (it != h->tune_cache.end()) {
+      TcConvPlan* pl = tc_conv_plan_create(p, w, it->second[0], it->second[1], it->second[2], it->second[3], it->second[4],
+                                           it->second[5], it->second[6]);
+      if (tc_conv_plan_sk(pl)) tc_conv_plan_set_sk_workspace(pl, sk_workspace());
+      return pl;
+    }
     const int bns[4] = {256, 128, 64, 32};
     const int sts[3] = {0, 3, 2};
     const int grids[3] = {148, 296, 1 << 30};
@@ -505,6 +523,8 @@ struct NetBuilder {
       ts = h->tune_stream;
       YB_CHECK_CUDA(cudaDeviceSynchronize());
     }
+    const int nsk = h->sk_candidates ? 2 : 1;   // stream-K: persistent default grid only
+    for (int ki = 0; ki < nsk; ++ki)
     for (int di = 0; di < npdl; ++di)
     for (int ei = 0; ei < nepi; ++ei)
     for (int pi = 0; pi < npair; ++pi)
@@ -515,21 +535,24 @@ struct NetBuilder {
           if (pi && bns[bi] < 64) continue;
           if (ei && (bns[bi] < 64 || gi == 1)) continue;   // 320-thread CTAs: one per SM
           if (di && (pi || ei || gi == 1)) continue;        // PDL-friendly: single CTAs, one epilogue group, <= 1 CTA/SM of its own
+          if (ki && (gi != 0 || di || h->pdl)) continue;    // stream-K: one CTA (cluster) per SM (TPC), no PDL
           TcConvPlan* cand = nullptr;
           try {
-            cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi], pi, ei ? 2 : 1, di);
+            cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi], pi, ei ? 2 : 1, di, ki);
           } catch (const Error&) {
             continue;   // this tiling does not fit in shared memory (split precision doubles every stage)
           }
           if ((pi && !tc_conv_plan_pair(cand)) || (ei && tc_conv_plan_epi_groups(cand) != 2) ||
-              (di && !tc_conv_plan_pdl_friendly(cand))) {
+              (di && !tc_conv_plan_pdl_friendly(cand)) || (ki && !tc_conv_plan_sk(cand))) {
             tc_conv_plan_destroy(cand);
             continue;
           }
+          if (ki) tc_conv_plan_set_sk_workspace(cand, sk_workspace());
           if (h->pdl) tc_conv_plan_set_pdl(cand, 1);
           const std::string ck = std::to_string(tc_conv_plan_bn(cand)) + "/" + std::to_string(tc_conv_plan_stages(cand)) +
                                  "/" + std::to_string(tc_conv_plan_grid(cand)) + "/" + std::to_string(tc_conv_plan_pair(cand)) + "/" +
-                                 std::to_string(tc_conv_plan_epi_groups(cand)) + "/" + std::to_string(tc_conv_plan_pdl_friendly(cand));
+                                 std::to_string(tc_conv_plan_epi_groups(cand)) + "/" + std::to_string(tc_conv_plan_pdl_friendly(cand)) +
+                                 "/" + std::to_string(tc_conv_plan_sk(cand));
           if (!seen.insert(ck).second) {  // overrides were clamped to an already-timed configuration
             tc_conv_plan_destroy(cand);
             continue;
@@ -561,7 +584,7 @@ struct NetBuilder {
     cudaEventDestroy(e1);
     YB_REQUIRE(best != nullptr, "autotune: no candidate");
     h->tune_cache[tkey] = {tc_conv_plan_bn(best), tc_conv_plan_stages(best), tc_conv_plan_grid(best), tc_conv_plan_pair(best),
-                           tc_conv_plan_epi_groups(best), tc_conv_plan_pdl_friendly(best)};
+                           tc_conv_plan_epi_groups(best), tc_conv_plan_pdl_friendly(best), tc_conv_plan_sk(best)};
     return best;
   }
 };
@@ -788,12 +811,14 @@ static const HostTensor& need(yb_handle* h, const std::string& name) {
 }
 
 ConvW& yb_handle::get_conv(const std::string& conv_key, const std::string& bn_key, bool want_tc, bool want_f32,
-                           bool want_f16, int pack) {
+                           bool want_f16, int pack, int cin_pad) {
   ConvW& cw = convs[conv_key];
   const HostTensor& w = need(this, conv_key + ".weight");
   YB_REQUIRE(w.shape.size() == 4, ("weight " + conv_key + " is not 4-D").c_str());
   const int Co = (int)w.shape[0], Ci = (int)w.shape[1], KH = (int)w.shape[2], KW = (int)w.shape[3];
+  const int CiP = (want_tc && pack == 0 && cin_pad > Ci) ? cin_pad : Ci;   // row length of the tcgen05 packing
   if (cw.Cout == 0) {
+    cw.cin_pad = CiP;
     cw.Cin = Ci;
     cw.Cout = Co;
     cw.KH = KH;
@@ -855,7 +880,7 @@ ConvW& yb_handle::get_conv(const std::string& conv_key, const std::string& bn_ke
     const int e = split_exponent(mx);
     const float up = ldexpf(1.f, e);
     cw.out_scale = ldexpf(1.f, -e);
-    const size_t kpad = (pack == 2) ? (size_t)stem_tc_kpad(KH) : K;   // plane length along K
+    const size_t kpad = (pack == 2) ? (size_t)stem_tc_kpad(KH) : (size_t)taps * CiP;   // plane length along K
     std::vector<__half> pk(2 * kpad * Co, __float2half_rn(0.f));
     for (int o = 0; o < Co; ++o)
       for (int c = 0; c < Ci; ++c)
@@ -869,16 +894,16 @@ ConvW& yb_handle::get_conv(const std::string& conv_key, const std::string& bn_ke
           } else if (pack == 1) {   // DCN: [Cout][hi(9*Cin) | lo(9*Cin)], k = t*Cin + c
             hi = (size_t)o * 2 * K + (size_t)t * Ci + c;
             plane = K;
-          } else {                  // [tap][Cout][hi(Cin) | lo(Cin)]
-            hi = ((size_t)t * Co + o) * 2 * Ci + c;
-            plane = (size_t)Ci;
+          } else {                  // [tap][Cout][hi(CinP) | lo(CinP)]
+            hi = ((size_t)t * Co + o) * 2 * CiP + c;
+            plane = (size_t)CiP;
           }
           split_pack(v, up, &pk[hi], &pk[hi + plane]);
         }
     cw.w_tc = (__half*)dmalloc(weight_allocs, pk.size() * 2);
     YB_CHECK_CUDA(cudaMemcpy(cw.w_tc, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
   } else if (need_tc) {
-    std::vector<__half> pk(K * Co);
+    std::vector<__half> pk((size_t)taps * CiP * Co, __float2half_rn(0.f));
     if (pack == 2) {
       // stem: [Cout][Kpad], k = c*taps + t (the OIHW flattening), zero padded to a multiple of 64
       const size_t kpad = (size_t)stem_tc_kpad(KH);
@@ -897,7 +922,7 @@ ConvW& yb_handle::get_conv(const std::string& conv_key, const std::string& bn_ke
       for (int o = 0; o < Co; ++o)
         for (int c = 0; c < Ci; ++c)
           for (int t = 0; t < taps; ++t)
-            pk[((size_t)t * Co + o) * Ci + c] = __float2half_rn(w.data[((size_t)o * Ci + c) * taps + t] * scale[o]);
+            pk[((size_t)t * Co + o) * CiP + c] = __float2half_rn(w.data[((size_t)o * Ci + c) * taps + t] * scale[o]);
     }
     cw.w_tc = (__half*)dmalloc(weight_allocs, pk.size() * 2);
     YB_CHECK_CUDA(cudaMemcpy(cw.w_tc, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));

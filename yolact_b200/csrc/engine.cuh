@@ -26,6 +26,8 @@ struct HostTensor {
 // One convolution's device-resident parameters (BatchNorm already folded).
 struct ConvW {
   int Cin = 0, Cout = 0, KH = 0, KW = 0;
+  int cin_pad = 0;           // w_tc rows are padded with zeros to this many input channels (a multiple of 64) when the
+                             // producer writes zero-padded pixels (Darknet: 32 -> 64); 0 = Cin
   float* w_f32 = nullptr;    // [KH*KW*Cin][Cout]           (SIMT fp32)
   __half* w_f16 = nullptr;   // [KH*KW*Cin][Cout]           (SIMT fp16)
   __half* w_tc = nullptr;    // [KH*KW][Cout][Cin]          (tcgen05), or [1][Cout][9*Cin] for DCN
@@ -60,6 +62,7 @@ struct Executor {
   std::vector<TcConvPlan*> plans;
   std::vector<StemTcPlan*> stem_plans;
   std::vector<DcnTcPlan*> dcn_plans;
+  void* sk_ws[8] = {};           // stream-K workspace per graph lane (plans of one lane are stream-ordered)
   std::vector<Op> ops;           // the conv stack (yb_forward)
   size_t fork_index = 0;         // ops[fork_index..] may run on their lanes concurrently (0 = no fork)
   float* d_in = nullptr;         // NCHW fp32 copy of the input (stable address for graph replay)
@@ -116,7 +119,8 @@ struct yb_handle {
   std::map<std::string, yb::ConvW> convs;
   std::map<std::string, std::unique_ptr<yb::Executor>> execs;
   std::vector<void*> weight_allocs;
-  std::map<std::string, std::array<int, 6>> tune_cache;  // layer shape -> (BN, stages, grid, pair, epilogue groups, pdl-friendly) from the autotuner
+  std::map<std::string, std::array<int, 7>> tune_cache;  // layer shape -> (BN, stages, grid, pair, epilogue groups, pdl-friendly, stream-K) from the autotuner
+  bool sk_candidates = true;      // YB_SK=0: the autotuner skips stream-K plans
   cudaStream_t tune_stream = nullptr;   // private stream of the autotuner when PDL candidates are timed
   yb::Executor* last_exec = nullptr;
   // standalone op workspaces
@@ -138,7 +142,7 @@ struct yb_handle {
 
   // ---- weights
   yb::ConvW& get_conv(const std::string& conv_key, const std::string& bn_key, bool want_tc, bool want_f32,
-                      bool want_f16, int pack = 0);
+                      bool want_f16, int pack = 0, int cin_pad = 0);
   int peek_cout(const std::string& conv_key) const;
   yb::ConvW& get_fused_head(const std::string& head_name);
   void finalize();

@@ -57,7 +57,11 @@ struct TcConvPlan;  // opaque: tensor maps + tiling; built once per (layer, shap
 TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override = 0,
                                 int stages_override = 0, int grid_override = 0, int pair_override = 0,
                                 int epi_override = 0,    // epi_override == 2: two 4-warp epilogue groups (320 threads)
-                                int pdl_override = 0);   // > 0: plan sized for 2 CTAs/SM + programmatic dependent launch
+                                int pdl_override = 0,    // > 0: plan sized for 2 CTAs/SM + programmatic dependent launch
+                                int sk_override = 0);    // > 0: stream-K (needs tc_conv_plan_set_sk_workspace before launch)
+int tc_conv_plan_sk(const TcConvPlan* plan);
+size_t tc_conv_sk_workspace_bytes();
+void tc_conv_plan_set_sk_workspace(TcConvPlan* plan, void* ws);
 int tc_conv_plan_pdl_friendly(const TcConvPlan* plan);
 int tc_conv_plan_pair(const TcConvPlan* plan);
 int tc_conv_plan_epi_groups(const TcConvPlan* plan);
@@ -77,7 +81,7 @@ int stem_tc_kpad(int ks);   // K = 3*ks*ks rounded up to 64
 // split: w_packed is [cout][hi(kpad) | lo(kpad)] scaled by 1 / out_scale, y is [.., hi(cout) | lo(cout)]
 StemTcPlan* stem_tc_plan_create(const float* x_nchw, const __half* w_packed, const float* bias, __half* y, int B,
                                 int H, int W, int ks, int stride, int pad, int cout, int act, int split = 0,
-                                float out_scale = 1.f);
+                                float out_scale = 1.f, int cpad = 0);   // cpad > cout: zero-padded output pixels
 void stem_tc_plan_destroy(StemTcPlan* plan);
 void stem_tc_plan_set_worker_groups(StemTcPlan* plan, int wg);   // 2: two threads per pixel (7x7 stem)
 void launch_stem_tc(const StemTcPlan* plan, cudaStream_t stream, LaunchCounter* lc);

@@ -80,6 +80,13 @@ struct alignas(64) TcParams {
   int split;
   int cin;              // logical input channels: the lo plane starts at channel `cin` of the A / B tensor maps
   float out_scale;
+  // stream-K (sk != 0): the units' k-block iterations are dealt out in equal contiguous shares, one share per CTA /
+  // cluster; a share that ends inside a unit leaves an fp32 partial tile in sk_ws (one slot of 128 x BN floats per
+  // CTA) and raises sk_flags[2 * slot + epilogue group]; the CTA holding the unit's FIRST k-blocks adds the partials
+  // and runs the epilogue
+  int sk;
+  float* sk_ws;
+  int* sk_flags;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -221,6 +228,43 @@ __device__ __forceinline__ TileCoord decode_unit(const TcParams& p, int u, int r
   return decode_mn(p, PAIR ? 2 * mg + rank : mg, nt, BN);
 }
 
+// Work of one CTA (cluster): a list of segments (unit, [k0, k1)).  Without stream-K: whole units unit0, unit0 + step, ...
+// With stream-K: the contiguous iteration range [cid * I / G, (cid + 1) * I / G) of I = units * k-blocks, cut at unit
+// boundaries -- so a CTA's first segment may be the TAIL of a unit (k0 > 0: dumped as a partial) and its last one the
+// HEAD of a unit (k0 == 0, k1 < num_kb: this CTA collects the partials and finishes the unit).
+struct WorkIter {
+  int num_kb, num_units, ustep, sk, u;
+  long long it, it_hi;
+  __device__ __forceinline__ static long long share_lo(long long total, int c, int G) { return total * c / G; }
+  __device__ __forceinline__ void init(int sk_, int num_kb_, int num_units_, int unit0, int ustep_) {
+    sk = sk_;
+    num_kb = num_kb_;
+    num_units = num_units_;
+    ustep = ustep_;
+    u = unit0;
+    const long long total = (long long)num_units_ * num_kb_;
+    it = share_lo(total, unit0, ustep_);
+    it_hi = share_lo(total, unit0 + 1, ustep_);
+  }
+  __device__ __forceinline__ bool next(int& uu, int& k0, int& k1) {
+    if (!sk) {
+      if (u >= num_units) return false;
+      uu = u;
+      k0 = 0;
+      k1 = num_kb;
+      u += ustep;
+      return true;
+    }
+    if (it >= it_hi) return false;
+    uu = (int)(it / num_kb);
+    k0 = (int)(it - (long long)uu * num_kb);
+    const long long rem = it_hi - it;
+    k1 = (rem < (long long)(num_kb - k0)) ? (int)(k0 + rem) : num_kb;
+    it += k1 - k0;
+    return true;
+  }
+};
+
 template <int BN, bool PAIR, int H, bool SPLIT>
 __global__ void __launch_bounds__(64 + 128 * H)
 tc_conv_kernel(const __grid_constant__ TcParams p) {
@@ -307,9 +351,12 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       const uint32_t tx_bytes = ((uint32_t)p.a_box_bytes + (uint32_t)B_PLANE_BYTES) * (uint32_t)NPL * (PAIR ? 2u : 1u);
       const uint32_t leader_full = PAIR ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0u;
       uint32_t kbg = 0;
-      for (int u = unit0; u < num_units; u += ustep) {
+      WorkIter wi;
+      wi.init(p.sk, num_kb, num_units, unit0, ustep);
+      int u, k0, k1;
+      while (wi.next(u, k0, k1)) {
         const TileCoord tc_ = decode_unit<PAIR>(p, u, rank, BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+        for (int kb = k0; kb < k1; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)stages;
           const uint32_t it = kbg / (uint32_t)stages;
           mbar_wait(&empty_bar[s], (it & 1u) ^ 1u);
@@ -345,13 +392,16 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0 && rank == 0) {   // in a pair only the even CTA issues (for both)
       uint32_t kbg = 0, t = 0;
-      for (int u = unit0; u < num_units; u += ustep, ++t) {
+      WorkIter wi;
+      wi.init(p.sk, num_kb, num_units, unit0, ustep);
+      int u, k0, k1;
+      for (; wi.next(u, k0, k1); ++t) {
         const uint32_t acc = t % (uint32_t)acc_stages;
         const uint32_t use = t / (uint32_t)acc_stages;
         mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * (uint32_t)(NPL * BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+        for (int kb = k0; kb < k1; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)stages;
           const uint32_t it = kbg / (uint32_t)stages;
           mbar_wait(&full_bar[s], it & 1u);
@@ -366,15 +416,15 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 field
-            mma(da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (kb > 0 || k > 0) ? 1u : 0u);
+            mma(da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (kb > k0 || k > 0) ? 1u : 0u);
           }
           if (SPLIT) {
             const uint64_t dal = make_sw128_desc(sa + A_STAGE_BYTES);
             const uint64_t dbl = make_sw128_desc(sb + B_PLANE_BYTES);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // A_lo * W_hi -> second accumulator
-              if (PAIR) umma_f16_pair(tmem_d + BN, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              else umma_f16(tmem_d + BN, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              if (PAIR) umma_f16_pair(tmem_d + BN, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > k0 || k > 0) ? 1u : 0u);
+              else umma_f16(tmem_d + BN, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb > k0 || k > 0) ? 1u : 0u);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // A_hi * W_lo -> second accumulator
               if (PAIR) umma_f16_pair(tmem_d + BN, da + (uint64_t)(2 * k), dbl + (uint64_t)(2 * k), p.idesc, 1u);
@@ -417,15 +467,27 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
     // residual chunk stream (epi_tma only): this group's chunks, in order and across tiles; chunk number gq of
     // the group lives in residual tile (H == 2 ? hgrp : gq & 1); the issuer keeps NBUF chunks in flight.
     // (pf_tile, pf_c) = next chunk to fetch.
-    int pf_tile = unit0, pf_c = hgrp;
+    WorkIter pfi;                    // walks ahead over the segments that run the epilogue proper (k0 == 0)
+    pfi.init(p.sk, num_kb, num_units, unit0, ustep);
+    int pf_tile = -1, pf_c = hgrp;
+    auto pf_advance = [&]() {
+      int uu, a, b;
+      pf_tile = -1;
+      while (pfi.next(uu, a, b))
+        if (a == 0) {
+          pf_tile = uu;
+          break;
+        }
+    };
+    pf_advance();
     uint32_t pf_g = 0;
     auto prefetch_res = [&]() {
-      while (pf_tile < num_units) {
+      while (pf_tile >= 0) {
         const TileCoord tcp = decode_unit<PAIR>(p, pf_tile, rank, BN);
         const int nch = (min(BN, p.Cout - tcp.n0) + 63) >> 6;
         if (pf_c >= nch) {            // this group has no (more) chunks in that tile
           pf_c = hgrp;
-          pf_tile += ustep;
+          pf_advance();
           continue;
         }
         const uint32_t buf = (NBUF == 1) ? (uint32_t)hgrp : (pf_g & 1u);
@@ -443,9 +505,21 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       for (int i = 0; i < NBUF; ++i) prefetch_res();
     }
 
-    uint32_t t = 0, g = 0;  // local tile counter, staged-chunk counter of this group
-    for (int u = unit0; u < num_units; u += ustep, ++t) {
+    uint32_t t = 0, g = 0;  // local segment counter, staged-chunk counter of this group
+    WorkIter wi;
+    wi.init(p.sk, num_kb, num_units, unit0, ustep);
+    int u, k0, k1;
+    // stream-K bookkeeping: this CTA's workspace slot, and (for the head of a split unit) the slots it collects
+    const int sk_slot = PAIR ? 2 * unit0 + rank : unit0;
+    for (; wi.next(u, k0, k1); ++t) {
       const TileCoord tc_ = decode_unit<PAIR>(p, u, rank, BN);
+      const bool sk_dump = (k0 > 0);                       // tail / middle of a unit: leave a partial tile
+      const bool sk_head = (k0 == 0 && k1 < num_kb);       // head of a split unit: add the partials, then finish
+      int sk_parts = 0;
+      if (sk_head) {
+        const long long total = (long long)num_units * num_kb, unit_end = (long long)(u + 1) * num_kb;
+        while (unit0 + 1 + sk_parts < ustep && WorkIter::share_lo(total, unit0 + 1 + sk_parts, ustep) < unit_end) ++sk_parts;
+      }
       const int x0 = tc_.x0, y0 = tc_.y0, b = tc_.b, n0 = tc_.n0;
       const uint32_t acc = t % (uint32_t)acc_stages;
       const uint32_t use = t / (uint32_t)acc_stages;
@@ -459,10 +533,56 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       tc_fence_after();
       group_sync();   // bias visible; the group's readers of the previous tile's bias are done
 
-      if (p.epi_tma) {
+      if (sk_dump) {
+        // ---- stream-K partial: the combined fp32 accumulator of this group's chunks goes to the CTA's workspace slot
+        const int nchunks = (min(BN, p.Cout - n0) + 63) >> 6;
+        float* wrow = p.sk_ws + ((size_t)sk_slot * BLOCK_M + (size_t)row) * BN;
+#pragma unroll 1
+        for (int c = hgrp; c < nchunks; c += H) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(tmem_acc + (uint32_t)(c * 64), r0);
+          tmem_ld32_nowait(tmem_acc + (uint32_t)(c * 64 + 32), r1);
+          if (SPLIT) {
+            uint32_t q[32];
+            tmem_ld32_nowait(tmem_acc + (uint32_t)(BN + c * 64), q);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r0[j] = __float_as_uint(__fmaf_rn(__uint_as_float(q[j]), YB_LO_INV, __uint_as_float(r0[j])));
+            tmem_ld32_nowait(tmem_acc + (uint32_t)(BN + c * 64 + 32), q);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r1[j] = __float_as_uint(__fmaf_rn(__uint_as_float(q[j]), YB_LO_INV, __uint_as_float(r1[j])));
+          }
+          tmem_ld_wait();
+          uint4* w4 = reinterpret_cast<uint4*>(wrow + c * 64);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            w4[j] = make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
+            w4[8 + j] = make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]);
+          }
+        }
+        tc_fence_before();
+        __threadfence();     // the partial is visible device-wide before the flag
+        group_sync();
+        if (issuer) {
+          release_acc(acc);
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + 2 * sk_slot + hgrp), "r"(1) : "memory");
+        }
+      } else if (p.epi_tma) {
         // ---- staged epilogue: TMEM -> regs -> (+bias, +residual from smem, act) -> swizzled smem tile
         //      -> one TMA store per 64-channel chunk (full 128-byte lines, OOB rows clipped by hardware)
         const int nchunks = (min(BN, p.Cout - n0) + 63) >> 6;
+        if (sk_head) {   // the partial tiles of this unit's other k ranges (the following CTAs / clusters left them first thing)
+          if (issuer)
+            for (int j = 1; j <= sk_parts; ++j) {
+              const int* f = p.sk_flags + 2 * (PAIR ? 2 * (unit0 + j) + rank : unit0 + j) + hgrp;
+              int v;
+              do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+              } while (v == 0);
+            }
+          group_sync();
+        }
         const int c_last = ((nchunks - 1 - hgrp) / H) * H + hgrp;   // this group's last chunk (< hgrp: none)
         if (nchunks <= hgrp) {   // nothing to read for this group in this tile
           tc_fence_before();
@@ -492,6 +612,24 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             for (int j = 0; j < 32; ++j) r1[j] = __float_as_uint(__fmaf_rn(__uint_as_float(q[j]), YB_LO_INV, __uint_as_float(r1[j])));
           }
           tmem_ld_wait();
+          if (sk_head) {
+            for (int j = 1; j <= sk_parts; ++j) {
+              const int slot = PAIR ? 2 * (unit0 + j) + rank : unit0 + j;
+              const float4* w4 = reinterpret_cast<const float4*>(p.sk_ws + ((size_t)slot * BLOCK_M + (size_t)row) * BN + c * 64);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 a = __ldcg(w4 + i), b = __ldcg(w4 + 8 + i);
+                r0[4 * i] = __float_as_uint(__uint_as_float(r0[4 * i]) + a.x);
+                r0[4 * i + 1] = __float_as_uint(__uint_as_float(r0[4 * i + 1]) + a.y);
+                r0[4 * i + 2] = __float_as_uint(__uint_as_float(r0[4 * i + 2]) + a.z);
+                r0[4 * i + 3] = __float_as_uint(__uint_as_float(r0[4 * i + 3]) + a.w);
+                r1[4 * i] = __float_as_uint(__uint_as_float(r1[4 * i]) + b.x);
+                r1[4 * i + 1] = __float_as_uint(__uint_as_float(r1[4 * i + 1]) + b.y);
+                r1[4 * i + 2] = __float_as_uint(__uint_as_float(r1[4 * i + 2]) + b.z);
+                r1[4 * i + 3] = __float_as_uint(__uint_as_float(r1[4 * i + 3]) + b.w);
+              }
+            }
+          }
           if (has_res) mbar_wait(&res_full_bar[buf], (NBUF == 1) ? (g & 1u) : ((g >> 1) & 1u));
           const int nbase = n0 + c * 64;
           const float* sb = my_bias + c * 64;
@@ -518,6 +656,11 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
             if (has_res) prefetch_res();   // the group is done reading res_tile[buf]: refill it
           }
         }
+        if (sk_head && issuer)   // every thread of the group has read the partials (barrier above): re-arm the flags
+          for (int j = 1; j <= sk_parts; ++j)
+            asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + 2 * (PAIR ? 2 * (unit0 + j) + rank : unit0 + j) + hgrp),
+                         "r"(0)
+                         : "memory");
       } else {
         // ---- direct epilogue (fp32 / unaligned outputs: the head tensors): each warp transposes its
         //      32 rows x 32 columns through shared memory so that a store instruction writes 32
@@ -665,6 +808,7 @@ void tc::encode_map_f16(CUtensorMap* map, const void* base, int rank, const uint
 struct TcConvPlan {
   TcParams prm;
   int split = 0;
+  int sk = 0;           // stream-K requested (effective once a workspace is attached: prm.sk)
   int BN = 128;
   int pair = 0;
   int epi_groups = 1;   // H: 4-warp epilogue groups per CTA
@@ -683,7 +827,7 @@ bool tc_conv_supported(const ConvProblem& p) {
 }
 
 TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override, int stages_override,
-                                int grid_override, int pair_override, int epi_override, int pdl_override) {
+                                int grid_override, int pair_override, int epi_override, int pdl_override, int sk_override) {
   YB_REQUIRE(tc_conv_supported(p), "tc_conv: unsupported problem");
   YB_REQUIRE(p.Ho == (p.H + 2 * p.pad - p.KH) / p.stride + 1, "tc_conv: bad Ho");
   YB_REQUIRE(p.Wo == (p.W + 2 * p.pad - p.KW) / p.stride + 1, "tc_conv: bad Wo");
@@ -799,7 +943,17 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   const int num_tiles = (pair ? (q.m_tiles + 1) / 2 : q.m_tiles) * q.n_tiles;   // work units (pairs of M tiles when paired)
   int grid = std::min(num_tiles, grid_override > 0 ? (pair ? std::max(1, grid_override / 2) : grid_override) : (pair ? 74 : 148));
   if (pair) grid = std::min(grid, 74);   // one cluster per TPC: 148 SMs = 74 CTA pairs, one CTA per SM
-  q.acc_stages = (grid < num_tiles) ? 2 : 1;
+  // stream-K: one share of the k-block iterations per SM (cluster), whatever the unit count -- worth it only when the
+  // units do not fill whole waves; needs the staged (TMA) epilogue and co-resident CTAs (<= one per SM)
+  const long long total_it = (long long)num_tiles * q.ntaps * q.kchunks;
+  int sk = (sk_override > 0 && q.epi_tma && !(pdl_override > 0)) ? 1 : 0;
+  if (sk) {
+    const int gsk = std::min<long long>(grid_override > 0 ? grid : (pair ? 74 : 148), total_it);
+    if (gsk <= 1 || num_tiles % gsk == 0) sk = 0;   // whole waves already: nothing to balance
+    else grid = gsk;
+  }
+  plan->sk = sk;
+  q.acc_stages = (grid < num_tiles || sk) ? 2 : 1;
   if (q.acc_stages * npl * BN > 512) q.acc_stages = 1;   // split: two accumulators per tile (2 * BN columns)
   int tmem_cols = 32;
   while (tmem_cols < q.acc_stages * npl * BN) tmem_cols *= 2;
@@ -807,7 +961,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   // get the SAME accumulator address, which the single cta_group::2 MMA requires.
   if (pair) tmem_cols = 512;
   q.tmem_cols = tmem_cols;
-  const int tiles_per_cta = ceil_div(num_tiles, grid);
+  const int tiles_per_cta = sk ? 2 : ceil_div(num_tiles, grid);
   // two epilogue groups (8 warps) work on two 64-channel chunks at once; pointless for a single-chunk tile
   // PDL-friendly plan: <= ~108 KB of shared memory, one epilogue group (192 threads x 122 registers) and <= 256 TMEM
   // columns, so a CTA of the NEXT layer can become resident beside it and overlap its prologue + first weight tiles
@@ -947,6 +1101,15 @@ int tc_conv_plan_grid(const TcConvPlan* plan) { return (int)plan->grid.x; }
 int tc_conv_plan_pair(const TcConvPlan* plan) { return plan->pair; }
 int tc_conv_plan_epi_groups(const TcConvPlan* plan) { return plan->epi_groups; }
 int tc_conv_plan_pdl_friendly(const TcConvPlan* plan) { return plan->pdl_friendly; }
+int tc_conv_plan_sk(const TcConvPlan* plan) { return plan->sk; }
+size_t tc_conv_sk_workspace_bytes() { return (size_t)148 * BLOCK_M * 256 * sizeof(float) + 148 * 2 * sizeof(int); }
+// ws: tc_conv_sk_workspace_bytes() of device memory whose LAST 148 * 2 ints (the flags) are zero; kernels that share a
+// workspace must be stream-ordered (each launch leaves the flags zero again)
+void tc_conv_plan_set_sk_workspace(TcConvPlan* plan, void* ws) {
+  plan->prm.sk = (plan->sk && ws) ? 1 : 0;
+  plan->prm.sk_ws = reinterpret_cast<float*>(ws);
+  plan->prm.sk_flags = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + (size_t)148 * BLOCK_M * 256 * sizeof(float));
+}
 
 template <int BN, bool PAIR, int H, bool SPLIT>
 static void launch_bn(const TcConvPlan* plan, cudaStream_t stream) {
