@@ -177,6 +177,11 @@ int yb_create(const yb_config* cfg, int device, yb_handle** out) {
   h->cfg = *cfg;
   h->device = device;
   h->ops_only = (cfg->backbone == YB_BACKBONE_NONE);
+  // measured defaults (profiles/r2_*): programmatic dependent launch gains 3.6 % of the conv stack in the single-pass
+  // fp16 mode and loses 1.5 % in the split mode (whose plans fill the SM, nothing can become resident early); stream-K
+  // gains 1.6 % in the split mode and nothing in the fp16 mode
+  h->pdl = (cfg->precision == YB_PREC_F16TC);
+  h->sk_candidates = (cfg->precision == YB_PREC_F16X3);
   if (const char* at = getenv("YB_AUTOTUNE")) h->autotune = (atoi(at) != 0);
   if (const char* pc = getenv("YB_PAIR")) h->pair_candidates = (atoi(pc) != 0);
   if (const char* ec = getenv("YB_EPI2")) h->epi2_candidates = (atoi(ec) != 0);

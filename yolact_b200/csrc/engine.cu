@@ -228,10 +228,14 @@ struct NetBuilder {
                          stem_tc_supported(k, stride, pad, in.C, h->peek_cout(key));
     ConvW& w = stem_tc ? h->get_conv(key, bn, /*want_tc=*/true, false, false, /*pack=*/2)
                        : h->get_conv(key, bn, /*want_tc=*/tc, /*want_f32=*/!tc && !simt_half, /*want_f16=*/simt_half, 0,
-                                     /*cin_pad=*/tc ? in.C : 0);
+                                     /*cin_pad=*/tc ? in.C : 0,
+                                     // a half-precision output narrower than 64 channels (Darknet's first block: 32)
+                                     // is written as zero-padded 64-channel pixels for the tcgen05 conv that follows
+                                     /*cout_pad=*/(tc && !out_f32 && !ospec && !residual) ? ((h->peek_cout(key) + 63) / 64) * 64 : 0);
     YB_REQUIRE((w.Cin == in.C || (tc && w.cin_pad == in.C)) && w.KH == k && w.KW == k,
                ("conv " + key + ": weight shape mismatch").c_str());
-    p.Cout = w.Cout;
+    const int cout_eff = (tc && w.cout_pad > w.Cout) ? w.cout_pad : w.Cout;   // incl. zero padding channels
+    p.Cout = cout_eff;
     p.bias = w.bias;
     p.out_scale = w.out_scale;
     Act out;
@@ -248,11 +252,11 @@ struct NetBuilder {
       p.y_pix_stride = ospec->pix_stride;
     } else {
       // the tcgen05 stem zero-pads its pixels to a multiple of 64 channels for the tensor-core conv that follows
-      const int out_c = stem_tc ? ((w.Cout + 63) / 64) * 64 : w.Cout;
+      const int out_c = stem_tc ? ((w.Cout + 63) / 64) * 64 : cout_eff;
       out = alloc_act(in.B, p.Ho, p.Wo, out_c, out_f32);
       p.y = out.ptr;
       p.y_f32 = (f16 && out.f32) ? 1 : 0;
-      const int ps = out.split ? 2 * w.Cout : w.Cout;
+      const int ps = out.split ? 2 * cout_eff : cout_eff;
       p.y_batch_stride = (int64_t)p.Ho * p.Wo * ps;
       p.y_pix_stride = ps;
     }
@@ -811,13 +815,15 @@ static const HostTensor& need(yb_handle* h, const std::string& name) {
 }
 
 ConvW& yb_handle::get_conv(const std::string& conv_key, const std::string& bn_key, bool want_tc, bool want_f32,
-                           bool want_f16, int pack, int cin_pad) {
+                           bool want_f16, int pack, int cin_pad, int cout_pad) {
   ConvW& cw = convs[conv_key];
   const HostTensor& w = need(this, conv_key + ".weight");
   YB_REQUIRE(w.shape.size() == 4, ("weight " + conv_key + " is not 4-D").c_str());
   const int Co = (int)w.shape[0], Ci = (int)w.shape[1], KH = (int)w.shape[2], KW = (int)w.shape[3];
   const int CiP = (want_tc && pack == 0 && cin_pad > Ci) ? cin_pad : Ci;   // row length of the tcgen05 packing
+  const int CoP = (want_tc && pack == 0 && cout_pad > Co) ? cout_pad : Co;  // rows of the tcgen05 packing (zeros beyond Co)
   if (cw.Cout == 0) {
+    cw.cout_pad = CoP;
     cw.cin_pad = CiP;
     cw.Cin = Ci;
     cw.Cout = Co;
@@ -881,7 +887,7 @@ ConvW& yb_handle::get_conv(const std::string& conv_key, const std::string& bn_ke
     const float up = ldexpf(1.f, e);
     cw.out_scale = ldexpf(1.f, -e);
     const size_t kpad = (pack == 2) ? (size_t)stem_tc_kpad(KH) : (size_t)taps * CiP;   // plane length along K
-    std::vector<__half> pk(2 * kpad * Co, __float2half_rn(0.f));
+    std::vector<__half> pk(2 * kpad * CoP, __float2half_rn(0.f));
     for (int o = 0; o < Co; ++o)
       for (int c = 0; c < Ci; ++c)
         for (int t = 0; t < taps; ++t) {
@@ -895,7 +901,7 @@ ConvW& yb_handle::get_conv(const std::string& conv_key, const std::string& bn_ke
             hi = (size_t)o * 2 * K + (size_t)t * Ci + c;
             plane = K;
           } else {                  // [tap][Cout][hi(CinP) | lo(CinP)]
-            hi = ((size_t)t * Co + o) * 2 * CiP + c;
+            hi = ((size_t)t * CoP + o) * 2 * CiP + c;
             plane = (size_t)CiP;
           }
           split_pack(v, up, &pk[hi], &pk[hi + plane]);
@@ -903,7 +909,7 @@ ConvW& yb_handle::get_conv(const std::string& conv_key, const std::string& bn_ke
     cw.w_tc = (__half*)dmalloc(weight_allocs, pk.size() * 2);
     YB_CHECK_CUDA(cudaMemcpy(cw.w_tc, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
   } else if (need_tc) {
-    std::vector<__half> pk((size_t)taps * CiP * Co, __float2half_rn(0.f));
+    std::vector<__half> pk((size_t)taps * CiP * CoP, __float2half_rn(0.f));
     if (pack == 2) {
       // stem: [Cout][Kpad], k = c*taps + t (the OIHW flattening), zero padded to a multiple of 64
       const size_t kpad = (size_t)stem_tc_kpad(KH);
@@ -922,14 +928,15 @@ ConvW& yb_handle::get_conv(const std::string& conv_key, const std::string& bn_ke
       for (int o = 0; o < Co; ++o)
         for (int c = 0; c < Ci; ++c)
           for (int t = 0; t < taps; ++t)
-            pk[((size_t)t * Co + o) * CiP + c] = __float2half_rn(w.data[((size_t)o * Ci + c) * taps + t] * scale[o]);
+            pk[((size_t)t * CoP + o) * CiP + c] = __float2half_rn(w.data[((size_t)o * Ci + c) * taps + t] * scale[o]);
     }
     cw.w_tc = (__half*)dmalloc(weight_allocs, pk.size() * 2);
     YB_CHECK_CUDA(cudaMemcpy(cw.w_tc, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
   }
   if (!cw.bias && (has_bias || has_bn)) {
-    cw.bias = (float*)dmalloc(weight_allocs, (size_t)Co * 4);
-    YB_CHECK_CUDA(cudaMemcpy(cw.bias, shift.data(), (size_t)Co * 4, cudaMemcpyHostToDevice));
+    shift.resize((size_t)std::max(Co, cw.cout_pad), 0.f);   // zero bias for the padding channels
+    cw.bias = (float*)dmalloc(weight_allocs, shift.size() * 4);
+    YB_CHECK_CUDA(cudaMemcpy(cw.bias, shift.data(), shift.size() * 4, cudaMemcpyHostToDevice));
   }
   return cw;
 }

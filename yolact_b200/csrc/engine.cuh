@@ -26,6 +26,8 @@ struct HostTensor {
 // One convolution's device-resident parameters (BatchNorm already folded).
 struct ConvW {
   int Cin = 0, Cout = 0, KH = 0, KW = 0;
+  int cout_pad = 0;          // w_tc / bias carry this many output channels (zero rows beyond Cout): a 32-channel layer
+                             // then writes 64-channel pixels the next tcgen05 conv can consume; 0 = Cout
   int cin_pad = 0;           // w_tc rows are padded with zeros to this many input channels (a multiple of 64) when the
                              // producer writes zero-padded pixels (Darknet: 32 -> 64); 0 = Cin
   float* w_f32 = nullptr;    // [KH*KW*Cin][Cout]           (SIMT fp32)
@@ -106,7 +108,7 @@ struct yb_handle {
   bool use_graphs = true;
   bool profiling = false;
   bool fuse_heads = true;   // YB_FUSE_HEADS=0: three separate head convs per level
-  bool pdl = false;         // YB_PDL=1: programmatic dependent launch between consecutive tcgen05 convs
+  bool pdl = false;         // programmatic dependent launch between consecutive tcgen05 convs: on in the fp16 mode (YB_PDL=0/1)
   bool stem_on_tc = true;   // YB_STEM_TC=0 falls back to the SIMT stem
   bool dcn_fused = true;    // YB_DCN_FUSED=0: separate gather kernel + fp16 column buffer + 1x1 tcgen05 contraction (round 1)
   int stem_wg = 0;          // YB_STEM_WG=1|2: worker threads per output pixel in the 7x7 stem; 0 = 1 (f16: 2 measured slower, 0.176 vs 0.154 ms), 2 in the split mode
@@ -120,7 +122,7 @@ struct yb_handle {
   std::map<std::string, std::unique_ptr<yb::Executor>> execs;
   std::vector<void*> weight_allocs;
   std::map<std::string, std::array<int, 7>> tune_cache;  // layer shape -> (BN, stages, grid, pair, epilogue groups, pdl-friendly, stream-K) from the autotuner
-  bool sk_candidates = true;      // YB_SK=0: the autotuner skips stream-K plans
+  bool sk_candidates = true;      // the autotuner times stream-K plans: on in the split mode (YB_SK=0/1)
   cudaStream_t tune_stream = nullptr;   // private stream of the autotuner when PDL candidates are timed
   yb::Executor* last_exec = nullptr;
   // standalone op workspaces
@@ -142,7 +144,7 @@ struct yb_handle {
 
   // ---- weights
   yb::ConvW& get_conv(const std::string& conv_key, const std::string& bn_key, bool want_tc, bool want_f32,
-                      bool want_f16, int pack = 0, int cin_pad = 0);
+                      bool want_f16, int pack = 0, int cin_pad = 0, int cout_pad = 0);
   int peek_cout(const std::string& conv_key) const;
   yb::ConvW& get_fused_head(const std::string& head_name);
   void finalize();

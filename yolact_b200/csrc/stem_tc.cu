@@ -12,13 +12,9 @@
 // TMA-loads the [Cout][Kpad] weight tile, issues ceil(K/16) tcgen05.mma (M=128, N=Cout) and commits;
 // the workers then read their accumulator row from TMEM and store one full 64/128-byte line each.
 // Several CTAs per SM overlap gather / MMA / epilogue of different tiles.
-//
-// PATCH variant (default): the CTA's 128 pixels are an 8 x 16 block of ONE image and the (8*S + K - S) x (16*S + K - S) x 3
-// input patch they share is first staged in shared memory with coalesced loads (zero padding applied there); the
-// workers then build their rows from shared memory.  The per-thread gather of the flat variant issued 147 scalar
-// global loads per pixel (12x more L1 traffic than input bytes) and was latency bound: 0.16 ms (f16) / 0.47 ms (split,
-// one CTA per SM) for 8 frames.
-#include <stdlib.h>
+// (Measured and removed in round 2: an 8 x 16 tile variant that staged the shared input patch in shared memory first --
+// 0.225 vs 0.16 ms in the fp16 mode, 0.39 vs 0.39 ms in the split mode: the gather is not the bound, the serial
+// gather -> MMA -> store chain of a single-tile CTA is; in the split mode the 144 KB of operand tiles allow one CTA per SM.)
 #include "tc_common.cuh"
 
 namespace yb {
@@ -36,7 +32,6 @@ struct alignas(64) StemParams {
   const float* bias;
   __half* y;
   int B, H, W, Ho, Wo;
-  int tiles_x, tiles_y;   // PATCH variant: 8 x 16 output tiles per image
   int cpad;               // channels per output pixel (>= COUT, multiple of 8; channels COUT..cpad-1 are written as zeros so
                           // that a tensor-core conv with Cin % 64 == 0 can consume a 32-channel stem, e.g. Darknet's)
   long long M;
@@ -51,14 +46,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // SPLIT (YB_PREC_F16X3): the patch is written as a hi and a lo fp16 tile, the weights come as [Cout][hi(Kpad) | lo(Kpad)],
 // three MMA passes (hi*hi + lo*hi + hi*lo) accumulate in one fp32 tile and the output pixel is [hi(COUT) | lo(COUT)].
-constexpr int ST_TH = 8, ST_TW = 16;   // PATCH variant: output tile (rows x cols), ST_TH * ST_TW == ST_M
-
-template <int KS, int STRIDE, int PAD, int COUT, int WG, bool SPLIT, bool PATCH>
+template <int KS, int STRIDE, int PAD, int COUT, int WG, bool SPLIT>
 __global__ void __launch_bounds__(128 * WG + 32)
 stem_tc_kernel(const __grid_constant__ StemParams p) {
   constexpr int NPL = SPLIT ? 2 : 1;
-  constexpr int PR = ST_TH * STRIDE + KS - STRIDE;                 // patch rows
-  constexpr int PWD = ((ST_TW * STRIDE + KS - STRIDE) + 3) & ~3;   // patch row pitch (floats)
   constexpr int MMA_WARP = 4 * WG;
   constexpr int K = 3 * KS * KS;
   constexpr int ATOMS = (K + 63) / 64;
@@ -72,7 +63,6 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                               // [plane][atom]
   uint8_t* sB = smem + NPL * ATOMS * A_ATOM_BYTES;  // [plane][atom]
-  float* patch = reinterpret_cast<float*>(sB + NPL * ATOMS * B_ATOM_BYTES);   // [3][PR][PWD] (PATCH only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -83,28 +73,6 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
     tma_prefetch_desc(&p.tmW);
   }
   if (warp == MMA_WARP) tmem_alloc<NPL * COUT>(&s_tmem);   // split: second accumulator for the lo cross terms
-  // tile -> (image, first output row / column)
-  int tb = 0, ty0 = 0, tx0 = 0;
-  if (PATCH) {
-    int t = blockIdx.x;
-    const int txi = t % p.tiles_x;
-    t /= p.tiles_x;
-    ty0 = (t % p.tiles_y) * ST_TH;
-    tb = t / p.tiles_y;
-    tx0 = txi * ST_TW;
-    // stage the shared input patch: coalesced along the row, zero padding by predication
-    const int gy0 = ty0 * STRIDE - PAD, gx0 = tx0 * STRIDE - PAD;
-    const float* xb = p.x + (size_t)tb * 3 * p.H * p.W;
-    for (int i = tid; i < 3 * PR * PWD; i += 128 * WG + 32) {
-      const int pc = i % PWD;
-      const int rr = i / PWD;
-      const int pr = rr % PR, c = rr / PR;
-      const int gy = gy0 + pr, gx = gx0 + pc;
-      float v = 0.f;
-      if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) v = __ldg(xb + ((size_t)c * p.H + gy) * p.W + gx);
-      patch[i] = v;
-    }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -136,22 +104,15 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
   } else {
     const int row = tid & 127;
     const int wg = tid >> 7;   // worker group: which half of the k-groups / output channels this thread handles
-    long long m = (long long)blockIdx.x * ST_M + row;
-    bool valid = m < p.M;
+    const long long m = (long long)blockIdx.x * ST_M + row;
+    const bool valid = m < p.M;
     int b = 0, ho = 0, wo = 0;
-    if (PATCH) {
-      b = tb;
-      ho = ty0 + row / ST_TW;
-      wo = tx0 + row % ST_TW;
-      valid = ho < p.Ho && wo < p.Wo;
-      m = ((long long)b * p.Ho + ho) * p.Wo + wo;
-    } else if (valid) {
+    if (valid) {
       wo = (int)(m % p.Wo);
       const long long t = m / p.Wo;
       ho = (int)(t % p.Ho);
       b = (int)(t / p.Ho);
     }
-    const float* prow = patch + (row / ST_TW) * STRIDE * PWD + (row % ST_TW) * STRIDE;   // this pixel's patch origin
     const int hb = ho * STRIDE - PAD, wb = wo * STRIDE - PAD;
     unsigned rmask = 0, cmask = 0;
 #pragma unroll
@@ -177,8 +138,7 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
           float val = 0.f;
           if (k < K) {
             const int c = k / (KS * KS), r = (k % (KS * KS)) / KS, s = k % KS;
-            if (PATCH) val = prow[(c * PR + r) * PWD + s];   // padding already applied in the patch
-            else if (((rmask >> r) & 1u) && ((cmask >> s) & 1u)) val = __ldg(xb + (size_t)c * plane + r * p.W + s);
+            if (((rmask >> r) & 1u) && ((cmask >> s) & 1u)) val = __ldg(xb + (size_t)c * plane + r * p.W + s);
           }
           v[e] = val;
         }
@@ -251,19 +211,17 @@ stem_tc_kernel(const __grid_constant__ StemParams p) {
   }
 }
 
-template <int KS, int STRIDE, int PAD, int COUT, int WG, bool SPLIT, bool PATCH>
+template <int KS, int STRIDE, int PAD, int COUT, int WG, bool SPLIT>
 void launch_variant(const StemParams& prm, cudaStream_t stream) {
   constexpr int K = 3 * KS * KS;
   constexpr int ATOMS = (K + 63) / 64;
-  constexpr int PR = ST_TH * STRIDE + KS - STRIDE;
-  constexpr int PWD = ((ST_TW * STRIDE + KS - STRIDE) + 3) & ~3;
-  const size_t smem = (size_t)(SPLIT ? 2 : 1) * ATOMS * (ST_M * 128 + COUT * 128) + (PATCH ? 3 * PR * PWD * 4 : 0) + 1024;
+  const size_t smem = (size_t)(SPLIT ? 2 : 1) * ATOMS * (ST_M * 128 + COUT * 128) + 1024;
   static PerDeviceOnce attr;
   if (attr.first())
-    YB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<KS, STRIDE, PAD, COUT, WG, SPLIT, PATCH>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned grid = PATCH ? (unsigned)(prm.B * prm.tiles_x * prm.tiles_y) : (unsigned)((prm.M + ST_M - 1) / ST_M);
-  stem_tc_kernel<KS, STRIDE, PAD, COUT, WG, SPLIT, PATCH><<<grid, 128 * WG + 32, smem, stream>>>(prm);
+    YB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<KS, STRIDE, PAD, COUT, WG, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+  const unsigned grid = (unsigned)((prm.M + ST_M - 1) / ST_M);
+  stem_tc_kernel<KS, STRIDE, PAD, COUT, WG, SPLIT><<<grid, 128 * WG + 32, smem, stream>>>(prm);
 }
 
 }  // namespace
@@ -273,7 +231,6 @@ struct StemTcPlan {
   int ks, stride, pad, cout;
   int wg = 1;   // worker groups (7x7 stem only)
   int split = 0;
-  int patch = 1;   // 8 x 16 tiles with the input patch staged in shared memory (YB_STEM_PATCH=0: flat per-thread gather)
 };
 
 bool stem_tc_supported(int ks, int stride, int pad, int cin, int cout) {
@@ -303,9 +260,6 @@ StemTcPlan* stem_tc_plan_create(const float* x_nchw, const __half* w_packed, con
   q.M = (long long)B * q.Ho * q.Wo;
   q.cpad = cpad > cout ? cpad : cout;
   YB_REQUIRE(q.cpad % 8 == 0, "stem_tc: the padded channel count must be a multiple of 8");
-  q.tiles_x = (q.Wo + ST_TW - 1) / ST_TW;
-  q.tiles_y = (q.Ho + ST_TH - 1) / ST_TH;
-  if (const char* e = getenv("YB_STEM_PATCH")) plan->patch = atoi(e) != 0;
   q.act = act;
   q.out_scale = split ? out_scale : 1.f;
   plan->split = split ? 1 : 0;
@@ -322,24 +276,23 @@ StemTcPlan* stem_tc_plan_create(const float* x_nchw, const __half* w_packed, con
 void stem_tc_plan_destroy(StemTcPlan* plan) { delete plan; }
 void stem_tc_plan_set_worker_groups(StemTcPlan* plan, int wg) { plan->wg = (wg == 2 && plan->ks == 7) ? 2 : 1; }
 
-template <bool SPLIT, bool PATCH>
-static void launch_stem_sp(const StemTcPlan* plan, cudaStream_t stream) {
-  if (plan->ks == 7) {
-    if (plan->wg == 2)
-      launch_variant<7, 2, 3, 64, 2, SPLIT, PATCH>(plan->prm, stream);
-    else
-      launch_variant<7, 2, 3, 64, 1, SPLIT, PATCH>(plan->prm, stream);
-  } else {
-    launch_variant<3, 1, 1, 32, 1, SPLIT, PATCH>(plan->prm, stream);
-  }
-}
-
 void launch_stem_tc(const StemTcPlan* plan, cudaStream_t stream, LaunchCounter* lc) {
-  // (split: 144 KB of operand tiles, one CTA per SM -- two worker threads per pixel by default, engine.cu)
   if (plan->split) {
-    if (plan->patch) launch_stem_sp<true, true>(plan, stream); else launch_stem_sp<true, false>(plan, stream);
+    // the split stem holds 144 KB of operand tiles (one CTA per SM): two worker threads per pixel double the warps
+    // that hide the gather's latency (YB_STEM_WG=1 selects one)
+    if (plan->ks == 7 && plan->wg == 2)
+      launch_variant<7, 2, 3, 64, 2, true>(plan->prm, stream);
+    else if (plan->ks == 7)
+      launch_variant<7, 2, 3, 64, 1, true>(plan->prm, stream);
+    else
+      launch_variant<3, 1, 1, 32, 1, true>(plan->prm, stream);
+  } else if (plan->ks == 7) {
+    if (plan->wg == 2)
+      launch_variant<7, 2, 3, 64, 2, false>(plan->prm, stream);
+    else
+      launch_variant<7, 2, 3, 64, 1, false>(plan->prm, stream);
   } else {
-    if (plan->patch) launch_stem_sp<false, true>(plan, stream); else launch_stem_sp<false, false>(plan, stream);
+    launch_variant<3, 1, 1, 32, 1, false>(plan->prm, stream);
   }
   YB_CHECK_LAUNCH();
   if (lc) lc->n++;
