@@ -12,6 +12,10 @@
 //    on-device second opinion for the tensor-core path).
 //  * launch_dcn_gather_f16: gather to fp16 NHWC columns [B,Ho,Wo,9*C] (2 B/element instead of
 //    4, channel-contiguous 16-byte stores) consumed by the tcgen05 kernel as a 1x1 conv, K = 9*C.
+//    Round-1 path, kept behind YB_DCN_FUSED=0 as the A/B partner of the fused kernel (dcn_tc.cu), which is the default:
+//    one launch, no column buffer, 4.6 % faster on yolact_plus_base (profiles/r2_call4_summary.txt).  (A
+//    warp-cooperative variant of this gather was validated in round 2 -- +2.8 % -- and removed: the fused kernel
+//    supersedes it.)
 #include <stdlib.h>
 #include <string>
 #include "kernels.cuh"
@@ -232,74 +236,6 @@ __global__ void dcn_gather_f16_kernel(const __half* __restrict__ x, const float*
 }
 
 
-// Warp-cooperative variant (experimental, YB_DCN_GATHER=warp): one warp = one output pixel.  Lanes 0..8 each work out
-// the sampling geometry and the modulation mask of one tap (4 corner offsets, 4 bilinear weights with the mask folded
-// in); the other lanes receive them by shuffle while the warp walks the taps, every lane gathering its own 8-channel
-// vectors (lane, lane + 32, ...) -- the per-(pixel, tap) arithmetic is done once instead of once per 8 channels.
-__global__ void __launch_bounds__(256)
-dcn_gather_f16_warp_kernel(const __half* __restrict__ x, const float* __restrict__ om,
-                           __half* __restrict__ cols, int B, int H, int W, int C, int Ho, int Wo,
-                           int stride, int pad, int dil, int mask_logits) {
-  const int CV = C / 8;
-  const int lane = threadIdx.x & 31;
-  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t M = (int64_t)B * Ho * Wo;
-  for (int64_t m = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
-    const int wo = (int)(m % Wo);
-    const int64_t t2 = m / Wo;
-    const int ho = (int)(t2 % Ho);
-    const int b = (int)(t2 / Ho);
-    const float* pom = om + m * 27;
-    TapGeom g;
-    g.o00 = g.o01 = g.o10 = g.o11 = -1;
-    g.w00 = g.w01 = g.w10 = g.w11 = 0.f;
-    if (lane < 9) {
-      g = tap_geometry(pom, lane, ho, wo, H, W, stride, pad, dil);
-      const float msk = tap_mask(pom, lane, mask_logits);
-      // NOTE: the per-thread kernel multiplies the interpolated value by the mask; folding the mask into the four
-      // weights changes the rounding (fp32, then fp16 on store): same tolerance class, not bit-identical
-      g.w00 *= msk;
-      g.w01 *= msk;
-      g.w10 *= msk;
-      g.w11 *= msk;
-    }
-    const __half* xb = x + (size_t)b * H * W * C;
-    __half* cb = cols + (size_t)m * 9 * C;
-#pragma unroll 1
-    for (int tap = 0; tap < 9; ++tap) {
-      const int o00 = __shfl_sync(0xffffffffu, g.o00, tap), o01 = __shfl_sync(0xffffffffu, g.o01, tap);
-      const int o10 = __shfl_sync(0xffffffffu, g.o10, tap), o11 = __shfl_sync(0xffffffffu, g.o11, tap);
-      const float w00 = __shfl_sync(0xffffffffu, g.w00, tap), w01 = __shfl_sync(0xffffffffu, g.w01, tap);
-      const float w10 = __shfl_sync(0xffffffffu, g.w10, tap), w11 = __shfl_sync(0xffffffffu, g.w11, tap);
-      for (int cv = lane; cv < CV; cv += 32) {
-        float acc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        auto corner = [&](int o, float wgt) {
-          if (o < 0) return;
-          const uint4 raw = *reinterpret_cast<const uint4*>(xb + (size_t)o * C + cv * 8);
-          const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(h2[j]);
-            acc[2 * j] = fmaf(wgt, f.x, acc[2 * j]);
-            acc[2 * j + 1] = fmaf(wgt, f.y, acc[2 * j + 1]);
-          }
-        };
-        corner(o00, w00);
-        corner(o01, w01);
-        corner(o10, w10);
-        corner(o11, w11);
-        uint4 outv;
-        __half2* o2 = reinterpret_cast<__half2*>(&outv);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o2[j] = __halves2half2(from_f32<__half>(acc[2 * j]), from_f32<__half>(acc[2 * j + 1]));
-        *reinterpret_cast<uint4*>(cb + (size_t)tap * C + cv * 8) = outv;
-      }
-    }
-  }
-}
-
 }  // namespace
 
 template <typename T>
@@ -325,15 +261,6 @@ void launch_dcn_gather_f16(const __half* x, const float* om, __half* cols, int B
                            int C, int Ho, int Wo, int stride, int pad, int dil, int mask_logits,
                            cudaStream_t stream, LaunchCounter* lc, int split) {
   YB_REQUIRE(C % 8 == 0, "dcn gather: C must be a multiple of 8");
-  static const bool warp_variant = getenv("YB_DCN_GATHER") && std::string(getenv("YB_DCN_GATHER")) == "warp";
-  if (warp_variant && !split) {   // experimental, see dcn_gather_f16_warp_kernel
-    int64_t g = ((int64_t)B * Ho * Wo + 7) / 8;   // 8 warps (pixels) per CTA
-    if (g > 148 * 32) g = 148 * 32;
-    dcn_gather_f16_warp_kernel<<<(unsigned)g, 256, 0, stream>>>(x, om, cols, B, H, W, C, Ho, Wo, stride, pad, dil, mask_logits);
-    YB_CHECK_LAUNCH();
-    if (lc) lc->n++;
-    return;
-  }
   const int64_t total = (int64_t)B * Ho * Wo * 9 * (C / 8);
   int64_t g = (total + 255) / 256;
   if (g > 148 * 32) g = 148 * 32;

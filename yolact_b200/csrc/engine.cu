@@ -277,7 +277,7 @@ struct NetBuilder {
                                            stride, pad, w.Cout, act, split ? 1 : 0, w.out_scale, out.C);
       stem_tc_plan_set_worker_groups(sp, h->stem_wg > 0 ? h->stem_wg : (split ? 2 : 1));
       ex->stem_plans.push_back(sp);
-      op.name += (h->stem_wg > 0 ? h->stem_wg : (split ? 2 : 1)) == 2 ? " stem wg=2" : " stem";
+      op.name += " stem wg=" + std::to_string(h->stem_wg > 0 ? h->stem_wg : (split ? 2 : 1));
       op.fn = [sp, lc](cudaStream_t s) { launch_stem_tc(sp, s, lc); };
       push(op);
       return out;

@@ -274,13 +274,17 @@ StemTcPlan* stem_tc_plan_create(const float* x_nchw, const __half* w_packed, con
 }
 
 void stem_tc_plan_destroy(StemTcPlan* plan) { delete plan; }
-void stem_tc_plan_set_worker_groups(StemTcPlan* plan, int wg) { plan->wg = (wg == 2 && plan->ks == 7) ? 2 : 1; }
+void stem_tc_plan_set_worker_groups(StemTcPlan* plan, int wg) {
+  plan->wg = ((wg == 2 || wg == 4) && plan->ks == 7) ? wg : 1;
+}
 
 void launch_stem_tc(const StemTcPlan* plan, cudaStream_t stream, LaunchCounter* lc) {
   if (plan->split) {
     // the split stem holds 144 KB of operand tiles (one CTA per SM): two worker threads per pixel double the warps
     // that hide the gather's latency (YB_STEM_WG=1 selects one)
-    if (plan->ks == 7 && plan->wg == 2)
+    if (plan->ks == 7 && plan->wg == 4)
+      launch_variant<7, 2, 3, 64, 4, true>(plan->prm, stream);   // 512 workers: 4 threads per pixel
+    else if (plan->ks == 7 && plan->wg == 2)
       launch_variant<7, 2, 3, 64, 2, true>(plan->prm, stream);
     else if (plan->ks == 7)
       launch_variant<7, 2, 3, 64, 1, true>(plan->prm, stream);
