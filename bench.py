@@ -565,7 +565,8 @@ def main():
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        traffic = (tj.get(args.precision) or {}).get("traffic_bytes_per_step") if isinstance(tj.get(args.precision), dict) else None
+        if args.config == "yolact_base_config" and B == 8 and size == cfg.max_size and isinstance(tj.get(args.precision), dict):
+            traffic = tj[args.precision].get("traffic_bytes_per_step")   # measured for this workload only
     except Exception:
         pass
     passes = 3 if args.precision == "f16x3" else 1

@@ -23,7 +23,7 @@ def main(path, title):
         d[r["Metric Name"]] = v * UNIT.get(r.get("Metric Unit", ""), 1.0)
     T, TP = "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
     DR, DW, L2, WA = "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active"
-    short = lambda n: re.sub(r"\(.*", "", n).replace("yb::<unnamed>::", "").replace("void ", "").strip()
+    short = lambda n: re.sub(r"\(.*", "", n).replace("yb::<unnamed>::", "").replace("<unnamed>::", "").replace("unnamed>::", "").replace("yb::", "").replace("void ", "").strip()
     total = sum(d.get(T, 0.0) for d in launches.values())
     agg = defaultdict(lambda: [0, 0.0, 0.0, 0.0, 0.0])
     for d in launches.values():
