@@ -1,6 +1,8 @@
 """Multi-GPU path on hardware: images sharded by batch across ranks (one process per GPU, NCCL), the only collective is
-the final all_gather of detection records -- the gathered result must EQUAL the single-GPU run on the whole batch
-(the analogue of CustomDataParallel.gather, /root/reference/eval.py:630-634).  Skipped with fewer than 2 GPUs; the
+the final all_gather of detection records -- the gathered result must equal the single-GPU run on the whole batch
+(the analogue of CustomDataParallel.gather, /root/reference/eval.py:630-634): same counts, same class ids rank for
+rank, boxes / scores / coefficients to 1e-4 (a shard of 2 images and a batch of 5 may get different tile plans from
+the autotuner -- e.g. stream-K splits the reduction differently -- so the last bits of the fp32 sums differ).  Skipped with fewer than 2 GPUs; the
 host logic alone is covered on CPU by tests/test_parallel_gloo.py."""
 import os
 import socket
@@ -78,7 +80,11 @@ def test_sharded_run_plus_nccl_gather_equals_single_gpu():
     for r, (a, b) in enumerate(spans):
         rows = slice(r * per_rank, r * per_rank + (b - a))     # rank-major rows of the gather <-> images [a, b)
         for name, g, f in zip(names, gathered, full):
-            assert torch.equal(g[rows], f[a:b]), "rank %d %s differs from the single-GPU run" % (r, name)
+            if name in ("cls", "count"):
+                assert torch.equal(g[rows], f[a:b]), "rank %d %s differs from the single-GPU run" % (r, name)
+            else:
+                d = float((g[rows] - f[a:b]).abs().max())
+                assert d < 1e-4, "rank %d %s differs from the single-GPU run by %.2e" % (r, name, d)
         pad = slice(r * per_rank + (b - a), (r + 1) * per_rank)
         assert int(gathered[4][pad].sum()) == 0                # padded rows of a short shard carry count 0
     assert int(full[4].min()) > 0
