@@ -374,7 +374,8 @@ def main():
         sampler.start()
     ms = timed(lambda i: step_device(net, i, "f32", masks_f32), args.steps, max(3, args.warmup))
     clocks = sampler.stop() if rank == 0 else None
-    launches = (net.launch_count() + output_utils.launch_count() - l0)
+    # kernels launched inside the TIMED region only (the counter also saw the warm-up steps of `timed`)
+    launches = (net.launch_count() + output_utils.launch_count() - l0) * args.steps // (args.steps + max(3, args.warmup))
     fps = world * B * args.steps / (ms / 1e3)
     hold[0] = hold[1] = None
 
@@ -442,12 +443,9 @@ def main():
                 ho["boxes"][b, :n].copy_(boxes, non_blocking=True)
                 ho["masks"][b, :n].copy_(masks, non_blocking=True)
         if world > 1:
-            d = [p["detection"] for p in preds]
-            # the shard's detections join the global batch: one NCCL all_gather of fixed-size records (eval.py:630-634)
-            pad = lambda key, shape, dt: torch.stack([torch.cat([x[key], torch.zeros((M - x[key].shape[0],) + shape, dtype=dt, device=dev)]) for x in d])
-            gather_detections(pad("box", (4,), torch.float32), pad("mask", (k,), torch.float32), pad("class", (), torch.int64),
-                              pad("score", (), torch.float32),
-                              torch.tensor([x["score"].shape[0] for x in d], dtype=torch.int32, device=dev), per_rank_batch=B)
+            # the shard's detections join the global batch: one pack kernel + ONE NCCL all_gather of fixed-size records
+            # (the analogue of CustomDataParallel.gather, eval.py:630-634)
+            gather_detections(*net.last_padded_detections, per_rank_batch=B)
         ev_d2h[kk].record(s_out)
         if i >= 1:
             ev_d2h[(i - 1) % 2].synchronize()        # step i-1's results are on the host

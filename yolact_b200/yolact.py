@@ -409,6 +409,9 @@ class Yolact(nn.Module):
         if self.training:
             return self.forward_raw(x)
         box, coef, cls, score, count, proto = self.infer_padded(x)
+        # the fixed-size tensors the per-image views below are cut from: what a multi-GPU caller hands to
+        # parallel.gather_detections (one pack kernel + one all_gather) instead of re-padding the views
+        self.last_padded_detections = (box, coef, cls, score, count)
         counts = count.cpu().tolist()  # the only host sync: Detect's output is variable-size by contract
         out = []
         for b, n in enumerate(counts):
