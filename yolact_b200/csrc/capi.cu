@@ -104,16 +104,20 @@ struct CallGuard {
   cudaStream_t stream = nullptr;
   bool chain = false;
   explicit CallGuard(yb_handle* h_) : h(h_), dg(h_->device), lk(h_->mu) {}
+  static bool capturing(cudaStream_t s) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess) {
+      cudaGetLastError();
+      return true;
+    }
+    return st != cudaStreamCaptureStatusNone;
+  }
   CallGuard(yb_handle* h_, cudaStream_t s) : h(h_), dg(h_->device), lk(h_->mu), stream(s), chain(true) {
-    if (h->ev_last && h->has_last && h->last_stream != s) cudaStreamWaitEvent(s, h->ev_last, 0);
+    // (a stream the CALLER is capturing neither waits on nor records the handle's event: ordering is the caller's graph)
+    if (h->ev_last && h->has_last && h->last_stream != s && !capturing(s)) cudaStreamWaitEvent(s, h->ev_last, 0);
   }
   ~CallGuard() {
-    if (!chain) return;
-    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
-      cudaGetLastError();
-      return;   // the caller is capturing this stream itself: ordering is the caller's graph
-    }
+    if (!chain || capturing(stream)) return;
     if (!h->ev_last && cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming) != cudaSuccess) {
       cudaGetLastError();
       h->ev_last = nullptr;
@@ -186,6 +190,7 @@ int yb_create(const yb_config* cfg, int device, yb_handle** out) {
   if (const char* pc = getenv("YB_PAIR")) h->pair_candidates = (atoi(pc) != 0);
   if (const char* ec = getenv("YB_EPI2")) h->epi2_candidates = (atoi(ec) != 0);
   if (const char* sk = getenv("YB_SK")) h->sk_candidates = (atoi(sk) != 0);
+  if (const char* as = getenv("YB_ASTAT")) h->astat_candidates = (atoi(as) != 0);
   if (const char* sw = getenv("YB_STEM_WG")) h->stem_wg = (atoi(sw) == 2 || atoi(sw) == 4) ? atoi(sw) : 1;   // default 0: per precision mode
   if (const char* st = getenv("YB_STEM_TC")) h->stem_on_tc = (atoi(st) != 0);
   if (const char* df = getenv("YB_DCN_FUSED")) h->dcn_fused = (atoi(df) != 0);

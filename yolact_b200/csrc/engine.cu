@@ -527,8 +527,8 @@ struct NetBuilder {
       ts = h->tune_stream;
       YB_CHECK_CUDA(cudaDeviceSynchronize());
     }
-    const int nsk = h->sk_candidates ? 2 : 1;   // stream-K: persistent default grid only
-    for (int ki = 0; ki < nsk; ++ki)
+    // ki: 0 plain, 1 stream-K, 2 stream-K + A-stationary (1x1 convs with a short K; plan creation falls back to 1 / 0)
+    for (int ki = 0; ki < 3; ++ki)
     for (int di = 0; di < npdl; ++di)
     for (int ei = 0; ei < nepi; ++ei)
     for (int pi = 0; pi < npair; ++pi)
@@ -539,7 +539,9 @@ struct NetBuilder {
           if (pi && bns[bi] < 64) continue;
           if (ei && (bns[bi] < 64 || gi == 1)) continue;   // 320-thread CTAs: one per SM
           if (di && (pi || ei || gi == 1)) continue;        // PDL-friendly: single CTAs, one epilogue group, <= 1 CTA/SM of its own
-          if (ki && (gi != 0 || di || h->pdl)) continue;    // stream-K: one CTA (cluster) per SM (TPC), no PDL
+          if (ki == 1 && !h->sk_candidates) continue;
+          if (ki == 2 && (!h->astat_candidates || p.KH * p.KW != 1)) continue;
+          if (ki && (gi != 0 || di)) continue;              // stream-K: one CTA (cluster) per SM (TPC), no PDL-friendly plan
           TcConvPlan* cand = nullptr;
           try {
             cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi], pi, ei ? 2 : 1, di, ki);
@@ -547,12 +549,12 @@ struct NetBuilder {
             continue;   // this tiling does not fit in shared memory (split precision doubles every stage)
           }
           if ((pi && !tc_conv_plan_pair(cand)) || (ei && tc_conv_plan_epi_groups(cand) != 2) ||
-              (di && !tc_conv_plan_pdl_friendly(cand)) || (ki && !tc_conv_plan_sk(cand))) {
+              (di && !tc_conv_plan_pdl_friendly(cand)) || (ki && tc_conv_plan_sk(cand) != ki)) {
             tc_conv_plan_destroy(cand);
             continue;
           }
           if (ki) tc_conv_plan_set_sk_workspace(cand, sk_workspace());
-          if (h->pdl) tc_conv_plan_set_pdl(cand, 1);
+          if (h->pdl && !ki) tc_conv_plan_set_pdl(cand, 1);
           const std::string ck = std::to_string(tc_conv_plan_bn(cand)) + "/" + std::to_string(tc_conv_plan_stages(cand)) +
                                  "/" + std::to_string(tc_conv_plan_grid(cand)) + "/" + std::to_string(tc_conv_plan_pair(cand)) + "/" +
                                  std::to_string(tc_conv_plan_epi_groups(cand)) + "/" + std::to_string(tc_conv_plan_pdl_friendly(cand)) +
