@@ -184,6 +184,11 @@ SPLIT_MODES = {
     "astat": {"YB_CONV2D_SK": "2"},
     "astat_bn64_grid5": {"YB_CONV2D_SK": "2", "YB_CONV2D_BN": "64", "YB_CONV2D_GRID": "5"},
     "astat_pair": {"YB_CONV2D_SK": "2", "YB_CONV2D_PAIR": "1", "YB_CONV2D_BN": "64"},
+    # one epilogue group with double-buffered output staging; persistent so that a CTA stages many chunks
+    "epi3": {"YB_CONV2D_EPI": "3"},
+    "epi3_grid3_bn128": {"YB_CONV2D_EPI": "3", "YB_CONV2D_GRID": "3", "YB_CONV2D_BN": "128"},
+    "epi3_pair": {"YB_CONV2D_EPI": "3", "YB_CONV2D_PAIR": "1"},
+    "epi2_grid3": {"YB_CONV2D_EPI": "2", "YB_CONV2D_GRID": "3"},     # two groups; residual read from global memory
 }
 
 

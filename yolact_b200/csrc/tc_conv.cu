@@ -95,6 +95,10 @@ struct alignas(64) TcParams {
   int astat;
   int ares_off;
   int res_direct;
+  // epilogue buffering per 4-warp group: output staging buffers (a buffer = one tile per plane) and residual buffers.
+  // Two groups: one each (the groups alternate).  One group: fp16 2 / 2; split 1 / 1, or 2 / 1 ("epi 3" plans: the
+  // store of chunk g no longer has to finish reading shared memory before chunk g + 1 can be staged).
+  int nbuf_out, nbuf_res;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -206,10 +210,10 @@ __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 hf = __half22float2(o2[j]);
-        // hi saturates at +-65504; the residual of a saturated value is dropped (lo = 0 keeps hi + lo finite)
-        const float l0 = fabsf(v[2 * j]) > 65504.f ? 0.f : v[2 * j] - hf.x;
-        const float l1 = fabsf(v[2 * j + 1]) > 65504.f ? 0.f : v[2 * j + 1] - hf.y;
-        l2[j] = lo2_from_f32(l0, l1);          // lo plane: residual * 2^11 (see common.cuh)
+        // hi saturates at +-65504 (pack_sat); the residual is taken against the clamped value, so a saturated
+        // element gets lo = 0 and hi + lo stays finite
+        const float c0 = fminf(fmaxf(v[2 * j], -65504.f), 65504.f), c1 = fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f);
+        l2[j] = lo2_from_f32(c0 - hf.x, c1 - hf.y);   // lo plane: residual * 2^11 (see common.cuh)
       }
       *reinterpret_cast<uint4*>(out_tile + A_STAGE_BYTES + off) = ol;
     }
@@ -526,7 +530,8 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
     const bool has_res = (p.residual != nullptr) && !p.res_direct;   // residual staged by TMA (res_direct: read from global)
     const uint32_t sw = (uint32_t)(row & 7);
     float* my_bias = sbias + hgrp * BN;
-    constexpr int NBUF = (H == 2 || SPLIT) ? 1 : 2;           // staging / residual buffers per group (a buffer = NPL tiles)
+    const int nbuf_out = (H == 2) ? 1 : p.nbuf_out;           // staging / residual buffers per group (a buffer = NPL tiles)
+    const int nbuf_res = (H == 2) ? 1 : p.nbuf_res;
     constexpr int BUF_BYTES = NPL * A_STAGE_BYTES;
     auto group_sync = [&]() {                                 // the 128 threads of this group
       if (hgrp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -566,7 +571,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           pf_advance();
           continue;
         }
-        const uint32_t buf = (NBUF == 1) ? (uint32_t)hgrp : (pf_g & 1u);
+        const uint32_t buf = (nbuf_res == 1) ? (uint32_t)hgrp : (pf_g & 1u);
         mbar_expect_tx(&res_full_bar[buf], (uint32_t)p.a_box_bytes * (uint32_t)NPL);
 #pragma unroll
         for (int pl = 0; pl < NPL; ++pl)
@@ -578,7 +583,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       }
     };
     if (p.epi_tma && has_res && issuer) {
-      for (int i = 0; i < NBUF; ++i) prefetch_res();
+      for (int i = 0; i < nbuf_res; ++i) prefetch_res();
     }
 
     uint32_t t = 0, g = 0;  // local segment counter, staged-chunk counter of this group
@@ -666,11 +671,14 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
         }
 #pragma unroll 1
         for (int c = hgrp; c < nchunks; c += H, ++g) {
-          const uint32_t buf = (NBUF == 1) ? (uint32_t)hgrp : (g & 1u);
-          uint8_t* out_tile = out_base + buf * BUF_BYTES;
+          const uint32_t obuf = (nbuf_out == 1) ? (uint32_t)hgrp : (g & 1u);
+          const uint32_t buf = (nbuf_res == 1) ? (uint32_t)hgrp : (g & 1u);   // residual buffer / barrier of this chunk
+          uint8_t* out_tile = out_base + obuf * BUF_BYTES;
           uint8_t* res_tile = res_base + buf * BUF_BYTES;
-          if (g >= (uint32_t)NBUF) {
-            if (issuer) bulk_wait_read<NBUF - 1>();  // the store that last used this staging tile has read it
+          if (g >= (uint32_t)nbuf_out) {
+            if (issuer) {   // the store that last used this staging buffer has read it
+              if (nbuf_out == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+            }
             group_sync();
           }
           uint32_t r0[32], r1[32];
@@ -706,7 +714,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
               }
             }
           }
-          if (has_res) mbar_wait(&res_full_bar[buf], (NBUF == 1) ? (g & 1u) : ((g >> 1) & 1u));
+          if (has_res) mbar_wait(&res_full_bar[buf], (nbuf_res == 1) ? (g & 1u) : ((g >> 1) & 1u));
           const int nbase = n0 + c * 64;
           const float* sb = my_bias + c * 64;
           const uint8_t* rt = has_res ? res_tile : nullptr;
@@ -892,6 +900,7 @@ struct TcConvPlan {
   int BN = 128;
   int pair = 0;
   int epi_groups = 1;   // H: 4-warp epilogue groups per CTA
+  int epi3 = 0;         // split, one group, double-buffered output staging
   int pdl_friendly = 0; // sized so that two CTAs (this kernel's and the next layer's) fit on one SM
   dim3 grid;
   size_t smem_bytes = 0;
@@ -1008,7 +1017,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
     // ring stage = weight tile only; the residual is read from global memory: [A resident][W ring][out staging]
     auto stages_for = [&](int bn, int hg) {
       const int sb = npl * (pair ? bn / 2 : bn) * BLOCK_K * 2;
-      const int tiles = split ? 2 * hg : 2;
+      const int tiles = split ? 2 * ((hg == 2 || epi_override == 3) ? 2 : 1) : 2;
       const int ob = std::max(tiles * A_STAGE_BYTES, hg == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES);
       return (221 * 1024 - ares_bytes - ob) / sb;
     };
@@ -1026,9 +1035,10 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
     // N tile) until at least two pipeline stages fit
     auto stages_for = [&](int bn, int hg) {
       const int sb = 2 * (A_STAGE_BYTES + (pair ? bn / 2 : bn) * BLOCK_K * 2);
-      const int tiles = 2 * hg;
-      const int ob = std::max(tiles * A_STAGE_BYTES, hg == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES);
-      const int rb = (q.epi_tma && p.residual) ? tiles * A_STAGE_BYTES : 0;
+      const int otiles = 2 * ((hg == 2 || epi_override == 3) ? 2 : 1), rtiles = 2 * hg;
+      const int ob = std::max(otiles * A_STAGE_BYTES, hg == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES);
+      // two groups on a flattened layout read the residual from global memory (no staging tiles), see res_direct below
+      const int rb = (q.epi_tma && p.residual && !(hg == 2 && flat)) ? rtiles * A_STAGE_BYTES : 0;
       return (221 * 1024 - ob - rb) / sb;
     };
     while (stages_for(plan->BN, epi_req) < 2) {
@@ -1062,7 +1072,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   plan->sk = sk;
   plan->astat = astat;
   q.astat = astat;
-  q.res_direct = (astat && p.residual) ? 1 : 0;
+  q.res_direct = (astat && p.residual) ? 1 : 0;   // (extended below: split plans with two epilogue groups)
   q.acc_stages = (grid < num_tiles || sk) ? 2 : 1;
   if (q.acc_stages * npl * BN > 512) q.acc_stages = 1;   // split: two accumulators per tile (2 * BN columns)
   int tmem_cols = 32;
@@ -1084,12 +1094,18 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
     q.tmem_cols = tc;
   }
   plan->epi_groups = (epi_req == 2 && !pdlf) ? 2 : 1;
-  // staging: 2 x 16 KB tiles (one per group when there are two); the direct (fp32) epilogue needs a padded
-  // 32x33 float transpose buffer per epilogue warp
-  // (split: one buffer of two tiles per group)
-  const int epi_tiles = split ? 2 * plan->epi_groups : 2;
-  const int out_bytes = std::max(epi_tiles * A_STAGE_BYTES, plan->epi_groups == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES);
-  const int res_bytes = (q.epi_tma && p.residual && !astat) ? epi_tiles * A_STAGE_BYTES : 0;
+  // staging buffers (a buffer = one 16 KB tile per plane): two groups -> one output and one residual buffer each; one
+  // group -> fp16: 2 + 2, split: 1 + 1, or 2 + 1 when epi_override == 3.  The direct (fp32) epilogue needs a padded
+  // 32x33 float transpose buffer per epilogue warp.
+  q.nbuf_out = (plan->epi_groups == 2) ? 1 : ((!split || epi_override == 3) ? 2 : 1);
+  q.nbuf_res = (plan->epi_groups == 2) ? 1 : (split ? 1 : 2);
+  plan->epi3 = (split && plan->epi_groups == 1 && q.nbuf_out == 2) ? 1 : 0;
+  const int out_tiles = npl * (plan->epi_groups == 2 ? 2 : q.nbuf_out), res_tiles = npl * (plan->epi_groups == 2 ? 2 : q.nbuf_res);
+  const int out_bytes = std::max(out_tiles * A_STAGE_BYTES, plan->epi_groups == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES);
+  // split + two epilogue groups + residual: staging (2 x 32 KB out + 2 x 32 KB residual) would leave one pipeline stage;
+  // on flattened layouts the residual is read from global memory instead
+  if (split && plan->epi_groups == 2 && p.residual && flat && q.epi_tma) q.res_direct = 1;
+  const int res_bytes = (q.epi_tma && p.residual && !q.res_direct) ? res_tiles * A_STAGE_BYTES : 0;
   int stages = std::min(MAX_STAGES, ((pdlf ? 108 : ((split || astat) ? 221 : 200)) * 1024 - out_bytes - res_bytes -
                                      (astat ? ares_bytes : 0)) / stage_bytes);
   if (stages < 1 && pdlf) {   // does not fit in half an SM: an ordinary plan
@@ -1211,7 +1227,7 @@ int tc_conv_plan_bn(const TcConvPlan* plan) { return plan->BN; }
 int tc_conv_plan_stages(const TcConvPlan* plan) { return plan->prm.stages; }
 int tc_conv_plan_grid(const TcConvPlan* plan) { return (int)plan->grid.x; }
 int tc_conv_plan_pair(const TcConvPlan* plan) { return plan->pair; }
-int tc_conv_plan_epi_groups(const TcConvPlan* plan) { return plan->epi_groups; }
+int tc_conv_plan_epi_groups(const TcConvPlan* plan) { return plan->epi3 ? 3 : plan->epi_groups; }
 int tc_conv_plan_pdl_friendly(const TcConvPlan* plan) { return plan->pdl_friendly; }
 int tc_conv_plan_sk(const TcConvPlan* plan) { return plan->sk ? (plan->astat ? 2 : 1) : 0; }
 size_t tc_conv_sk_workspace_bytes() { return (size_t)148 * BLOCK_M * 256 * sizeof(float) + 148 * 2 * sizeof(int); }
