@@ -108,8 +108,8 @@ TC_CASES = [
     (1, 64, 20, 20, 32, 1, 1, 0, 3, False),      # Darknet block conv1: fp16 output narrower than the 64-channel store box
     (2, 256, 35, 35, 1024, 1, 1, 0, 1, True),    # stage-3 conv3: 16 residual/output chunks per tile row
     (1, 256, 69, 69, 72, 3, 1, 1, 1, False),     # Cout = 72: last chunk is 8 channels wide
-    (1, 128, 69, 69, 512, 1, 1, 0, 1, True),     # stage-2 conv3 (A-stationary candidate, K = 128, 4-8 N tiles, residual)
-    (1, 512, 18, 18, 2048, 1, 1, 0, 1, True),    # stage-4 conv3 (K = 512: A-stationary in the fp16 mode only)
+    (1, 128, 69, 69, 512, 1, 1, 0, 1, True),     # stage-2 conv3: 1x1 + residual, 4-8 N tiles
+    (1, 512, 18, 18, 2048, 1, 1, 0, 1, True),    # stage-4 conv3
 ]
 
 
@@ -137,11 +137,6 @@ TC_MODES = {
     "sk_grid7_bn64": {"YB_CONV2D_SK": "1", "YB_CONV2D_GRID": "7", "YB_CONV2D_BN": "64"},
     "sk_pair": {"YB_CONV2D_SK": "1", "YB_CONV2D_PAIR": "1"},
     "sk_pair_grid6_epi2": {"YB_CONV2D_SK": "1", "YB_CONV2D_PAIR": "1", "YB_CONV2D_GRID": "6", "YB_CONV2D_EPI": "2"},
-    # A-stationary (1x1 convs with K <= 512 and >= 2 N tiles; other shapes fall back to plain stream-K / default plans)
-    "astat": {"YB_CONV2D_SK": "2"},
-    "astat_bn64_grid5": {"YB_CONV2D_SK": "2", "YB_CONV2D_BN": "64", "YB_CONV2D_GRID": "5"},
-    "astat_pair": {"YB_CONV2D_SK": "2", "YB_CONV2D_PAIR": "1", "YB_CONV2D_BN": "64"},
-    "astat_pdl": {"YB_CONV2D_SK": "2", "YB_CONV2D_BN": "64", "YB_CONV2D_PDL": "1"},
 }
 if os.environ.get("YB_TEST_NO_PAIR"):   # escape hatch while the pair kernel is being brought up
     TC_MODES = {k: v for k, v in TC_MODES.items() if not k.startswith("pair")}
@@ -181,14 +176,7 @@ SPLIT_MODES = {
     "sk_grid5": {"YB_CONV2D_SK": "1", "YB_CONV2D_GRID": "5"},
     "sk_pair": {"YB_CONV2D_SK": "1", "YB_CONV2D_PAIR": "1"},
     "sk_pair_grid6": {"YB_CONV2D_SK": "1", "YB_CONV2D_PAIR": "1", "YB_CONV2D_GRID": "6"},
-    "astat": {"YB_CONV2D_SK": "2"},
-    "astat_bn64_grid5": {"YB_CONV2D_SK": "2", "YB_CONV2D_BN": "64", "YB_CONV2D_GRID": "5"},
-    "astat_pair": {"YB_CONV2D_SK": "2", "YB_CONV2D_PAIR": "1", "YB_CONV2D_BN": "64"},
-    # one epilogue group with double-buffered output staging; persistent so that a CTA stages many chunks
-    "epi3": {"YB_CONV2D_EPI": "3"},
-    "epi3_grid3_bn128": {"YB_CONV2D_EPI": "3", "YB_CONV2D_GRID": "3", "YB_CONV2D_BN": "128"},
-    "epi3_pair": {"YB_CONV2D_EPI": "3", "YB_CONV2D_PAIR": "1"},
-    "epi2_grid3": {"YB_CONV2D_EPI": "2", "YB_CONV2D_GRID": "3"},     # two groups; residual read from global memory
+    "epi2_grid3": {"YB_CONV2D_EPI": "2", "YB_CONV2D_GRID": "3"},     # two groups; 1x1 residual read from global memory
 }
 
 

@@ -287,7 +287,7 @@ struct NetBuilder {
       TcConvPlan* plan = autotune_tc(p, w.w_tc);
       ex->plans.push_back(plan);
       op.name += " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) + " st=" + std::to_string(tc_conv_plan_stages(plan)) +
-                 " g=" + std::to_string(tc_conv_plan_grid(plan)) + (tc_conv_plan_pair(plan) ? " pair" : "") + (tc_conv_plan_epi_groups(plan) == 2 ? " epi2" : (tc_conv_plan_epi_groups(plan) == 3 ? " epi3" : "")) +
+                 " g=" + std::to_string(tc_conv_plan_grid(plan)) + (tc_conv_plan_pair(plan) ? " pair" : "") + (tc_conv_plan_epi_groups(plan) == 2 ? " epi2" : "") +
               (tc_conv_plan_pdl_friendly(plan) ? " pdlf" : "") + (tc_conv_plan_sk(plan) ? " sk" : "");
       tc_conv_plan_set_pdl(plan, h->pdl ? 1 : 0);
       op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
@@ -472,7 +472,7 @@ struct NetBuilder {
     op.name = hn + ".bbox+conf+mask " + std::to_string(in.C) + "->" + std::to_string(w.Cout) + " k3s1 " +
               std::to_string(in.H) + "x" + std::to_string(in.W) + " tc BN=" + std::to_string(tc_conv_plan_bn(plan)) +
               " st=" + std::to_string(tc_conv_plan_stages(plan)) + " g=" + std::to_string(tc_conv_plan_grid(plan)) +
-              (tc_conv_plan_pair(plan) ? " pair" : "") + (tc_conv_plan_epi_groups(plan) == 2 ? " epi2" : (tc_conv_plan_epi_groups(plan) == 3 ? " epi3" : "")) +
+              (tc_conv_plan_pair(plan) ? " pair" : "") + (tc_conv_plan_epi_groups(plan) == 2 ? " epi2" : "") +
               (tc_conv_plan_pdl_friendly(plan) ? " pdlf" : "") + (tc_conv_plan_sk(plan) ? " sk" : "");
     op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
     push(op);
@@ -516,8 +516,7 @@ struct NetBuilder {
     YB_CHECK_CUDA(cudaEventCreate(&e1));
     // extra candidates: CTA pairs (cta_group::2, persistent grid only) and two epilogue groups per CTA
     const int npair = h->pair_candidates ? 2 : 1;
-    // ei: 0 one epilogue group, 1 two groups, 2 (split mode) one group with double-buffered output staging
-    const int nepi = h->epi2_candidates ? (p.split ? 3 : 2) : 1;
+    const int nepi = h->epi2_candidates ? 2 : 1;
     // YB_PDL=1 (experimental): every single-CTA candidate is timed with programmatic dependent launch on a private
     // stream (consecutive launches of one kernel overlap like consecutive layers do), plus "PDL-friendly" plans that
     // leave room on the SM for the next layer's CTA
@@ -528,8 +527,8 @@ struct NetBuilder {
       ts = h->tune_stream;
       YB_CHECK_CUDA(cudaDeviceSynchronize());
     }
-    // ki: 0 plain, 1 stream-K, 2 stream-K + A-stationary (1x1 convs with a short K; plan creation falls back to 1 / 0)
-    for (int ki = 0; ki < 3; ++ki)
+    const int nsk = h->sk_candidates ? 2 : 1;   // stream-K: persistent default grid only
+    for (int ki = 0; ki < nsk; ++ki)
     for (int di = 0; di < npdl; ++di)
     for (int ei = 0; ei < nepi; ++ei)
     for (int pi = 0; pi < npair; ++pi)
@@ -538,24 +537,22 @@ struct NetBuilder {
         for (int gi = 0; gi < (pi ? 1 : 3); ++gi) {
           if (bns[bi] > 64 && bns[bi] >= 2 * p.Cout) continue;
           if (pi && bns[bi] < 64) continue;
-          if (ei == 1 && (bns[bi] < 64 || gi == 1)) continue;   // 320-thread CTAs: one per SM
+          if (ei && (bns[bi] < 64 || gi == 1)) continue;   // 320-thread CTAs: one per SM
           if (di && (pi || ei || gi == 1)) continue;        // PDL-friendly: single CTAs, one epilogue group, <= 1 CTA/SM of its own
-          if (ki == 1 && !h->sk_candidates) continue;
-          if (ki == 2 && (!h->astat_candidates || p.KH * p.KW != 1)) continue;
-          if (ki && (gi != 0 || di)) continue;              // stream-K: one CTA (cluster) per SM (TPC), no PDL-friendly plan
+          if (ki && (gi != 0 || di || h->pdl)) continue;    // stream-K: one CTA (cluster) per SM (TPC), no PDL
           TcConvPlan* cand = nullptr;
           try {
-            cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi], pi, ei == 1 ? 2 : (ei == 2 ? 3 : 1), di, ki);
+            cand = tc_conv_plan_create(p, w, bns[bi], sts[si], grids[gi], pi, ei ? 2 : 1, di, ki);
           } catch (const Error&) {
             continue;   // this tiling does not fit in shared memory (split precision doubles every stage)
           }
-          if ((pi && !tc_conv_plan_pair(cand)) || (ei && tc_conv_plan_epi_groups(cand) != (ei == 1 ? 2 : 3)) ||
-              (di && !tc_conv_plan_pdl_friendly(cand)) || (ki && tc_conv_plan_sk(cand) != ki)) {
+          if ((pi && !tc_conv_plan_pair(cand)) || (ei && tc_conv_plan_epi_groups(cand) != 2) ||
+              (di && !tc_conv_plan_pdl_friendly(cand)) || (ki && !tc_conv_plan_sk(cand))) {
             tc_conv_plan_destroy(cand);
             continue;
           }
           if (ki) tc_conv_plan_set_sk_workspace(cand, sk_workspace());
-          if (h->pdl && !ki) tc_conv_plan_set_pdl(cand, 1);
+          if (h->pdl) tc_conv_plan_set_pdl(cand, 1);
           const std::string ck = std::to_string(tc_conv_plan_bn(cand)) + "/" + std::to_string(tc_conv_plan_stages(cand)) +
                                  "/" + std::to_string(tc_conv_plan_grid(cand)) + "/" + std::to_string(tc_conv_plan_pair(cand)) + "/" +
                                  std::to_string(tc_conv_plan_epi_groups(cand)) + "/" + std::to_string(tc_conv_plan_pdl_friendly(cand)) +

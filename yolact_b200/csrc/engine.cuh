@@ -123,7 +123,6 @@ struct yb_handle {
   std::vector<void*> weight_allocs;
   std::map<std::string, std::array<int, 7>> tune_cache;  // layer shape -> (BN, stages, grid, pair, epilogue groups, pdl-friendly, stream-K) from the autotuner
   bool sk_candidates = true;      // the autotuner times stream-K plans: on in the split mode (YB_SK=0/1)
-  bool astat_candidates = true;   // ... and A-stationary plans for the 1x1 convs (YB_ASTAT=0/1)
   cudaStream_t tune_stream = nullptr;   // private stream of the autotuner when PDL candidates are timed
   yb::Executor* last_exec = nullptr;
   // standalone op workspaces

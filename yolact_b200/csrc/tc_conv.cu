@@ -87,18 +87,9 @@ struct alignas(64) TcParams {
   int sk;
   float* sk_ws;
   int* sk_flags;
-  // A-stationary (astat != 0; 1x1 convs with a short K and several N tiles, always together with the stream-K walk, whose
-  // unit order puts the N tiles of one M tile next to each other): the kchunks k-blocks of the M tile's A operand are
-  // loaded ONCE into a resident region (ares_off) and reused for every N tile the CTA processes for that M tile; the
-  // ring stages then hold weight tiles only.  The residual is read straight from global memory (res_direct) because its
-  // staging tiles would not fit beside the resident A.
-  int astat;
-  int ares_off;
+  // split plans with two epilogue groups on a flattened (1x1, stride 1) layout read the residual straight from global
+  // memory: its staging tiles (2 x 32 KB) would leave a single pipeline stage beside the two output staging buffers
   int res_direct;
-  // epilogue buffering per 4-warp group: output staging buffers (a buffer = one tile per plane) and residual buffers.
-  // Two groups: one each (the groups alternate).  One group: fp16 2 / 2; split 1 / 1, or 2 / 1 ("epi 3" plans: the
-  // store of chunk g no longer has to finish reading shared memory before chunk g + 1 can be staged).
-  int nbuf_out, nbuf_res;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -153,7 +144,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // One 64-channel chunk of one accumulator row: (* out_scale) +bias (smem, broadcast), +residual (swizzled smem
 // tile), activation, fp16 pack, swizzled 16-byte stores into the output staging tile.  SPLIT: the residual is
 // hi + lo from two tiles and the result is written as hi / lo = rn(v - hi) into two staging tiles.
-// res_g (A-stationary plans): this row's 64 residual channels in GLOBAL memory (hi plane; the lo plane res_lo_off halfs
+// res_g (res_direct plans): this row's 64 residual channels in GLOBAL memory (hi plane; the lo plane res_lo_off halfs
 // further) instead of a staged tile.
 template <int ACT, bool RES_AFTER, bool SPLIT>
 __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1, const float* sbias,
@@ -299,17 +290,11 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint64_t res_full_bar[2];
-  __shared__ uint64_t a_full_bar[MAX_STAGES];   // A-stationary: one per resident k-block
-  __shared__ uint64_t a_empty_bar;
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float sbias[H * BN];   // one copy per epilogue group
 
   // 1024-byte alignment required by SWIZZLE_128B (host adds 1024 bytes of slack)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  // A-stationary plans: ring stages carry weight tiles only, the A k-blocks live in their own region
-  const int stage_bytes = p.astat ? B_STAGE_BYTES : STAGE_BYTES;
-  const int b_off = p.astat ? 0 : A_BYTES;
-  uint8_t* a_res = smem + p.ares_off;
   uint8_t* out_base = smem + p.out_off;   // epilogue staging tiles: [buffer][plane] x 16 KB
   uint8_t* res_base = smem + p.res_off;   // residual tiles, same layout (only when residual && epi_tma)
 
@@ -329,8 +314,6 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int i = 0; i < MAX_STAGES; ++i) mbar_init(&a_full_bar[i], 1);
-    mbar_init(&a_empty_bar, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], (PAIR ? 2 : 1) * H);   // every epilogue group (of both CTAs of a pair) drains it
@@ -354,7 +337,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
   uint32_t pre = 0;   // producer thread only: k-blocks whose weight tile is already in flight
   if (p.pdl) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (!PAIR && !SPLIT && !p.sk && !p.astat && warp == 0 && lane == 0 && unit0 < num_units) {   // (stream-K walks start mid-unit)
+    if (!PAIR && !SPLIT && !p.sk && warp == 0 && lane == 0 && unit0 < num_units) {   // (a stream-K walk starts mid-unit)
       const TileCoord t0 = decode_unit<PAIR>(p, unit0, rank, BN);
       const int npre = min(stages, num_kb);
       for (int kb = 0; kb < npre; ++kb) {
@@ -378,59 +361,16 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       WorkIter wi;
       wi.init(p.sk, num_kb, num_units, unit0, ustep);
       int u, k0, k1;
-      int cur_m = -1;
-      uint32_t a_loads = 0;
-      const uint32_t leader_afull = PAIR ? mapa_u32(smem_u32(&a_full_bar[0]), 0) : 0u;
       while (wi.next(u, k0, k1)) {
         const TileCoord tc_ = decode_unit<PAIR>(p, u, rank, BN);
-        if (p.astat && u / p.n_tiles != cur_m) {
-          // new M tile: (re)load its A k-blocks once the MMAs that read the previous ones have completed
-          cur_m = u / p.n_tiles;
-          mbar_wait(&a_empty_bar, (a_loads & 1u) ^ 1u);
-          ++a_loads;
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            uint8_t* sa = a_res + (size_t)kc * A_BYTES;
-            const uint32_t abytes = (uint32_t)p.a_box_bytes * (uint32_t)NPL * (PAIR ? 2u : 1u);
-            if (PAIR) {
-              if (rank == 0) mbar_expect_tx(&a_full_bar[kc], abytes);
-              const uint32_t fb = leader_afull + (uint32_t)kc * (uint32_t)sizeof(uint64_t);
-#pragma unroll
-              for (int pl = 0; pl < NPL; ++pl)
-                tma_load_4d_pair(sa + pl * A_STAGE_BYTES, &p.tmA[p.tap_map[0]], fb, kc * BLOCK_K + pl * p.cin,
-                                 tc_.x0 + p.tap_dx[0], tc_.y0 + p.tap_dy[0], tc_.b);
-            } else {
-              mbar_expect_tx(&a_full_bar[kc], abytes);
-#pragma unroll
-              for (int pl = 0; pl < NPL; ++pl)
-                tma_load_4d(sa + pl * A_STAGE_BYTES, &p.tmA[p.tap_map[0]], &a_full_bar[kc], kc * BLOCK_K + pl * p.cin,
-                            tc_.x0 + p.tap_dx[0], tc_.y0 + p.tap_dy[0], tc_.b);
-            }
-          }
-        }
         for (int kb = k0; kb < k1; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)stages;
           const uint32_t it = kbg / (uint32_t)stages;
           mbar_wait(&empty_bar[s], (it & 1u) ^ 1u);
           const int tap = kb / p.kchunks;
           const int kc = kb - tap * p.kchunks;
-          uint8_t* sa = smem + (size_t)s * stage_bytes;
-          uint8_t* sb = sa + b_off;
-          if (p.astat) {   // weight tile only
-            const uint32_t wbytes = (uint32_t)B_PLANE_BYTES * (uint32_t)NPL * (PAIR ? 2u : 1u);
-            if (PAIR) {
-              if (rank == 0) mbar_expect_tx(&full_bar[s], wbytes);
-              const uint32_t fb = leader_full + s * (uint32_t)sizeof(uint64_t);
-#pragma unroll
-              for (int pl = 0; pl < NPL; ++pl)
-                tma_load_3d_pair(sb + pl * B_PLANE_BYTES, &p.tmB, fb, kc * BLOCK_K + pl * p.cin, tc_.n0 + rank * (BN / 2), tap);
-            } else {
-              mbar_expect_tx(&full_bar[s], wbytes);
-#pragma unroll
-              for (int pl = 0; pl < NPL; ++pl)
-                tma_load_3d(sb + pl * B_PLANE_BYTES, &p.tmB, &full_bar[s], kc * BLOCK_K + pl * p.cin, tc_.n0, tap);
-            }
-            continue;
-          }
+          uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
           const CUtensorMap* ma = &p.tmA[p.tap_map[tap]];
           const int ax = tc_.x0 + p.tap_dx[tap], ay = tc_.y0 + p.tap_dy[tap];
           if (PAIR) {
@@ -462,19 +402,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       WorkIter wi;
       wi.init(p.sk, num_kb, num_units, unit0, ustep);
       int u, k0, k1;
-      int cur_m = -1;
-      uint32_t a_loads = 0;
       for (; wi.next(u, k0, k1); ++t) {
-        if (p.astat && u / p.n_tiles != cur_m) {
-          // the MMAs issued so far were the last readers of the resident A: release it, then wait for the new M tile's
-          if (cur_m >= 0) {
-            if (PAIR) umma_commit_pair(&a_empty_bar); else umma_commit(&a_empty_bar);
-          }
-          cur_m = u / p.n_tiles;
-          for (int kc = 0; kc < p.kchunks; ++kc) mbar_wait(&a_full_bar[kc], a_loads & 1u);
-          ++a_loads;
-          tc_fence_after();
-        }
         const uint32_t acc = t % (uint32_t)acc_stages;
         const uint32_t use = t / (uint32_t)acc_stages;
         mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
@@ -485,9 +413,8 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           const uint32_t it = kbg / (uint32_t)stages;
           mbar_wait(&full_bar[s], it & 1u);
           tc_fence_after();
-          const uint32_t sring = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sa = p.astat ? smem_u32(a_res + (size_t)(kb % p.kchunks) * A_BYTES) : sring;
-          const uint32_t sb = sring + (uint32_t)b_off;
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
           const uint64_t da = make_sw128_desc(sa);
           const uint64_t db = make_sw128_desc(sb);
           auto mma = [&](uint64_t a, uint64_t b, uint32_t accum) {
@@ -530,8 +457,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
     const bool has_res = (p.residual != nullptr) && !p.res_direct;   // residual staged by TMA (res_direct: read from global)
     const uint32_t sw = (uint32_t)(row & 7);
     float* my_bias = sbias + hgrp * BN;
-    const int nbuf_out = (H == 2) ? 1 : p.nbuf_out;           // staging / residual buffers per group (a buffer = NPL tiles)
-    const int nbuf_res = (H == 2) ? 1 : p.nbuf_res;
+    constexpr int NBUF = (H == 2 || SPLIT) ? 1 : 2;           // staging / residual buffers per group (a buffer = NPL tiles)
     constexpr int BUF_BYTES = NPL * A_STAGE_BYTES;
     auto group_sync = [&]() {                                 // the 128 threads of this group
       if (hgrp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -571,7 +497,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
           pf_advance();
           continue;
         }
-        const uint32_t buf = (nbuf_res == 1) ? (uint32_t)hgrp : (pf_g & 1u);
+        const uint32_t buf = (NBUF == 1) ? (uint32_t)hgrp : (pf_g & 1u);
         mbar_expect_tx(&res_full_bar[buf], (uint32_t)p.a_box_bytes * (uint32_t)NPL);
 #pragma unroll
         for (int pl = 0; pl < NPL; ++pl)
@@ -583,7 +509,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
       }
     };
     if (p.epi_tma && has_res && issuer) {
-      for (int i = 0; i < nbuf_res; ++i) prefetch_res();
+      for (int i = 0; i < NBUF; ++i) prefetch_res();
     }
 
     uint32_t t = 0, g = 0;  // local segment counter, staged-chunk counter of this group
@@ -671,14 +597,11 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
         }
 #pragma unroll 1
         for (int c = hgrp; c < nchunks; c += H, ++g) {
-          const uint32_t obuf = (nbuf_out == 1) ? (uint32_t)hgrp : (g & 1u);
-          const uint32_t buf = (nbuf_res == 1) ? (uint32_t)hgrp : (g & 1u);   // residual buffer / barrier of this chunk
-          uint8_t* out_tile = out_base + obuf * BUF_BYTES;
+          const uint32_t buf = (NBUF == 1) ? (uint32_t)hgrp : (g & 1u);
+          uint8_t* out_tile = out_base + buf * BUF_BYTES;
           uint8_t* res_tile = res_base + buf * BUF_BYTES;
-          if (g >= (uint32_t)nbuf_out) {
-            if (issuer) {   // the store that last used this staging buffer has read it
-              if (nbuf_out == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
-            }
+          if (g >= (uint32_t)NBUF) {
+            if (issuer) bulk_wait_read<NBUF - 1>();  // the store that last used this staging tile has read it
             group_sync();
           }
           uint32_t r0[32], r1[32];
@@ -714,7 +637,7 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
               }
             }
           }
-          if (has_res) mbar_wait(&res_full_bar[buf], (nbuf_res == 1) ? (g & 1u) : ((g >> 1) & 1u));
+          if (has_res) mbar_wait(&res_full_bar[buf], (NBUF == 1) ? (g & 1u) : ((g >> 1) & 1u));
           const int nbase = n0 + c * 64;
           const float* sb = my_bias + c * 64;
           const uint8_t* rt = has_res ? res_tile : nullptr;
@@ -896,11 +819,9 @@ struct TcConvPlan {
   TcParams prm;
   int split = 0;
   int sk = 0;           // stream-K requested (effective once a workspace is attached: prm.sk)
-  int astat = 0;        // A-stationary (implies sk)
   int BN = 128;
   int pair = 0;
   int epi_groups = 1;   // H: 4-warp epilogue groups per CTA
-  int epi3 = 0;         // split, one group, double-buffered output staging
   int pdl_friendly = 0; // sized so that two CTAs (this kernel's and the next layer's) fit on one SM
   dim3 grid;
   size_t smem_bytes = 0;
@@ -1005,40 +926,15 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   // ---- CTA pairs: two adjacent M tiles per (cluster of 2), each CTA stages half of the weight tile
   const int pair = (pair_override > 0 && m_tiles >= 2 && plan->BN >= 64) ? 1 : 0;
   int epi_req = (epi_override == 2 && plan->BN >= 64) ? 2 : 1;
-  // A-stationary (sk_override == 2): flattened 1x1 convs whose whole K fits beside the weight ring (<= 128 KB of A
-  // k-blocks) and that have at least two N tiles to reuse it for; rides on the stream-K walk
-  const int ares_bytes = q.kchunks * npl * A_STAGE_BYTES;
-  int astat = (sk_override == 2 && flat && q.ntaps == 1 && q.epi_tma && ares_bytes <= 128 * 1024 && !(pdl_override > 0)) ? 1 : 0;
-  if (astat) {
-    while (plan->BN > bn_min && 2 * plan->BN > p.Cout) plan->BN /= 2;     // >= 2 N tiles
-    if (2 * plan->BN > p.Cout || (pair && plan->BN < 64)) astat = 0;
-  }
-  if (astat) {
-    // ring stage = weight tile only; the residual is read from global memory: [A resident][W ring][out staging]
-    auto stages_for = [&](int bn, int hg) {
-      const int sb = npl * (pair ? bn / 2 : bn) * BLOCK_K * 2;
-      const int tiles = split ? 2 * ((hg == 2 || epi_override == 3) ? 2 : 1) : 2;
-      const int ob = std::max(tiles * A_STAGE_BYTES, hg == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES);
-      return (221 * 1024 - ares_bytes - ob) / sb;
-    };
-    while (stages_for(plan->BN, epi_req) < 2) {
-      if (epi_req == 2) epi_req = 1;
-      else if (plan->BN > std::max(bn_min, pair ? 64 : 32)) plan->BN /= 2;
-      else {
-        astat = 0;
-        break;
-      }
-    }
-  }
-  if (split && !astat) {
+  if (split) {
     // every stage and every epilogue buffer is twice as large: step down (second epilogue group first, then the
     // N tile) until at least two pipeline stages fit
     auto stages_for = [&](int bn, int hg) {
       const int sb = 2 * (A_STAGE_BYTES + (pair ? bn / 2 : bn) * BLOCK_K * 2);
-      const int otiles = 2 * ((hg == 2 || epi_override == 3) ? 2 : 1), rtiles = 2 * hg;
-      const int ob = std::max(otiles * A_STAGE_BYTES, hg == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES);
-      // two groups on a flattened layout read the residual from global memory (no staging tiles), see res_direct below
-      const int rb = (q.epi_tma && p.residual && !(hg == 2 && flat)) ? rtiles * A_STAGE_BYTES : 0;
+      const int tiles = 2 * hg;
+      const int ob = std::max(tiles * A_STAGE_BYTES, hg == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES);
+      // two groups on a flattened layout read the residual from global memory (no staging tiles), see res_direct
+      const int rb = (q.epi_tma && p.residual && !(hg == 2 && flat)) ? tiles * A_STAGE_BYTES : 0;
       return (221 * 1024 - ob - rb) / sb;
     };
     while (stages_for(plan->BN, epi_req) < 2) {
@@ -1051,8 +947,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   plan->pair = pair;
   q.pair = pair;
   q.nb = Bv;
-  const int stage_bytes = astat ? npl * (pair ? BN / 2 : BN) * BLOCK_K * 2
-                                : npl * (A_STAGE_BYTES + (pair ? BN / 2 : BN) * BLOCK_K * 2);
+  const int stage_bytes = npl * (A_STAGE_BYTES + (pair ? BN / 2 : BN) * BLOCK_K * 2);
   // ---- persistent grid + shared-memory layout: [pipeline stages][2 x 16 KB out tiles][2 x 16 KB residual tiles]
   q.m_tiles = (int)m_tiles;
   q.n_tiles = ceil_div(p.Cout, BN);
@@ -1065,14 +960,10 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   int sk = (sk_override > 0 && q.epi_tma && !(pdl_override > 0)) ? 1 : 0;
   if (sk) {
     const int gsk = std::min<long long>(grid_override > 0 ? grid : (pair ? 74 : 148), total_it);
-    if (gsk <= 1 || (num_tiles % gsk == 0 && !astat)) sk = 0;   // whole waves already: nothing to balance
+    if (gsk <= 1 || num_tiles % gsk == 0) sk = 0;   // whole waves already: nothing to balance
     else grid = gsk;
   }
-  if (!sk) astat = 0;
   plan->sk = sk;
-  plan->astat = astat;
-  q.astat = astat;
-  q.res_direct = (astat && p.residual) ? 1 : 0;   // (extended below: split plans with two epilogue groups)
   q.acc_stages = (grid < num_tiles || sk) ? 2 : 1;
   if (q.acc_stages * npl * BN > 512) q.acc_stages = 1;   // split: two accumulators per tile (2 * BN columns)
   int tmem_cols = 32;
@@ -1094,20 +985,14 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
     q.tmem_cols = tc;
   }
   plan->epi_groups = (epi_req == 2 && !pdlf) ? 2 : 1;
-  // staging buffers (a buffer = one 16 KB tile per plane): two groups -> one output and one residual buffer each; one
-  // group -> fp16: 2 + 2, split: 1 + 1, or 2 + 1 when epi_override == 3.  The direct (fp32) epilogue needs a padded
-  // 32x33 float transpose buffer per epilogue warp.
-  q.nbuf_out = (plan->epi_groups == 2) ? 1 : ((!split || epi_override == 3) ? 2 : 1);
-  q.nbuf_res = (plan->epi_groups == 2) ? 1 : (split ? 1 : 2);
-  plan->epi3 = (split && plan->epi_groups == 1 && q.nbuf_out == 2) ? 1 : 0;
-  const int out_tiles = npl * (plan->epi_groups == 2 ? 2 : q.nbuf_out), res_tiles = npl * (plan->epi_groups == 2 ? 2 : q.nbuf_res);
-  const int out_bytes = std::max(out_tiles * A_STAGE_BYTES, plan->epi_groups == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES);
-  // split + two epilogue groups + residual: staging (2 x 32 KB out + 2 x 32 KB residual) would leave one pipeline stage;
-  // on flattened layouts the residual is read from global memory instead
-  if (split && plan->epi_groups == 2 && p.residual && flat && q.epi_tma) q.res_direct = 1;
-  const int res_bytes = (q.epi_tma && p.residual && !q.res_direct) ? res_tiles * A_STAGE_BYTES : 0;
-  int stages = std::min(MAX_STAGES, ((pdlf ? 108 : ((split || astat) ? 221 : 200)) * 1024 - out_bytes - res_bytes -
-                                     (astat ? ares_bytes : 0)) / stage_bytes);
+  // staging: 2 x 16 KB tiles (one per group when there are two); the direct (fp32) epilogue needs a padded
+  // 32x33 float transpose buffer per epilogue warp
+  // (split: one buffer of two tiles per group)
+  const int epi_tiles = split ? 2 * plan->epi_groups : 2;
+  const int out_bytes = std::max(epi_tiles * A_STAGE_BYTES, plan->epi_groups == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES);
+  q.res_direct = (split && plan->epi_groups == 2 && p.residual && flat && q.epi_tma) ? 1 : 0;
+  const int res_bytes = (q.epi_tma && p.residual && !q.res_direct) ? epi_tiles * A_STAGE_BYTES : 0;
+  int stages = std::min(MAX_STAGES, ((pdlf ? 108 : (split ? 221 : 200)) * 1024 - out_bytes - res_bytes) / stage_bytes);
   if (stages < 1 && pdlf) {   // does not fit in half an SM: an ordinary plan
     plan->pdl_friendly = 0;
     stages = std::min(MAX_STAGES, (200 * 1024 - out_bytes - res_bytes) / stage_bytes);
@@ -1116,8 +1001,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   if (stages_override > 0) stages = std::min(stages, stages_override);
   stages = std::max(1, std::min(stages, q.ntaps * q.kchunks * tiles_per_cta));
   q.stages = stages;
-  q.ares_off = stages * stage_bytes;                       // A-stationary: resident A k-blocks behind the weight ring
-  q.out_off = stages * stage_bytes + (astat ? ares_bytes : 0);
+  q.out_off = stages * stage_bytes;
   q.res_off = q.out_off + out_bytes;
   plan->smem_bytes = (size_t)q.res_off + res_bytes + 1024;
   if (plan->pdl_friendly && plan->smem_bytes > (size_t)112 * 1024) plan->pdl_friendly = 0;   // does not fit twice: plain plan
@@ -1227,14 +1111,13 @@ int tc_conv_plan_bn(const TcConvPlan* plan) { return plan->BN; }
 int tc_conv_plan_stages(const TcConvPlan* plan) { return plan->prm.stages; }
 int tc_conv_plan_grid(const TcConvPlan* plan) { return (int)plan->grid.x; }
 int tc_conv_plan_pair(const TcConvPlan* plan) { return plan->pair; }
-int tc_conv_plan_epi_groups(const TcConvPlan* plan) { return plan->epi3 ? 3 : plan->epi_groups; }
+int tc_conv_plan_epi_groups(const TcConvPlan* plan) { return plan->epi_groups; }
 int tc_conv_plan_pdl_friendly(const TcConvPlan* plan) { return plan->pdl_friendly; }
-int tc_conv_plan_sk(const TcConvPlan* plan) { return plan->sk ? (plan->astat ? 2 : 1) : 0; }
+int tc_conv_plan_sk(const TcConvPlan* plan) { return plan->sk; }
 size_t tc_conv_sk_workspace_bytes() { return (size_t)148 * BLOCK_M * 256 * sizeof(float) + 148 * 2 * sizeof(int); }
 // ws: tc_conv_sk_workspace_bytes() of device memory whose LAST 148 * 2 ints (the flags) are zero; kernels that share a
 // workspace must be stream-ordered (each launch leaves the flags zero again)
 void tc_conv_plan_set_sk_workspace(TcConvPlan* plan, void* ws) {
-  YB_REQUIRE(!plan->astat || ws, "tc_conv: an A-stationary plan needs the stream-K workspace");
   plan->prm.sk = (plan->sk && ws) ? 1 : 0;
   plan->prm.sk_ws = reinterpret_cast<float*>(ws);
   plan->prm.sk_flags = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + (size_t)148 * BLOCK_M * 256 * sizeof(float));
