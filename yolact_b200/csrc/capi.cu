@@ -190,6 +190,7 @@ int yb_create(const yb_config* cfg, int device, yb_handle** out) {
   if (const char* pc = getenv("YB_PAIR")) h->pair_candidates = (atoi(pc) != 0);
   if (const char* ec = getenv("YB_EPI2")) h->epi2_candidates = (atoi(ec) != 0);
   if (const char* sk = getenv("YB_SK")) h->sk_candidates = (atoi(sk) != 0);
+  if (const char* ch = getenv("YB_CHAIN")) h->chain_mode = std::min(2, std::max(0, atoi(ch)));
   if (const char* sw = getenv("YB_STEM_WG")) h->stem_wg = (atoi(sw) == 2 || atoi(sw) == 4) ? atoi(sw) : 1;   // default 0: per precision mode
   if (const char* st = getenv("YB_STEM_TC")) h->stem_on_tc = (atoi(st) != 0);
   if (const char* df = getenv("YB_DCN_FUSED")) h->dcn_fused = (atoi(df) != 0);

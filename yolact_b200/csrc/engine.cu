@@ -45,6 +45,7 @@ Executor::~Executor() {
   if (graph_fwd) cudaGraphExecDestroy(graph_fwd);
   for (auto& kv : infer_graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  for (auto* c : chains) tc_chain_destroy(c);
   for (auto* p : plans) tc_conv_plan_destroy(p);
   for (auto* p : stem_plans) stem_tc_plan_destroy(p);
   for (auto* p : dcn_plans) dcn_tc_plan_destroy(p);
@@ -291,6 +292,9 @@ struct NetBuilder {
               (tc_conv_plan_pdl_friendly(plan) ? " pdlf" : "") + (tc_conv_plan_sk(plan) ? " sk" : "");
       tc_conv_plan_set_pdl(plan, h->pdl ? 1 : 0);
       op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
+      op.has_prob = true;
+      op.prob = p;
+      op.w_tc = w.w_tc;
     } else {
       int types;
       if (!f16 || in.f32) {
@@ -476,6 +480,117 @@ struct NetBuilder {
               (tc_conv_plan_pdl_friendly(plan) ? " pdlf" : "") + (tc_conv_plan_sk(plan) ? " sk" : "");
     op.fn = [plan, lc](cudaStream_t s) { launch_tc_conv(plan, s, lc); };
     push(op);
+  }
+
+  // Runs of consecutive tensor-core convolutions in ops [begin, end) -- each reading the previous one's output, all at
+  // one resolution: the 1x1 -> 3x3 -> 1x1 bottlenecks of a ResNet stage after its first block (backbone.py:37-57), the
+  // protonet's 3x3 stack -- are re-planned for the chain kernel (tc_conv.cu) and replaced by ONE launch when that is
+  // faster than the separately tuned launches (both are timed here).  Returns the new end of the range.
+  size_t form_chains(size_t begin, size_t end) {
+    if (dry || h->chain_mode == 0) return end;
+    auto& ops = ex->ops;
+    auto candidate = [&](const Op& op) {
+      if (!op.has_prob) return false;
+      const ConvProblem& q = op.prob;
+      return q.split && q.stride == 1 && ((q.KH == 1 && q.pad == 0) || (q.KH == 3 && q.pad == 1)) && q.KH == q.KW &&
+             q.Cout % 128 == 0 && !q.y_f32 && q.nseg == 0 && q.y_pix_stride == 2 * q.Cout &&
+             q.y_batch_stride == (int64_t)q.Ho * q.Wo * q.y_pix_stride;
+    };
+    size_t i = begin;
+    while (i < end) {
+      if (!candidate(ops[i])) {
+        ++i;
+        continue;
+      }
+      size_t k = i + 1;
+      while (k < end && candidate(ops[k]) && ops[k].lane == ops[i].lane && ops[k].prob.x == ops[k - 1].prob.y &&
+             ops[k].prob.B == ops[i].prob.B && ops[k].prob.Ho == ops[i].prob.Ho && ops[k].prob.Wo == ops[i].prob.Wo)
+        ++k;
+      const size_t n = k - i;
+      if (n < 3) {
+        i = k;
+        continue;
+      }
+      // the chain's own plans: one tile shape for every layer
+      std::vector<TcConvPlan*> cp;
+      bool ok = true;
+      for (size_t j = i; j < k && ok; ++j) {
+        TcConvPlan* pl = nullptr;
+        try {
+          pl = tc_conv_plan_create(ops[j].prob, ops[j].w_tc, 128, 2, 148, 0, 2, 0, 0);
+        } catch (const Error&) {
+          ok = false;
+          break;
+        }
+        cp.push_back(pl);
+        if (!tc_conv_plan_chainable(pl)) ok = false;
+      }
+      TcChain* chain = nullptr;
+      if (ok) {
+        std::vector<const TcConvPlan*> cpl(cp.begin(), cp.end());
+        std::vector<int> dep(n, 1);
+        dep[0] = 0;
+        try {
+          chain = tc_chain_create(cpl, dep);
+        } catch (const Error&) {
+          chain = nullptr;
+        }
+      }
+      bool use = false;
+      if (chain && !tc_chain_graph_ok(chain)) {   // cooperative launches cannot be captured here: no chains
+        tc_chain_destroy(chain);
+        chain = nullptr;
+      }
+      if (chain) {
+        float ms_chain = 0.f, ms_sep = 0.f;
+        const auto lc_before = h->lc.n;
+        cudaEvent_t e0, e1;
+        YB_CHECK_CUDA(cudaEventCreate(&e0));
+        YB_CHECK_CUDA(cudaEventCreate(&e1));
+        auto time_it = [&](const std::function<void()>& f) {
+          float ms = 0.f;
+          for (int r = 0; r < 2; ++r) f();
+          YB_CHECK_CUDA(cudaEventRecord(e0, 0));
+          for (int r = 0; r < 5; ++r) f();
+          YB_CHECK_CUDA(cudaEventRecord(e1, 0));
+          YB_CHECK_CUDA(cudaEventSynchronize(e1));
+          YB_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+          return ms / 5.f;
+        };
+        ms_chain = time_it([&]() { launch_tc_chain(chain, 0, nullptr); });
+        ms_sep = time_it([&]() {
+          for (size_t j = i; j < k; ++j) ops[j].fn(0);
+        });
+        h->lc.n = lc_before;   // (the separate launches counted themselves)
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        use = (h->chain_mode == 2) || ms_chain < ms_sep;
+        if (getenv("YB_CHAIN_VERBOSE"))
+          fprintf(stderr, "[yolact_b200] chain %s .. (%zu layers): chain %.3f ms, separate %.3f ms -> %s\n", ops[i].name.c_str(),
+                  n, ms_chain, ms_sep, use ? "chain" : "separate");
+      }
+      if (!use) {
+        if (chain) tc_chain_destroy(chain);
+        for (auto* pl : cp) tc_conv_plan_destroy(pl);
+        i = k;
+        continue;
+      }
+      ex->chains.push_back(chain);
+      for (auto* pl : cp) ex->plans.push_back(pl);
+      Op op;
+      op.is_conv = true;
+      op.lane = ops[i].lane;
+      op.name = "chain x" + std::to_string(n) + " [" + ops[i].name.substr(0, ops[i].name.find(' ')) + " .. " +
+                ops[k - 1].name.substr(0, ops[k - 1].name.find(' ')) + "] " + std::to_string(ops[i].prob.Ho) + "x" +
+                std::to_string(ops[i].prob.Wo) + " tc BN=128 st=2 g=148 epi2";
+      LaunchCounter* lc = &h->lc;
+      op.fn = [chain, lc](cudaStream_t s) { launch_tc_chain(chain, s, lc); };
+      ops[i] = op;
+      ops.erase(ops.begin() + (i + 1), ops.begin() + k);
+      end -= (n - 1);
+      i = i + 1;
+    }
+    return end;
   }
 
   // stream-K workspace of the current lane (allocated on first use; the flags at its end start out zero)
@@ -690,6 +805,7 @@ void build_network(yb_handle* h, Executor* ex, bool dry) {
   Pl[3] = nb.conv("fpn.downsample_layers.0", "", Pl[2], 3, 2, 1, ACT_NONE);
   Pl[4] = nb.conv("fpn.downsample_layers.1", "", Pl[3], 3, 2, 1, ACT_NONE);
   for (int l = 0; l < 5; ++l) ex->feats[4 + l] = Pl[l];
+  nb.form_chains(0, ex->ops.size());
   ex->fork_index = ex->ops.size();   // protonet (lane 0) and the 5 head levels (lanes 1..5) are independent
 
   // ---------------- protonet on P3 (config.py:691, utils/functions.py:163-213, yolact.py:588-599) ----
@@ -703,6 +819,7 @@ void build_network(yb_handle* h, Executor* ex, bool dry) {
     p = nb.conv("proto_net.10", "", p, 1, 1, 0, ACT_RELU, nullptr, /*out_f32=*/true);
     ex->proto = (float*)p.ptr;
     YB_REQUIRE(p.H == ex->ph && p.W == ex->pw && p.C == MD, "proto shape mismatch");
+    nb.form_chains(ex->fork_index, ex->ops.size());   // proto_net.0 / .2 / .4: three 3x3 layers at one resolution
   }
 
   // ---------------- shared prediction head over the 5 levels (yolact.py:133-212, 616-634) -----------

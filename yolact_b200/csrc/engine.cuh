@@ -56,6 +56,10 @@ struct Op {
   std::string name;   // layer key, for yb_last_forward_profile
   int lane = 0;       // graph branch: 0 = trunk (+ protonet); 1..5 = prediction head of FPN level lane-1
   float last_ms = 0.f;
+  // tensor-core convolutions keep their problem so that runs of them can be re-planned as one chain launch
+  bool has_prob = false;
+  ConvProblem prob;
+  const __half* w_tc = nullptr;
 };
 
 struct Executor {
@@ -64,6 +68,7 @@ struct Executor {
   std::vector<TcConvPlan*> plans;
   std::vector<StemTcPlan*> stem_plans;
   std::vector<DcnTcPlan*> dcn_plans;
+  std::vector<TcChain*> chains;
   void* sk_ws[8] = {};           // stream-K workspace per graph lane (plans of one lane are stream-ordered)
   std::vector<Op> ops;           // the conv stack (yb_forward)
   size_t fork_index = 0;         // ops[fork_index..] may run on their lanes concurrently (0 = no fork)
@@ -123,6 +128,7 @@ struct yb_handle {
   std::vector<void*> weight_allocs;
   std::map<std::string, std::array<int, 7>> tune_cache;  // layer shape -> (BN, stages, grid, pair, epilogue groups, pdl-friendly, stream-K) from the autotuner
   bool sk_candidates = true;      // the autotuner times stream-K plans: on in the split mode (YB_SK=0/1)
+  int chain_mode = 1;             // runs of consecutive convs as one chain launch: 0 never, 1 when timed faster, 2 always (YB_CHAIN)
   cudaStream_t tune_stream = nullptr;   // private stream of the autotuner when PDL candidates are timed
   yb::Executor* last_exec = nullptr;
   // standalone op workspaces

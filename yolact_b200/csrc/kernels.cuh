@@ -1,6 +1,7 @@
 // Launcher declarations for every kernel of the path.  One launcher == one kernel launch
 // (each bumps LaunchCounter).  All launchers are asynchronous on `stream`.
 #pragma once
+#include <vector>
 #include "common.cuh"
 
 namespace yb {
@@ -72,6 +73,15 @@ int tc_conv_plan_stages(const TcConvPlan* plan);
 void tc_conv_plan_destroy(TcConvPlan* plan);
 bool tc_conv_supported(const ConvProblem& p);
 void launch_tc_conv(const TcConvPlan* plan, cudaStream_t stream, LaunchCounter* lc);
+// A run of consecutive layers (each reading the previous one's output) in ONE persistent launch with per-tile
+// dependency counters instead of kernel boundaries (tc_conv.cu, "chain kernel"); the plans must outlive the chain
+struct TcChain;
+bool tc_conv_plan_chainable(const TcConvPlan* plan);
+TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std::vector<int>& dep);
+void tc_chain_destroy(TcChain* chain);
+int tc_chain_layers(const TcChain* chain);
+bool tc_chain_graph_ok(const TcChain* chain);
+void launch_tc_chain(const TcChain* chain, cudaStream_t stream, LaunchCounter* lc);
 
 // ---- stem on tcgen05 (3-channel NCHW fp32 frame -> NHWC fp16) ---------------------------------------
 struct StemTcPlan;

@@ -166,7 +166,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1
     const uint32_t off = row * 128u + (((uint32_t)j8 ^ sw) << 4);
     if (res_tile || res_g) {
       const uint4 raw = res_tile ? *reinterpret_cast<const uint4*>(res_tile + off)
-                                 : __ldg(reinterpret_cast<const uint4*>(res_g + j8 * 8));
+                                 : __ldcg(reinterpret_cast<const uint4*>(res_g + j8 * 8));   // L2: inside a chain other SMs wrote it during this launch
       const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -176,7 +176,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1
       }
       if (SPLIT) {
         const uint4 rawl = res_tile ? *reinterpret_cast<const uint4*>(res_tile + A_STAGE_BYTES + off)
-                                    : __ldg(reinterpret_cast<const uint4*>(res_g + res_lo_off + j8 * 8));
+                                    : __ldcg(reinterpret_cast<const uint4*>(res_g + res_lo_off + j8 * 8));
         const __half2* l2 = reinterpret_cast<const __half2*>(&rawl);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -764,6 +764,351 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// chain kernel: a run of consecutive convolutions (the 1x1 -> 3x3 -> 1x1 (+residual) bottleneck blocks of one ResNet
+// stage, backbone.py:37-57) in ONE persistent launch
+// ---------------------------------------------------------------------------------------------
+// Every layer of the chain is an ordinary plan of the shape <BN = 128, single CTA, two epilogue groups, staged TMA
+// epilogue, residual read from global memory>; their parameter blocks (tensor maps included) sit in an array in global
+// memory.  The work units of all layers form ONE list (layer-major, then M tile, then N tile) that is dealt round-robin
+// to the 148 CTAs, so a CTA moves from its last tile of layer L straight to its first tile of layer L + 1: no launch,
+// no prologue (barriers, TMEM allocation, descriptor fetch), no tail where most SMs idle -- the three pipelines of a
+// CTA (TMA ring, TMEM accumulators, staging tiles) simply keep running across the layer boundary.
+// Dependencies are tracked per M tile instead of by a grid-wide barrier: the epilogue groups bump done[layer][m tile]
+// once their stores of a tile have completed; before the first ACTIVATION load of a tile the producer warp waits until
+// every tile of the previous layer that overlaps the tile's rows +-1 (the 3x3 halo) has been finished by all its
+// N tiles (the weight tiles of the first k-blocks are requested before the wait).  All dependencies point backwards in
+// the unit list and every CTA walks its units in list order, so the earliest unfinished unit can always run: no
+// deadlock as long as the CTAs are co-resident (grid <= SM count, one CTA per SM).
+struct ChainLayer {
+  int ubase;               // position of this layer's unit 0 in the chain's unit list
+  int units;               // m_tiles * n_tiles
+  int flat;                // 1: tile m = pixels [m * tw, m * tw + tw) of the flattened B*H*W axis; 0: tiles_x x tiles_y tiles per image
+  int W, H, rows;          // image size; rows = B * H  (global row r = b * H + y, pixel = r * W + x)
+  int tw, th, tiles_x, tiles_y;
+  int done_off;            // this layer's counters: done[done_off + m_tile]
+  int target;              // a finished M tile: n_tiles * 2 (each epilogue group of each N tile adds 1)
+  int dep;                 // 1: the input comes from the previous layer of the chain
+  int pad_;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__host__ __device__ constexpr int chain_stages(bool split) { return split ? 2 : 4; }
+__device__ __forceinline__ bool mbar_test_wait(uint32_t addr, uint32_t parity) {   // non-blocking
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// first unit of a layer that belongs to CTA `cta` when the chain's unit list is dealt round-robin over G CTAs
+__device__ __forceinline__ int chain_first_unit(int cta, int ubase, int G) {
+  int r = (cta - ubase) % G;
+  return r < 0 ? r + G : r;
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(320)
+tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restrict__ info, int nl, int* __restrict__ done) {
+  constexpr int BN = 128;
+  constexpr int H = 2;
+  constexpr int NPL = SPLIT ? 2 : 1;
+  constexpr int B_PLANE_BYTES = BN * BLOCK_K * 2;
+  constexpr int A_BYTES = NPL * A_STAGE_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + NPL * B_PLANE_BYTES;
+  constexpr int BUF_BYTES = NPL * A_STAGE_BYTES;
+  // the chain's own shared-memory layout (the plans' stage counts / offsets are not used): ring, then one staging
+  // buffer per epilogue group; two TMEM accumulator buffers
+  constexpr int stages = chain_stages(SPLIT);
+
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ uint64_t full_bar[MAX_STAGES];
+  __shared__ uint64_t empty_bar[MAX_STAGES];
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ __align__(16) float sbias[H * BN];
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* out_base = smem + stages * STAGE_BYTES;
+  const int G = (int)gridDim.x;
+  const int cta = (int)blockIdx.x;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], H);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&layers[0].tmB);
+    tma_prefetch_desc(&layers[0].tmA[0]);
+    tma_prefetch_desc(&layers[0].tmY);
+  }
+  if (warp == 1) tmem_alloc_dyn(&s_tmem_base, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer (lane 0 issues; the whole warp polls the dependency counters) =====================
+    const uint32_t tx_bytes_b = (uint32_t)B_PLANE_BYTES * (uint32_t)NPL;
+    uint32_t kbg = 0;
+    for (int L = 0; L < nl; ++L) {
+      const TcParams& p = layers[L];
+      const ChainLayer ci = info[L];
+      const int num_kb = p.ntaps * p.kchunks;
+      const uint32_t tx_bytes = (uint32_t)p.a_box_bytes * (uint32_t)NPL + tx_bytes_b;
+      if (lane == 0 && L + 1 < nl) {   // the next layer's descriptors: fetched long before their first use
+        tma_prefetch_desc(&layers[L + 1].tmB);
+        tma_prefetch_desc(&layers[L + 1].tmA[0]);
+      }
+      for (int u = chain_first_unit(cta, ci.ubase, G); u < ci.units; u += G) {
+        const TileCoord tc_ = decode_unit<false>(p, u, 0, BN);
+        bool ready = (ci.dep == 0);
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const uint32_t s = kbg % (uint32_t)stages;
+          const uint32_t it = kbg / (uint32_t)stages;
+          const int tap = kb / p.kchunks;
+          const int kc = kb - tap * p.kchunks;
+          uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          if (lane == 0) {
+            mbar_wait(&empty_bar[s], (it & 1u) ^ 1u);
+            mbar_expect_tx(&full_bar[s], tx_bytes);
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl)   // weights: constants, no dependency
+              tma_load_3d(sb + pl * B_PLANE_BYTES, &p.tmB, &full_bar[s], kc * BLOCK_K + pl * p.cin, tc_.n0, tap);
+          }
+          if (!ready) {
+            // rows of this tile, +-1 for the 3x3 halo (kept for the 1x1 layers too: it also orders a writer behind every
+            // reader of a recycled buffer, should the engine ever recycle activations)
+            int r0, r1;
+            if (ci.flat) {
+              const int lo = tc_.x0, hi = min(tc_.x0 + ci.tw, ci.rows * ci.W) - 1;
+              r0 = lo / ci.W;
+              r1 = hi / ci.W;
+            } else {
+              r0 = tc_.b * ci.H + tc_.y0;
+              r1 = tc_.b * ci.H + min(tc_.y0 + ci.th, ci.H) - 1;
+            }
+            r0 = max(r0 - 1, 0);
+            r1 = min(r1 + 1, ci.rows - 1);
+            const ChainLayer pi = info[L - 1];
+            int ia, ib;
+            if (pi.flat) {
+              ia = (r0 * pi.W) / pi.tw;
+              ib = ((r1 + 1) * pi.W - 1) / pi.tw;
+            } else {
+              const int ba = r0 / pi.H, ya = r0 - ba * pi.H, bb = r1 / pi.H, yb = r1 - bb * pi.H;
+              ia = (ba * pi.tiles_y + ya / pi.th) * pi.tiles_x;
+              ib = (bb * pi.tiles_y + yb / pi.th) * pi.tiles_x + pi.tiles_x - 1;
+            }
+            __syncwarp();
+            const int* cnt = done + pi.done_off;
+            for (int i = ia + lane; i <= ib; i += 32) {
+#ifdef YB_WATCHDOG
+              const long long t0 = clock64();
+#endif
+              while (ld_acquire_gpu(cnt + i) < pi.target) {
+#ifdef YB_WATCHDOG
+                if (clock64() - t0 > 4000000000ll) asm volatile("trap;");
+#endif
+              }
+            }
+            __syncwarp();
+            fence_proxy_async_all();   // the tiles were written through the async proxy (TMA stores) and are read through it
+            ready = true;
+          }
+          if (lane == 0) {
+            const CUtensorMap* ma = &p.tmA[p.tap_map[tap]];
+            const int ax = tc_.x0 + p.tap_dx[tap], ay = tc_.y0 + p.tap_dy[tap];
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl)
+              tma_load_4d(sa + pl * A_STAGE_BYTES, ma, &full_bar[s], kc * BLOCK_K + pl * p.cin, ax, ay, tc_.b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      uint32_t kbg = 0, t = 0;
+      for (int L = 0; L < nl; ++L) {
+        const TcParams& p = layers[L];
+        const int num_kb = p.ntaps * p.kchunks;
+        const uint32_t idesc = p.idesc;
+        const int ubase = info[L].ubase, units = info[L].units;
+        for (int u = chain_first_unit(cta, ubase, G); u < units; u += G, ++t) {
+          const uint32_t acc = t & 1u;
+          const uint32_t use = t >> 1;
+          mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * (uint32_t)(NPL * BN);
+          for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+            const uint32_t s = kbg % (uint32_t)stages;
+            const uint32_t it = kbg / (uint32_t)stages;
+            mbar_wait(&full_bar[s], it & 1u);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+            const uint32_t sb = sa + A_BYTES;
+            const uint64_t da = make_sw128_desc(sa);
+            const uint64_t db = make_sw128_desc(sb);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (SPLIT) {
+              const uint64_t dal = make_sw128_desc(sa + A_STAGE_BYTES);
+              const uint64_t dbl = make_sw128_desc(sb + B_PLANE_BYTES);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // A_lo * W_hi -> second accumulator
+                umma_f16(tmem_d + BN, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // A_hi * W_lo -> second accumulator
+                umma_f16(tmem_d + BN, da + (uint64_t)(2 * k), dbl + (uint64_t)(2 * k), idesc, 1u);
+            }
+            umma_commit(&empty_bar[s]);
+          }
+          umma_commit(&tmem_full_bar[acc]);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: two groups of 4 warps, even / odd 64-channel chunks =====================
+    const int quad = warp & 3;
+    const int hgrp = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const bool issuer = (warp == 2 + 4 * hgrp && lane == 0);
+    const uint32_t sw = (uint32_t)(row & 7);
+    float* my_bias = sbias + hgrp * BN;
+    uint8_t* out_tile = out_base + hgrp * BUF_BYTES;
+    auto group_sync = [&]() {
+      if (hgrp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
+    // issuer only: counter to bump once this thread's outstanding stores (the previous tile's) have completed
+    int* pending = nullptr;
+    auto flush_pending = [&]() {
+      bulk_wait_all();            // the stores have been performed, not just read out of shared memory
+      fence_proxy_async_all();
+      red_release_gpu_add(pending, 1);
+      pending = nullptr;
+    };
+    uint32_t t = 0, g = 0;
+    for (int L = 0; L < nl; ++L) {
+      const TcParams& p = layers[L];
+      const int ubase = info[L].ubase, units = info[L].units, done_off = info[L].done_off;
+      const int act = p.act, raa = p.res_after_act, Cout = p.Cout, res_direct = p.res_direct, Wo = p.Wo;
+      const float out_scale = p.out_scale;
+      const float* bias = p.bias;
+      const __half* residual = p.residual;
+      const int n_tiles = p.n_tiles;
+      for (int u = chain_first_unit(cta, ubase, G); u < units; u += G, ++t) {
+        const TileCoord tc_ = decode_unit<false>(p, u, 0, BN);
+        const int x0 = tc_.x0, y0 = tc_.y0, b = tc_.b, n0 = tc_.n0;
+        const uint32_t acc = t & 1u;
+        const uint32_t use = t >> 1;
+        const uint32_t tmem_acc = tmem_base + acc * (uint32_t)(NPL * BN) + ((uint32_t)(quad * 32) << 16);
+        {
+          const int et = (threadIdx.x - 64) & 127;
+          for (int j = et; j < BN; j += 128) my_bias[j] = (bias && n0 + j < Cout) ? __ldg(bias + n0 + j) : 0.f;
+        }
+        // The previous tile's completion signal waits for its stores; that is free when this tile's accumulator is
+        // not ready yet (the group would idle anyway).  When it IS ready the signal is deferred until the first chunk
+        // of this tile has been computed (by then the stores have long landed) -- safe, because a ready accumulator
+        // means this tile depends on nothing that could be waiting for the deferred signal.
+        if (issuer && pending && !mbar_test_wait(smem_u32(&tmem_full_bar[acc]), use & 1u)) flush_pending();
+        mbar_wait(&tmem_full_bar[acc], use & 1u);
+        tc_fence_after();
+        group_sync();
+        const int nchunks = (min(BN, Cout - n0) + 63) >> 6;   // 2 (Cout % 128 == 0 in a chain)
+        const int c_last = ((nchunks - 1 - hgrp) / H) * H + hgrp;
+#pragma unroll 1
+        for (int c = hgrp; c < nchunks; c += H, ++g) {
+          if (g >= 1u) {
+            if (issuer) bulk_wait_read<0>();   // the store that last used this group's staging tile has read it
+            group_sync();
+          }
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(tmem_acc + (uint32_t)(c * 64), r0);
+          tmem_ld32_nowait(tmem_acc + (uint32_t)(c * 64 + 32), r1);
+          if (SPLIT) {
+            uint32_t q[32];
+            tmem_ld32_nowait(tmem_acc + (uint32_t)(BN + c * 64), q);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r0[j] = __float_as_uint(__fmaf_rn(__uint_as_float(q[j]), YB_LO_INV, __uint_as_float(r0[j])));
+            tmem_ld32_nowait(tmem_acc + (uint32_t)(BN + c * 64 + 32), q);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r1[j] = __float_as_uint(__fmaf_rn(__uint_as_float(q[j]), YB_LO_INV, __uint_as_float(r1[j])));
+          }
+          tmem_ld_wait();
+          const int nbase = n0 + c * 64;
+          const float* sb = my_bias + c * 64;
+          const __half* rg = nullptr;
+          if (res_direct && x0 + row < Wo) rg = residual + (size_t)(x0 + row) * (size_t)(NPL * Cout) + nbase;
+          switch (act) {
+            case ACT_RELU: epi_chunk<ACT_RELU, false, SPLIT>(r0, r1, sb, nullptr, out_tile, (uint32_t)row, sw, out_scale, rg, Cout); break;
+            case ACT_LEAKY:
+              if (raa)
+                epi_chunk<ACT_LEAKY, true, SPLIT>(r0, r1, sb, nullptr, out_tile, (uint32_t)row, sw, out_scale, rg, Cout);
+              else
+                epi_chunk<ACT_LEAKY, false, SPLIT>(r0, r1, sb, nullptr, out_tile, (uint32_t)row, sw, out_scale, rg, Cout);
+              break;
+            default: epi_chunk<ACT_NONE, false, SPLIT>(r0, r1, sb, nullptr, out_tile, (uint32_t)row, sw, out_scale, rg, Cout); break;
+          }
+          fence_proxy_async();
+          if (issuer && pending) flush_pending();   // deferred signal of the previous tile
+          if (c == c_last) tc_fence_before();
+          group_sync();
+          if (issuer) {
+            if (c == c_last) mbar_arrive(&tmem_empty_bar[acc]);
+            tma_store_4d(&p.tmY, out_tile, nbase, x0, y0, b);
+            if (SPLIT) tma_store_4d(&p.tmY, out_tile + A_STAGE_BYTES, nbase + Cout, x0, y0, b);
+            bulk_commit();
+          }
+        }
+        if (issuer) pending = done + done_off + u / n_tiles;
+      }
+    }
+    if (issuer) {
+      if (pending) flush_pending();
+      bulk_wait_read<0>();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_dyn(tmem_base, 512u);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -823,6 +1168,8 @@ struct TcConvPlan {
   int pair = 0;
   int epi_groups = 1;   // H: 4-warp epilogue groups per CTA
   int pdl_friendly = 0; // sized so that two CTAs (this kernel's and the next layer's) fit on one SM
+  int flat = 0;         // 1x1 / stride 1 / dense: all pixels of the batch on one axis
+  int B = 0, Ho = 0, Wo = 0;   // the problem's output geometry (prm.Ho / prm.Wo are the flattened view's)
   dim3 grid;
   size_t smem_bytes = 0;
 };
@@ -879,6 +1226,10 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
       best_th = th;
     }
   }
+  plan->flat = flat ? 1 : 0;
+  plan->B = p.B;
+  plan->Ho = p.Ho;
+  plan->Wo = p.Wo;
   q.tw = best_tw;
   q.th = best_th;
   q.tiles_x = ceil_div(Wov, q.tw);
@@ -1183,6 +1534,138 @@ static void launch_s(const TcConvPlan* plan, cudaStream_t stream) {
       default: YB_REQUIRE(false, "tc_conv: bad BN");
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// chains
+// ---------------------------------------------------------------------------------------------
+struct TcChain {
+  int nl = 0, split = 0, grid = 0, n_done = 0;
+  size_t smem_bytes = 0;
+  TcParams* d_layers = nullptr;
+  ChainLayer* d_info = nullptr;
+  int* d_done = nullptr;
+};
+
+// a plan the chain kernel can run: its one tile shape (BN = 128, two epilogue groups, staged epilogue, two accumulator
+// buffers) and nothing the chain does not implement (pairs, stream-K, staged residual, partial N tiles)
+bool tc_conv_plan_chainable(const TcConvPlan* pl) {
+  const TcParams& q = pl->prm;
+  return pl->BN == 128 && !pl->pair && pl->epi_groups == 2 && !pl->sk && !pl->pdl_friendly && q.epi_tma && q.nseg == 0 &&
+         q.Cout % 128 == 0 && (!q.residual || q.res_direct) && (q.act == ACT_RELU || q.act == ACT_NONE || q.act == ACT_LEAKY);
+}
+
+// plans[i + 1] reads what plans[i] writes (dep[i + 1] = 1) or an outside tensor (0); residuals come from anywhere earlier
+TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std::vector<int>& dep) {
+  YB_REQUIRE(!plans.empty() && plans.size() == dep.size(), "tc_chain: empty chain");
+  const TcConvPlan* p0 = plans[0];
+  std::vector<TcParams> lp;
+  std::vector<ChainLayer> li;
+  int ubase = 0, done_off = 0;
+  for (size_t i = 0; i < plans.size(); ++i) {
+    const TcConvPlan* pl = plans[i];
+    YB_REQUIRE(tc_conv_plan_chainable(pl), "tc_chain: plan not chainable");
+    YB_REQUIRE(pl->split == p0->split, "tc_chain: the layers of a chain share one precision mode");
+    YB_REQUIRE(pl->B == p0->B && pl->Ho == p0->Ho && pl->Wo == p0->Wo, "tc_chain: the layers of a chain share one resolution");
+    YB_REQUIRE(i == 0 ? dep[i] == 0 : true, "tc_chain: the first layer reads an outside tensor");
+    ChainLayer c = {};
+    c.ubase = ubase;
+    c.units = pl->prm.m_tiles * pl->prm.n_tiles;
+    c.flat = pl->flat;
+    c.W = pl->Wo;
+    c.H = pl->Ho;
+    c.rows = pl->B * pl->Ho;
+    c.tw = pl->prm.tw;
+    c.th = pl->prm.th;
+    c.tiles_x = pl->prm.tiles_x;
+    c.tiles_y = pl->prm.tiles_y;
+    c.done_off = done_off;
+    c.target = 2 * pl->prm.n_tiles;
+    c.dep = dep[i];
+    ubase += c.units;
+    done_off += pl->prm.m_tiles;
+    lp.push_back(pl->prm);
+    li.push_back(c);
+  }
+  auto* ch = new TcChain();
+  ch->nl = (int)plans.size();
+  ch->split = p0->split;
+  ch->n_done = done_off;
+  {
+    const int npl = p0->split ? 2 : 1;
+    ch->smem_bytes = (size_t)chain_stages(p0->split != 0) * npl * (A_STAGE_BYTES + 128 * BLOCK_K * 2) + (size_t)2 * npl * A_STAGE_BYTES + 1024;
+  }
+  int dev = 0, sms = 148;
+  YB_CHECK_CUDA(cudaGetDevice(&dev));
+  YB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  ch->grid = std::min(sms, ubase);   // one CTA per SM (the shared memory of a CTA sees to that): all co-resident
+  YB_CHECK_CUDA(cudaMalloc(&ch->d_layers, lp.size() * sizeof(TcParams)));
+  YB_CHECK_CUDA(cudaMalloc(&ch->d_info, li.size() * sizeof(ChainLayer)));
+  YB_CHECK_CUDA(cudaMalloc(&ch->d_done, (size_t)done_off * sizeof(int)));
+  YB_CHECK_CUDA(cudaMemcpy(ch->d_layers, lp.data(), lp.size() * sizeof(TcParams), cudaMemcpyHostToDevice));
+  YB_CHECK_CUDA(cudaMemcpy(ch->d_info, li.data(), li.size() * sizeof(ChainLayer), cudaMemcpyHostToDevice));
+  return ch;
+}
+void tc_chain_destroy(TcChain* ch) {
+  if (!ch) return;
+  cudaFree(ch->d_layers);
+  cudaFree(ch->d_info);
+  cudaFree(ch->d_done);
+  delete ch;
+}
+int tc_chain_layers(const TcChain* ch) { return ch->nl; }
+
+template <bool SPLIT>
+static void launch_chain_t(const TcChain* ch, cudaStream_t stream) {
+  static PerDeviceOnce attr;
+  if (attr.first())
+    YB_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)));
+  // Cooperative launch: the grid starts only when ALL its CTAs can be resident at once.  The tile dependencies make CTAs
+  // wait for each other, so a partially scheduled grid (two chains from different streams sharing the SMs) could deadlock.
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ch->grid);
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = ch->smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_chain_kernel<SPLIT>, (const TcParams*)ch->d_layers, (const ChainLayer*)ch->d_info,
+                                   ch->nl, ch->d_done));
+}
+
+// Can a chain launch be captured into a CUDA graph and replayed on this driver?  (One trial per process.)
+bool tc_chain_graph_ok(const TcChain* ch) {
+  static int cached = -1;
+  if (cached >= 0) return cached != 0;
+  bool ok = false;
+  cudaStream_t s = nullptr;
+  cudaGraph_t g = nullptr;
+  cudaGraphExec_t ge = nullptr;
+  if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess) {
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      try {
+        launch_tc_chain(ch, s, nullptr);
+      } catch (const Error&) {
+      }
+      if (cudaStreamEndCapture(s, &g) == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess)
+        ok = (cudaGraphLaunch(ge, s) == cudaSuccess) && (cudaStreamSynchronize(s) == cudaSuccess);
+    }
+  }
+  if (ge) cudaGraphExecDestroy(ge);
+  if (g) cudaGraphDestroy(g);
+  if (s) cudaStreamDestroy(s);
+  cudaGetLastError();
+  cached = ok ? 1 : 0;
+  return ok;
+}
+void launch_tc_chain(const TcChain* ch, cudaStream_t stream, LaunchCounter* lc) {
+  YB_CHECK_CUDA(cudaMemsetAsync(ch->d_done, 0, (size_t)ch->n_done * sizeof(int), stream));   // (a memset node in the captured graph)
+  if (ch->split) launch_chain_t<true>(ch, stream); else launch_chain_t<false>(ch, stream);
+  YB_CHECK_LAUNCH();
+  if (lc) lc->n++;
 }
 
 void launch_tc_conv(const TcConvPlan* plan, cudaStream_t stream, LaunchCounter* lc) {
