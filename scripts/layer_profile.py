@@ -23,4 +23,7 @@ for name, ms in prof:
     if m:
         ci, co, k, s, ho, wo = map(int, m.groups())
         gf = 2.0 * a.batch * ho * wo * ci * co * k * k / 1e9
+    m = re.search(r"gflop=([0-9.]+)", name)      # a chain of layers in one launch carries its total
+    if m:
+        gf = float(m.group(1))
     print("| %s | %.4f | %.2f | %.0f |" % (name, ms, gf, gf / ms if ms > 0 else 0))

@@ -18,10 +18,12 @@ pytestmark = pytest.mark.gpu
 
 CASES = [
     # config, batch, height, width
-    ("yolact_base_config", 2, 550, 550),          # stage 3: 23 blocks at 35x35 (67 chained layers), protonet at 69x69
+    ("yolact_base_config", 2, 550, 550),          # the whole trunk after the max-pool (102 layers, 4 resolutions), FPN, protonet
     ("yolact_base_config", 3, 256, 320),          # non-square, odd batch: flat tiles straddle rows and images
     ("yolact_resnet50_config", 1, 160, 160),      # a single M tile per layer
     ("yolact_im700_config", 1, 700, 700),
+    ("yolact_plus_resnet50_config", 2, 256, 256), # DCN blocks cut the trunk into several runs
+    ("yolact_darknet53_config", 2, 320, 320),     # 3x3 + residual layers are not chainable: short runs only
 ]
 
 

@@ -482,56 +482,75 @@ struct NetBuilder {
     push(op);
   }
 
-  // Runs of consecutive tensor-core convolutions in ops [begin, end) -- each reading the previous one's output, all at
-  // one resolution: the 1x1 -> 3x3 -> 1x1 bottlenecks of a ResNet stage after its first block (backbone.py:37-57), the
-  // protonet's 3x3 stack -- are re-planned for the chain kernel (tc_conv.cu) and replaced by ONE launch when that is
-  // faster than the separately tuned launches (both are timed here).  Returns the new end of the range.
+  // Runs of consecutive tensor-core convolutions in ops [begin, end) of one graph lane -- the whole ResNet trunk after
+  // the max-pool (backbone.py:37-57,126-139: every bottleneck incl. the stride-2 and downsample layers), the FPN's
+  // prediction / downsample layers, the protonet's 3x3 stack -- are re-planned for the chain kernel (tc_conv.cu) and
+  // replaced by ONE launch when that is faster than the separately tuned launches (both are timed here).  A layer of a
+  // run reads tensors written by earlier layers of the run (tracked per tile inside the kernel) or by ops before the run
+  // (complete before the launch).  Returns the new end of the range.
   size_t form_chains(size_t begin, size_t end) {
     if (dry || h->chain_mode == 0) return end;
     auto& ops = ex->ops;
-    auto candidate = [&](const Op& op) {
-      if (!op.has_prob) return false;
+    // the chain's own plan of an op: one tile shape family (N tile 128, or 64 for 64-channel layers); null = not chainable
+    auto chain_plan = [&](const Op& op) -> TcConvPlan* {
+      if (!op.has_prob) return nullptr;
       const ConvProblem& q = op.prob;
-      return q.split && q.stride == 1 && ((q.KH == 1 && q.pad == 0) || (q.KH == 3 && q.pad == 1)) && q.KH == q.KW &&
-             q.Cout % 128 == 0 && !q.y_f32 && q.nseg == 0 && q.y_pix_stride == 2 * q.Cout &&
-             q.y_batch_stride == (int64_t)q.Ho * q.Wo * q.y_pix_stride;
+      if (!(q.split && q.KH == q.KW && (q.KH == 1 || q.KH == 3) && (q.stride == 1 || q.stride == 2) && q.Cout % 64 == 0 &&
+            !q.y_f32 && q.nseg == 0 && q.y_pix_stride == 2 * q.Cout && q.y_batch_stride == (int64_t)q.Ho * q.Wo * q.y_pix_stride))
+        return nullptr;
+      TcConvPlan* pl = nullptr;
+      try {
+        pl = tc_conv_plan_create(q, op.w_tc, (q.Cout % 128 == 0) ? 128 : 64, 2, 148, 0, 2, 0, 0);
+      } catch (const Error&) {
+        return nullptr;
+      }
+      if (!tc_conv_plan_chainable(pl)) {
+        tc_conv_plan_destroy(pl);
+        return nullptr;
+      }
+      return pl;
     };
     size_t i = begin;
     while (i < end) {
-      if (!candidate(ops[i])) {
-        ++i;
-        continue;
-      }
-      size_t k = i + 1;
-      while (k < end && candidate(ops[k]) && ops[k].lane == ops[i].lane && ops[k].prob.x == ops[k - 1].prob.y &&
-             ops[k].prob.B == ops[i].prob.B && ops[k].prob.Ho == ops[i].prob.Ho && ops[k].prob.Wo == ops[i].prob.Wo)
-        ++k;
-      const size_t n = k - i;
-      if (n < 3) {
-        i = k;
-        continue;
-      }
-      // the chain's own plans: one tile shape for every layer
       std::vector<TcConvPlan*> cp;
-      bool ok = true;
-      for (size_t j = i; j < k && ok; ++j) {
-        TcConvPlan* pl = nullptr;
-        try {
-          pl = tc_conv_plan_create(ops[j].prob, ops[j].w_tc, 128, 2, 148, 0, 2, 0, 0);
-        } catch (const Error&) {
-          ok = false;
-          break;
-        }
+      size_t k = i;
+      while (k < end && ops[k].lane == ops[i].lane && (!ops[k].has_prob || !ops[i].has_prob || ops[k].prob.B == ops[i].prob.B)) {
+        TcConvPlan* pl = chain_plan(ops[k]);
+        if (!pl) break;
         cp.push_back(pl);
-        if (!tc_conv_plan_chainable(pl)) ok = false;
+        ++k;
+      }
+      const size_t n = k - i;
+      if (n < 2) {
+        for (auto* pl : cp) tc_conv_plan_destroy(pl);
+        i = std::max(k, i + 1);
+        continue;
+      }
+      // who writes what: input / residual produced inside the run -> a per-tile dependency
+      std::vector<int> dep_a(n, -1), dep_r(n, -1);
+      for (size_t j = 0; j < n; ++j)
+        for (size_t q = 0; q < j; ++q) {
+          if (ops[i + q].prob.y == ops[i + j].prob.x) dep_a[j] = (int)q;
+          if (ops[i + j].prob.residual && ops[i + q].prob.y == ops[i + j].prob.residual) dep_r[j] = (int)q;
+        }
+      // a residual written by a layer that the input chain leads back to through stride-1 layers is complete (on the
+      // rows this layer needs) whenever the input is: conv3's residual, the previous block's output, via conv2 and conv1
+      for (size_t j = 0; j < n; ++j) {
+        if (dep_r[j] < 0) continue;
+        int a = (int)j;
+        for (int step = 0; step < 8 && a >= 0 && ops[i + a].prob.stride == 1; ++step) {
+          a = dep_a[a];
+          if (a == dep_r[j]) {
+            dep_r[j] = -1;
+            break;
+          }
+        }
       }
       TcChain* chain = nullptr;
-      if (ok) {
+      {
         std::vector<const TcConvPlan*> cpl(cp.begin(), cp.end());
-        std::vector<int> dep(n, 1);
-        dep[0] = 0;
         try {
-          chain = tc_chain_create(cpl, dep);
+          chain = tc_chain_create(cpl, dep_a, dep_r);
         } catch (const Error&) {
           chain = nullptr;
         }
@@ -566,8 +585,9 @@ struct NetBuilder {
         cudaEventDestroy(e1);
         use = (h->chain_mode == 2) || ms_chain < ms_sep;
         if (getenv("YB_CHAIN_VERBOSE"))
-          fprintf(stderr, "[yolact_b200] chain %s .. (%zu layers): chain %.3f ms, separate %.3f ms -> %s\n", ops[i].name.c_str(),
-                  n, ms_chain, ms_sep, use ? "chain" : "separate");
+          fprintf(stderr, "[yolact_b200] chain %s .. %s (%zu layers): chain %.3f ms, separate %.3f ms -> %s\n",
+                  ops[i].name.substr(0, ops[i].name.find(' ')).c_str(), ops[k - 1].name.substr(0, ops[k - 1].name.find(' ')).c_str(), n,
+                  ms_chain, ms_sep, use ? "chain" : "separate");
       }
       if (!use) {
         if (chain) tc_chain_destroy(chain);
@@ -581,8 +601,17 @@ struct NetBuilder {
       op.is_conv = true;
       op.lane = ops[i].lane;
       op.name = "chain x" + std::to_string(n) + " [" + ops[i].name.substr(0, ops[i].name.find(' ')) + " .. " +
-                ops[k - 1].name.substr(0, ops[k - 1].name.find(' ')) + "] " + std::to_string(ops[i].prob.Ho) + "x" +
-                std::to_string(ops[i].prob.Wo) + " tc BN=128 st=2 g=148 epi2";
+                ops[k - 1].name.substr(0, ops[k - 1].name.find(' ')) + "] tc BN=128/64 st=2 g=148 epi2";
+      {
+        double gf = 0.0;
+        for (size_t j = i; j < k; ++j) {
+          const ConvProblem& q = ops[j].prob;
+          gf += 2.0 * q.B * q.Ho * q.Wo * (double)q.Cin * q.Cout * q.KH * q.KW / 1e9;
+        }
+        char buf[48];
+        snprintf(buf, sizeof(buf), " gflop=%.2f", gf);
+        op.name += buf;
+      }
       LaunchCounter* lc = &h->lc;
       op.fn = [chain, lc](cudaStream_t s) { launch_tc_chain(chain, s, lc); };
       ops[i] = op;

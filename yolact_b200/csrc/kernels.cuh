@@ -77,7 +77,7 @@ void launch_tc_conv(const TcConvPlan* plan, cudaStream_t stream, LaunchCounter* 
 // dependency counters instead of kernel boundaries (tc_conv.cu, "chain kernel"); the plans must outlive the chain
 struct TcChain;
 bool tc_conv_plan_chainable(const TcConvPlan* plan);
-TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std::vector<int>& dep);
+TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std::vector<int>& dep_a, const std::vector<int>& dep_r);
 void tc_chain_destroy(TcChain* chain);
 int tc_chain_layers(const TcChain* chain);
 bool tc_chain_graph_ok(const TcChain* chain);

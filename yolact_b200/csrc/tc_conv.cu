@@ -90,6 +90,7 @@ struct alignas(64) TcParams {
   // split plans with two epilogue groups on a flattened (1x1, stride 1) layout read the residual straight from global
   // memory: its staging tiles (2 x 32 KB) would leave a single pipeline stage beside the two output staging buffers
   int res_direct;
+  int bn;               // N tile (the kernel template's BN; the chain kernel reads it per layer)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -775,21 +776,38 @@ tc_conv_kernel(const __grid_constant__ TcParams p) {
 // CTA (TMA ring, TMEM accumulators, staging tiles) simply keep running across the layer boundary.
 // Dependencies are tracked per M tile instead of by a grid-wide barrier: the epilogue groups bump done[layer][m tile]
 // once their stores of a tile have completed; before the first ACTIVATION load of a tile the producer warp waits until
-// every tile of the previous layer that overlaps the tile's rows +-1 (the 3x3 halo) has been finished by all its
-// N tiles (the weight tiles of the first k-blocks are requested before the wait).  All dependencies point backwards in
-// the unit list and every CTA walks its units in list order, so the earliest unfinished unit can always run: no
-// deadlock as long as the CTAs are co-resident (grid <= SM count, one CTA per SM).
+// every tile of the layer that produces its input which overlaps the input rows the tile reads (its own rows mapped
+// through stride / padding / kernel height), and every tile of the layer that produces its residual which overlaps its
+// own rows, has been finished by all its N tiles (the weight tiles of the first k-blocks are requested before the
+// wait).  Layers may differ in resolution (stride-2 layers), N tile (64 / 128) and tile shape.  All dependencies point
+// backwards in the unit list and every CTA walks its units in list order, so the earliest unfinished unit can always
+// run: no deadlock as long as the CTAs are co-resident (cooperative launch, one CTA per SM).
+// Every activation has its own buffer (engine.cu alloc_act: nothing is recycled inside a forward pass), so there are
+// no write-after-read hazards to order.
 struct ChainLayer {
   int ubase;               // position of this layer's unit 0 in the chain's unit list
   int units;               // m_tiles * n_tiles
   int flat;                // 1: tile m = pixels [m * tw, m * tw + tw) of the flattened B*H*W axis; 0: tiles_x x tiles_y tiles per image
-  int W, H, rows;          // image size; rows = B * H  (global row r = b * H + y, pixel = r * W + x)
+  int W, H, rows;          // OUTPUT image size; rows = B * H  (global row r = b * H + y, pixel = r * W + x)
   int tw, th, tiles_x, tiles_y;
   int done_off;            // this layer's counters: done[done_off + m_tile]
   int target;              // a finished M tile: n_tiles * 2 (each epilogue group of each N tile adds 1)
-  int dep;                 // 1: the input comes from the previous layer of the chain
-  int pad_;
+  int dep_a;               // chain layer that writes this layer's input (-1: a tensor complete before the launch)
+  int dep_r;               // chain layer that writes this layer's residual (-1: none / outside / implied by dep_a's own dependencies)
+  int stride, pad, kh;     // output row y reads input rows [y * stride - pad, y * stride - pad + kh)
 };
+
+// M tiles of layer `pi` that overlap its global rows [ra, rb]
+__device__ __forceinline__ void chain_tiles_of_rows(const ChainLayer& pi, int ra, int rb, int& ia, int& ib) {
+  if (pi.flat) {
+    ia = (ra * pi.W) / pi.tw;
+    ib = ((rb + 1) * pi.W - 1) / pi.tw;
+  } else {
+    const int ba = ra / pi.H, ya = ra - ba * pi.H, bb = rb / pi.H, yb = rb - bb * pi.H;
+    ia = (ba * pi.tiles_y + ya / pi.th) * pi.tiles_x;
+    ib = (bb * pi.tiles_y + yb / pi.th) * pi.tiles_x + pi.tiles_x - 1;
+  }
+}
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
@@ -874,20 +892,20 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
 
   if (warp == 0) {
     // ===================== TMA producer (lane 0 issues; the whole warp polls the dependency counters) =====================
-    const uint32_t tx_bytes_b = (uint32_t)B_PLANE_BYTES * (uint32_t)NPL;
     uint32_t kbg = 0;
     for (int L = 0; L < nl; ++L) {
       const TcParams& p = layers[L];
       const ChainLayer ci = info[L];
       const int num_kb = p.ntaps * p.kchunks;
-      const uint32_t tx_bytes = (uint32_t)p.a_box_bytes * (uint32_t)NPL + tx_bytes_b;
+      const int bn = p.bn;
+      const uint32_t tx_bytes = ((uint32_t)p.a_box_bytes + (uint32_t)(bn * BLOCK_K * 2)) * (uint32_t)NPL;
       if (lane == 0 && L + 1 < nl) {   // the next layer's descriptors: fetched long before their first use
         tma_prefetch_desc(&layers[L + 1].tmB);
         tma_prefetch_desc(&layers[L + 1].tmA[0]);
       }
       for (int u = chain_first_unit(cta, ci.ubase, G); u < ci.units; u += G) {
-        const TileCoord tc_ = decode_unit<false>(p, u, 0, BN);
-        bool ready = (ci.dep == 0);
+        const TileCoord tc_ = decode_unit<false>(p, u, 0, bn);
+        bool ready = (ci.dep_a < 0 && ci.dep_r < 0);
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)stages;
           const uint32_t it = kbg / (uint32_t)stages;
@@ -903,8 +921,7 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
               tma_load_3d(sb + pl * B_PLANE_BYTES, &p.tmB, &full_bar[s], kc * BLOCK_K + pl * p.cin, tc_.n0, tap);
           }
           if (!ready) {
-            // rows of this tile, +-1 for the 3x3 halo (kept for the 1x1 layers too: it also orders a writer behind every
-            // reader of a recycled buffer, should the engine ever recycle activations)
+            // global output rows [r0, r1] of this tile
             int r0, r1;
             if (ci.flat) {
               const int lo = tc_.x0, hi = min(tc_.x0 + ci.tw, ci.rows * ci.W) - 1;
@@ -914,25 +931,32 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
               r0 = tc_.b * ci.H + tc_.y0;
               r1 = tc_.b * ci.H + min(tc_.y0 + ci.th, ci.H) - 1;
             }
-            r0 = max(r0 - 1, 0);
-            r1 = min(r1 + 1, ci.rows - 1);
-            const ChainLayer pi = info[L - 1];
-            int ia, ib;
-            if (pi.flat) {
-              ia = (r0 * pi.W) / pi.tw;
-              ib = ((r1 + 1) * pi.W - 1) / pi.tw;
-            } else {
-              const int ba = r0 / pi.H, ya = r0 - ba * pi.H, bb = r1 / pi.H, yb = r1 - bb * pi.H;
-              ia = (ba * pi.tiles_y + ya / pi.th) * pi.tiles_x;
-              ib = (bb * pi.tiles_y + yb / pi.th) * pi.tiles_x + pi.tiles_x - 1;
+            int ia = 0, ib = -1, ja = 0, jb = -1, ta = 0, tr = 0;
+            const int *ca = done, *cr = done;
+            if (ci.dep_a >= 0) {   // input rows, in the producer's row numbering (its image height differs under a stride)
+              const ChainLayer pa = info[ci.dep_a];
+              const int b0 = r0 / ci.H, y0 = r0 - b0 * ci.H, b1 = r1 / ci.H, y1 = r1 - b1 * ci.H;
+              const int ra = b0 * pa.H + max(y0 * ci.stride - ci.pad, 0);
+              const int rb = b1 * pa.H + min(y1 * ci.stride - ci.pad + ci.kh - 1, pa.H - 1);
+              chain_tiles_of_rows(pa, ra, rb, ia, ib);
+              ca = done + pa.done_off;
+              ta = pa.target;
             }
+            if (ci.dep_r >= 0) {   // the residual has this layer's geometry
+              const ChainLayer pr = info[ci.dep_r];
+              chain_tiles_of_rows(pr, r0, r1, ja, jb);
+              cr = done + pr.done_off;
+              tr = pr.target;
+            }
+            const int na = ib - ia + 1, nr = jb - ja + 1;
             __syncwarp();
-            const int* cnt = done + pi.done_off;
-            for (int i = ia + lane; i <= ib; i += 32) {
+            for (int i = lane; i < na + nr; i += 32) {
+              const int* c = (i < na) ? ca + ia + i : cr + ja + (i - na);
+              const int tgt = (i < na) ? ta : tr;
 #ifdef YB_WATCHDOG
               const long long t0 = clock64();
 #endif
-              while (ld_acquire_gpu(cnt + i) < pi.target) {
+              while (ld_acquire_gpu(c) < tgt) {
 #ifdef YB_WATCHDOG
                 if (clock64() - t0 > 4000000000ll) asm volatile("trap;");
 #endif
@@ -1025,15 +1049,16 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
       const float* bias = p.bias;
       const __half* residual = p.residual;
       const int n_tiles = p.n_tiles;
+      const int bn = p.bn;
       for (int u = chain_first_unit(cta, ubase, G); u < units; u += G, ++t) {
-        const TileCoord tc_ = decode_unit<false>(p, u, 0, BN);
+        const TileCoord tc_ = decode_unit<false>(p, u, 0, bn);
         const int x0 = tc_.x0, y0 = tc_.y0, b = tc_.b, n0 = tc_.n0;
         const uint32_t acc = t & 1u;
         const uint32_t use = t >> 1;
         const uint32_t tmem_acc = tmem_base + acc * (uint32_t)(NPL * BN) + ((uint32_t)(quad * 32) << 16);
         {
           const int et = (threadIdx.x - 64) & 127;
-          for (int j = et; j < BN; j += 128) my_bias[j] = (bias && n0 + j < Cout) ? __ldg(bias + n0 + j) : 0.f;
+          for (int j = et; j < bn; j += 128) my_bias[j] = (bias && n0 + j < Cout) ? __ldg(bias + n0 + j) : 0.f;
         }
         // The previous tile's completion signal waits for its stores; that is free when this tile's accumulator is
         // not ready yet (the group would idle anyway).  When it IS ready the signal is deferred until the first chunk
@@ -1043,8 +1068,15 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
         mbar_wait(&tmem_full_bar[acc], use & 1u);
         tc_fence_after();
         group_sync();
-        const int nchunks = (min(BN, Cout - n0) + 63) >> 6;   // 2 (Cout % 128 == 0 in a chain)
+        const int nchunks = (min(bn, Cout - n0) + 63) >> 6;   // 2, or 1 for a 64-wide N tile
         const int c_last = ((nchunks - 1 - hgrp) / H) * H + hgrp;
+        if (nchunks <= hgrp) {   // a 64-wide tile: nothing for the second group, which only hands the accumulator back
+          tc_fence_before();
+          if (issuer) {
+            mbar_arrive(&tmem_empty_bar[acc]);
+            if (pending) flush_pending();
+          }
+        }
 #pragma unroll 1
         for (int c = hgrp; c < nchunks; c += H, ++g) {
           if (g >= 1u) {
@@ -1091,7 +1123,10 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
             bulk_commit();
           }
         }
-        if (issuer) pending = done + done_off + u / n_tiles;
+        if (issuer) {
+          if (nchunks > hgrp) pending = done + done_off + u / n_tiles;
+          else red_release_gpu_add(done + done_off + u / n_tiles, 1);   // nothing stored: counts at once
+        }
       }
     }
     if (issuer) {
@@ -1170,6 +1205,7 @@ struct TcConvPlan {
   int pdl_friendly = 0; // sized so that two CTAs (this kernel's and the next layer's) fit on one SM
   int flat = 0;         // 1x1 / stride 1 / dense: all pixels of the batch on one axis
   int B = 0, Ho = 0, Wo = 0;   // the problem's output geometry (prm.Ho / prm.Wo are the flattened view's)
+  int Hi = 0, Wi = 0, stride = 1, pad = 0, KH = 1;
   dim3 grid;
   size_t smem_bytes = 0;
 };
@@ -1230,6 +1266,11 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   plan->B = p.B;
   plan->Ho = p.Ho;
   plan->Wo = p.Wo;
+  plan->Hi = p.H;
+  plan->Wi = p.W;
+  plan->stride = p.stride;
+  plan->pad = p.pad;
+  plan->KH = p.KH;
   q.tw = best_tw;
   q.th = best_th;
   q.tiles_x = ceil_div(Wov, q.tw);
@@ -1295,6 +1336,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
     }
   }
   const int BN = plan->BN;
+  q.bn = BN;
   plan->pair = pair;
   q.pair = pair;
   q.nb = Bv;
@@ -1551,13 +1593,14 @@ struct TcChain {
 // buffers) and nothing the chain does not implement (pairs, stream-K, staged residual, partial N tiles)
 bool tc_conv_plan_chainable(const TcConvPlan* pl) {
   const TcParams& q = pl->prm;
-  return pl->BN == 128 && !pl->pair && pl->epi_groups == 2 && !pl->sk && !pl->pdl_friendly && q.epi_tma && q.nseg == 0 &&
-         q.Cout % 128 == 0 && (!q.residual || q.res_direct) && (q.act == ACT_RELU || q.act == ACT_NONE || q.act == ACT_LEAKY);
+  return (pl->BN == 128 || pl->BN == 64) && !pl->pair && pl->epi_groups == 2 && !pl->sk && !pl->pdl_friendly && q.epi_tma &&
+         q.nseg == 0 && q.Cout % pl->BN == 0 && (!q.residual || q.res_direct) && (q.act == ACT_RELU || q.act == ACT_NONE || q.act == ACT_LEAKY);
 }
 
-// plans[i + 1] reads what plans[i] writes (dep[i + 1] = 1) or an outside tensor (0); residuals come from anywhere earlier
-TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std::vector<int>& dep) {
-  YB_REQUIRE(!plans.empty() && plans.size() == dep.size(), "tc_chain: empty chain");
+// dep_a[i] / dep_r[i]: index (< i) of the plan that writes plan i's input / residual, -1 for a tensor that is complete
+// before the launch (or, for the residual, one whose completion the input dependency already implies)
+TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std::vector<int>& dep_a, const std::vector<int>& dep_r) {
+  YB_REQUIRE(!plans.empty() && plans.size() == dep_a.size() && plans.size() == dep_r.size(), "tc_chain: empty chain");
   const TcConvPlan* p0 = plans[0];
   std::vector<TcParams> lp;
   std::vector<ChainLayer> li;
@@ -1566,8 +1609,10 @@ TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std:
     const TcConvPlan* pl = plans[i];
     YB_REQUIRE(tc_conv_plan_chainable(pl), "tc_chain: plan not chainable");
     YB_REQUIRE(pl->split == p0->split, "tc_chain: the layers of a chain share one precision mode");
-    YB_REQUIRE(pl->B == p0->B && pl->Ho == p0->Ho && pl->Wo == p0->Wo, "tc_chain: the layers of a chain share one resolution");
-    YB_REQUIRE(i == 0 ? dep[i] == 0 : true, "tc_chain: the first layer reads an outside tensor");
+    YB_REQUIRE(pl->B == p0->B, "tc_chain: the layers of a chain share one batch size");
+    YB_REQUIRE(dep_a[i] < (int)i && dep_r[i] < (int)i, "tc_chain: dependencies point backwards");
+    YB_REQUIRE(dep_r[i] < 0 || (plans[dep_r[i]]->Ho == pl->Ho && plans[dep_r[i]]->Wo == pl->Wo), "tc_chain: residual geometry");
+    YB_REQUIRE(dep_a[i] < 0 || (plans[dep_a[i]]->Ho == pl->Hi && plans[dep_a[i]]->Wo == pl->Wi), "tc_chain: input geometry");
     ChainLayer c = {};
     c.ubase = ubase;
     c.units = pl->prm.m_tiles * pl->prm.n_tiles;
@@ -1581,7 +1626,11 @@ TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std:
     c.tiles_y = pl->prm.tiles_y;
     c.done_off = done_off;
     c.target = 2 * pl->prm.n_tiles;
-    c.dep = dep[i];
+    c.dep_a = dep_a[i];
+    c.dep_r = dep_r[i];
+    c.stride = pl->stride;
+    c.pad = pl->pad;
+    c.kh = pl->KH;
     ubase += c.units;
     done_off += pl->prm.m_tiles;
     lp.push_back(pl->prm);
