@@ -216,7 +216,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 
 // ---- host: cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link) ----
 void encode_map_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box);
+                    const uint32_t* box, int swizzle_bytes = 128);   // 128 or 64 (inner box extent = that many bytes)
 
 }  // namespace tc
 }  // namespace yb

@@ -45,6 +45,7 @@ struct alignas(64) TcParams {
   CUtensorMap tmB;
   CUtensorMap tmY;      // output tile store  (epi_tma)
   CUtensorMap tmR;      // residual tile load (epi_tma && residual)
+  CUtensorMap tmY32;    // output tile store in 32-channel boxes, 64-byte swizzle (chain kernel: 8 KB staging tiles)
   int epi_tma;          // 1: fp16 NHWC output goes smem -> TMA store, residual comes in by TMA
   int out_off;          // byte offset of the 2 x 16 KB epilogue staging tiles inside dynamic smem
   int res_off;          // byte offset of the residual staging buffers inside dynamic smem
@@ -208,6 +209,70 @@ __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1
         l2[j] = lo2_from_f32(c0 - hf.x, c1 - hf.y);   // lo plane: residual * 2^11 (see common.cuh)
       }
       *reinterpret_cast<uint4*>(out_tile + A_STAGE_BYTES + off) = ol;
+    }
+  }
+}
+
+// Chain-kernel variant: a 32-channel chunk of one accumulator row (r: the combined fp32 accumulator) into an 8 KB staging
+// tile of 128 rows x 64 bytes with the 64-byte TMA swizzle (16-byte unit index ^= (row >> 1) & 3); the lo plane's tile
+// follows the hi plane's.  The residual always comes from global memory (res_g: this row's 32 channels, hi plane).
+constexpr int CHUNK32_BYTES = BLOCK_M * 32 * 2;   // 8 KB
+template <int ACT, bool RES_AFTER, bool SPLIT>
+__device__ __forceinline__ void epi_chunk32(const uint32_t* r, const float* sbias, uint8_t* out_tile, uint32_t row,
+                                            float out_scale, const __half* res_g, int res_lo_off) {
+  const uint32_t sw = (row >> 1) & 3u;
+#pragma unroll
+  for (int j8 = 0; j8 < 4; ++j8) {
+    const float4 b0 = *reinterpret_cast<const float4*>(sbias + j8 * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(sbias + j8 * 8 + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = __uint_as_float(r[j8 * 8 + j]);
+      v[j] = SPLIT ? __fmaf_rn(a, out_scale, bb[j]) : a + bb[j];
+      if (RES_AFTER) v[j] = act_t<ACT>(v[j]);
+    }
+    if (res_g) {
+      const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(res_g + j8 * 8));   // L2: other SMs wrote it during this launch
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        v[2 * j] += f.x;
+        v[2 * j + 1] += f.y;
+      }
+      if (SPLIT) {
+        const uint4 rawl = __ldcg(reinterpret_cast<const uint4*>(res_g + res_lo_off + j8 * 8));
+        const __half2* l2 = reinterpret_cast<const __half2*>(&rawl);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = lo2_to_f32(l2[j]);
+          v[2 * j] += f.x;
+          v[2 * j + 1] += f.y;
+        }
+      }
+    }
+    if (!RES_AFTER) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = act_t<ACT>(v[j]);
+    }
+    const uint32_t off = row * 64u + (((uint32_t)j8 ^ sw) << 4);
+    uint4 o;
+    __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o2[j] = pack_sat(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(out_tile + off) = o;
+    if (SPLIT) {
+      uint4 ol;
+      __half2* l2 = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 hf = __half22float2(o2[j]);
+        const float c0 = fminf(fmaxf(v[2 * j], -65504.f), 65504.f), c1 = fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f);
+        l2[j] = lo2_from_f32(c0 - hf.x, c1 - hf.y);
+      }
+      *reinterpret_cast<uint4*>(out_tile + CHUNK32_BYTES + off) = ol;
     }
   }
 }
@@ -820,7 +885,7 @@ __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-__host__ __device__ constexpr int chain_stages(bool split) { return split ? 2 : 4; }
+__host__ __device__ constexpr int chain_stages(bool split) { return split ? 3 : 6; }
 __device__ __forceinline__ bool mbar_test_wait(uint32_t addr, uint32_t parity) {   // non-blocking
   uint32_t ok;
   asm volatile(
@@ -850,9 +915,11 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
   constexpr int B_PLANE_BYTES = BN * BLOCK_K * 2;
   constexpr int A_BYTES = NPL * A_STAGE_BYTES;
   constexpr int STAGE_BYTES = A_BYTES + NPL * B_PLANE_BYTES;
-  constexpr int BUF_BYTES = NPL * A_STAGE_BYTES;
+  constexpr int BUF_BYTES = NPL * CHUNK32_BYTES;
   // the chain's own shared-memory layout (the plans' stage counts / offsets are not used): ring, then one staging
-  // buffer per epilogue group; two TMEM accumulator buffers
+  // buffer per epilogue group; two TMEM accumulator buffers.  The epilogue moves 32-channel chunks (8 KB tiles), which
+  // leaves room for a THIRD split-precision stage (3 x 64 KB + 32 KB): the main loop is bound by the bytes a CTA can
+  // keep in flight towards L2, not by the tensor pipe (profiles/ncu_tc_chain_r02.md)
   constexpr int stages = chain_stages(SPLIT);
 
   extern __shared__ uint8_t smem_dyn[];
@@ -882,7 +949,7 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
     fence_barrier_init();
     tma_prefetch_desc(&layers[0].tmB);
     tma_prefetch_desc(&layers[0].tmA[0]);
-    tma_prefetch_desc(&layers[0].tmY);
+    tma_prefetch_desc(&layers[0].tmY32);
   }
   if (warp == 1) tmem_alloc_dyn(&s_tmem_base, 512u);
   tc_fence_before();
@@ -1068,9 +1135,9 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
         mbar_wait(&tmem_full_bar[acc], use & 1u);
         tc_fence_after();
         group_sync();
-        const int nchunks = (min(bn, Cout - n0) + 63) >> 6;   // 2, or 1 for a 64-wide N tile
+        const int nchunks = (min(bn, Cout - n0) + 31) >> 5;   // 32-channel chunks: 4, or 2 for a 64-wide N tile
         const int c_last = ((nchunks - 1 - hgrp) / H) * H + hgrp;
-        if (nchunks <= hgrp) {   // a 64-wide tile: nothing for the second group, which only hands the accumulator back
+        if (nchunks <= hgrp) {   // nothing for this group, which only hands the accumulator back
           tc_fence_before();
           if (issuer) {
             mbar_arrive(&tmem_empty_bar[acc]);
@@ -1083,34 +1150,30 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
             if (issuer) bulk_wait_read<0>();   // the store that last used this group's staging tile has read it
             group_sync();
           }
-          uint32_t r0[32], r1[32];
-          tmem_ld32_nowait(tmem_acc + (uint32_t)(c * 64), r0);
-          tmem_ld32_nowait(tmem_acc + (uint32_t)(c * 64 + 32), r1);
+          uint32_t r[32];
+          tmem_ld32_nowait(tmem_acc + (uint32_t)(c * 32), r);
           if (SPLIT) {
             uint32_t q[32];
-            tmem_ld32_nowait(tmem_acc + (uint32_t)(BN + c * 64), q);
+            tmem_ld32_nowait(tmem_acc + (uint32_t)(BN + c * 32), q);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) r0[j] = __float_as_uint(__fmaf_rn(__uint_as_float(q[j]), YB_LO_INV, __uint_as_float(r0[j])));
-            tmem_ld32_nowait(tmem_acc + (uint32_t)(BN + c * 64 + 32), q);
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__fmaf_rn(__uint_as_float(q[j]), YB_LO_INV, __uint_as_float(r[j])));
+          } else {
             tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r1[j] = __float_as_uint(__fmaf_rn(__uint_as_float(q[j]), YB_LO_INV, __uint_as_float(r1[j])));
           }
-          tmem_ld_wait();
-          const int nbase = n0 + c * 64;
-          const float* sb = my_bias + c * 64;
+          const int nbase = n0 + c * 32;
+          const float* sb = my_bias + c * 32;
           const __half* rg = nullptr;
           if (res_direct && x0 + row < Wo) rg = residual + (size_t)(x0 + row) * (size_t)(NPL * Cout) + nbase;
           switch (act) {
-            case ACT_RELU: epi_chunk<ACT_RELU, false, SPLIT>(r0, r1, sb, nullptr, out_tile, (uint32_t)row, sw, out_scale, rg, Cout); break;
+            case ACT_RELU: epi_chunk32<ACT_RELU, false, SPLIT>(r, sb, out_tile, (uint32_t)row, out_scale, rg, Cout); break;
             case ACT_LEAKY:
               if (raa)
-                epi_chunk<ACT_LEAKY, true, SPLIT>(r0, r1, sb, nullptr, out_tile, (uint32_t)row, sw, out_scale, rg, Cout);
+                epi_chunk32<ACT_LEAKY, true, SPLIT>(r, sb, out_tile, (uint32_t)row, out_scale, rg, Cout);
               else
-                epi_chunk<ACT_LEAKY, false, SPLIT>(r0, r1, sb, nullptr, out_tile, (uint32_t)row, sw, out_scale, rg, Cout);
+                epi_chunk32<ACT_LEAKY, false, SPLIT>(r, sb, out_tile, (uint32_t)row, out_scale, rg, Cout);
               break;
-            default: epi_chunk<ACT_NONE, false, SPLIT>(r0, r1, sb, nullptr, out_tile, (uint32_t)row, sw, out_scale, rg, Cout); break;
+            default: epi_chunk32<ACT_NONE, false, SPLIT>(r, sb, out_tile, (uint32_t)row, out_scale, rg, Cout); break;
           }
           fence_proxy_async();
           if (issuer && pending) flush_pending();   // deferred signal of the previous tile
@@ -1118,8 +1181,8 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
           group_sync();
           if (issuer) {
             if (c == c_last) mbar_arrive(&tmem_empty_bar[acc]);
-            tma_store_4d(&p.tmY, out_tile, nbase, x0, y0, b);
-            if (SPLIT) tma_store_4d(&p.tmY, out_tile + A_STAGE_BYTES, nbase + Cout, x0, y0, b);
+            tma_store_4d(&p.tmY32, out_tile, nbase, x0, y0, b);
+            if (SPLIT) tma_store_4d(&p.tmY32, out_tile + CHUNK32_BYTES, nbase + Cout, x0, y0, b);
             bulk_commit();
           }
         }
@@ -1170,7 +1233,7 @@ PFN_encodeTiled get_encode_fn() {
 }  // namespace
 
 void tc::encode_map_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                const uint32_t* box) {
+                const uint32_t* box, int swizzle_bytes) {
   cuuint64_t gdim[5];
   cuuint64_t gstr[5];
   cuuint32_t bx[5];
@@ -1188,7 +1251,8 @@ void tc::encode_map_f16(CUtensorMap* map, const void* base, int rank, const uint
   YB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base must be 16-byte aligned");
   CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                                gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     throw Error(YB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
@@ -1477,10 +1541,12 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   if (q.epi_tma) {
     // output / residual tile maps: same geometry as the accumulator tile, 64-channel boxes
     uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)q.tw, (uint32_t)q.th, 1};
+    uint32_t box32[4] = {32u, (uint32_t)q.tw, (uint32_t)q.th, 1};
     if (flat) {
       uint64_t dims[4] = {CoutP, (uint64_t)Wov, 1, 1};
       uint64_t ystr[3] = {(uint64_t)p.y_pix_stride * 2, (uint64_t)Wov * p.y_pix_stride * 2, (uint64_t)Wov * p.y_pix_stride * 2};
       encode_map_f16(&q.tmY, p.y, 4, dims, ystr, box);
+      encode_map_f16(&q.tmY32, p.y, 4, dims, ystr, box32, 64);
       if (p.residual) {
         uint64_t rstr[3] = {CoutP * 2, (uint64_t)Wov * CoutP * 2, (uint64_t)Wov * CoutP * 2};
         encode_map_f16(&q.tmR, p.residual, 4, dims, rstr, box);
@@ -1489,6 +1555,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
       uint64_t dims[4] = {CoutP, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.B};
       uint64_t ystr[3] = {(uint64_t)p.y_pix_stride * 2, (uint64_t)p.Wo * p.y_pix_stride * 2, (uint64_t)p.y_batch_stride * 2};
       encode_map_f16(&q.tmY, p.y, 4, dims, ystr, box);
+      encode_map_f16(&q.tmY32, p.y, 4, dims, ystr, box32, 64);
       if (p.residual) {
         uint64_t rstr[3] = {CoutP * 2, (uint64_t)p.Wo * CoutP * 2, (uint64_t)p.Ho * p.Wo * CoutP * 2};
         encode_map_f16(&q.tmR, p.residual, 4, dims, rstr, box);
@@ -1642,7 +1709,7 @@ TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std:
   ch->n_done = done_off;
   {
     const int npl = p0->split ? 2 : 1;
-    ch->smem_bytes = (size_t)chain_stages(p0->split != 0) * npl * (A_STAGE_BYTES + 128 * BLOCK_K * 2) + (size_t)2 * npl * A_STAGE_BYTES + 1024;
+    ch->smem_bytes = (size_t)chain_stages(p0->split != 0) * npl * (A_STAGE_BYTES + 128 * BLOCK_K * 2) + (size_t)2 * npl * CHUNK32_BYTES + 1024;
   }
   int dev = 0, sms = 148;
   YB_CHECK_CUDA(cudaGetDevice(&dev));
@@ -1668,7 +1735,7 @@ template <bool SPLIT>
 static void launch_chain_t(const TcChain* ch, cudaStream_t stream) {
   static PerDeviceOnce attr;
   if (attr.first())
-    YB_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024)));
   // Cooperative launch: the grid starts only when ALL its CTAs can be resident at once.  The tile dependencies make CTAs
   // wait for each other, so a partially scheduled grid (two chains from different streams sharing the SMs) could deadlock.
   cudaLaunchConfig_t cfg = {};
