@@ -546,22 +546,12 @@ struct NetBuilder {
           }
         }
       }
+      // candidates: two epilogue groups + three operand stages, or four groups + two stages (split precision); timed
+      // against the separately tuned launches
       TcChain* chain = nullptr;
+      bool use = false;
       {
         std::vector<const TcConvPlan*> cpl(cp.begin(), cp.end());
-        try {
-          chain = tc_chain_create(cpl, dep_a, dep_r);
-        } catch (const Error&) {
-          chain = nullptr;
-        }
-      }
-      bool use = false;
-      if (chain && !tc_chain_graph_ok(chain)) {   // cooperative launches cannot be captured here: no chains
-        tc_chain_destroy(chain);
-        chain = nullptr;
-      }
-      if (chain) {
-        float ms_chain = 0.f, ms_sep = 0.f;
         const auto lc_before = h->lc.n;
         cudaEvent_t e0, e1;
         YB_CHECK_CUDA(cudaEventCreate(&e0));
@@ -576,18 +566,48 @@ struct NetBuilder {
           YB_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
           return ms / 5.f;
         };
-        ms_chain = time_it([&]() { launch_tc_chain(chain, 0, nullptr); });
-        ms_sep = time_it([&]() {
-          for (size_t j = i; j < k; ++j) ops[j].fn(0);
-        });
+        float ms_chain = 1e30f;
+        const int force_groups = getenv("YB_CHAIN_GROUPS") ? atoi(getenv("YB_CHAIN_GROUPS")) : 0;
+        for (int groups = 2; groups <= 4; groups += 2) {
+          if (force_groups && groups != force_groups) continue;
+          TcChain* cand = nullptr;
+          try {
+            cand = tc_chain_create(cpl, dep_a, dep_r, groups);
+          } catch (const Error&) {
+            cand = nullptr;
+          }
+          if (cand && !tc_chain_graph_ok(cand)) {   // cooperative launches cannot be captured here: no chains
+            tc_chain_destroy(cand);
+            cand = nullptr;
+          }
+          if (!cand) continue;
+          const float ms = time_it([&]() { launch_tc_chain(cand, 0, nullptr); });
+          if (getenv("YB_CHAIN_STATS")) {
+            const std::string nm = ops[i].name.substr(0, ops[i].name.find(' ')) + " groups=" + std::to_string(groups);
+            tc_chain_print_stats(cand, nm.c_str());
+          }
+          if (getenv("YB_CHAIN_VERBOSE")) fprintf(stderr, "[yolact_b200]   %d epilogue groups: %.3f ms\n", groups, ms);
+          if (ms < ms_chain) {
+            if (chain) tc_chain_destroy(chain);
+            chain = cand;
+            ms_chain = ms;
+          } else {
+            tc_chain_destroy(cand);
+          }
+        }
+        if (chain) {
+          const float ms_sep = time_it([&]() {
+            for (size_t j = i; j < k; ++j) ops[j].fn(0);
+          });
+          use = (h->chain_mode == 2) || ms_chain < ms_sep;
+          if (getenv("YB_CHAIN_VERBOSE"))
+            fprintf(stderr, "[yolact_b200] chain %s .. %s (%zu layers): chain %.3f ms (%d groups), separate %.3f ms -> %s\n",
+                    ops[i].name.substr(0, ops[i].name.find(' ')).c_str(), ops[k - 1].name.substr(0, ops[k - 1].name.find(' ')).c_str(), n,
+                    ms_chain, tc_chain_groups(chain), ms_sep, use ? "chain" : "separate");
+        }
         h->lc.n = lc_before;   // (the separate launches counted themselves)
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
-        use = (h->chain_mode == 2) || ms_chain < ms_sep;
-        if (getenv("YB_CHAIN_VERBOSE"))
-          fprintf(stderr, "[yolact_b200] chain %s .. %s (%zu layers): chain %.3f ms, separate %.3f ms -> %s\n",
-                  ops[i].name.substr(0, ops[i].name.find(' ')).c_str(), ops[k - 1].name.substr(0, ops[k - 1].name.find(' ')).c_str(), n,
-                  ms_chain, ms_sep, use ? "chain" : "separate");
       }
       if (!use) {
         if (chain) tc_chain_destroy(chain);
@@ -601,7 +621,7 @@ struct NetBuilder {
       op.is_conv = true;
       op.lane = ops[i].lane;
       op.name = "chain x" + std::to_string(n) + " [" + ops[i].name.substr(0, ops[i].name.find(' ')) + " .. " +
-                ops[k - 1].name.substr(0, ops[k - 1].name.find(' ')) + "] tc BN=128/64 st=2 g=148 epi2";
+                ops[k - 1].name.substr(0, ops[k - 1].name.find(' ')) + "] tc BN=128/64 g=148 epi" + std::to_string(tc_chain_groups(chain));
       {
         double gf = 0.0;
         for (size_t j = i; j < k; ++j) {

@@ -77,10 +77,13 @@ void launch_tc_conv(const TcConvPlan* plan, cudaStream_t stream, LaunchCounter* 
 // dependency counters instead of kernel boundaries (tc_conv.cu, "chain kernel"); the plans must outlive the chain
 struct TcChain;
 bool tc_conv_plan_chainable(const TcConvPlan* plan);
-TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std::vector<int>& dep_a, const std::vector<int>& dep_r);
+TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std::vector<int>& dep_a, const std::vector<int>& dep_r,
+                         int groups = 2);   // epilogue groups per CTA: 2 (three split-precision stages) or 4 (two stages)
+int tc_chain_groups(const TcChain* chain);
 void tc_chain_destroy(TcChain* chain);
 int tc_chain_layers(const TcChain* chain);
 bool tc_chain_graph_ok(const TcChain* chain);
+void tc_chain_print_stats(TcChain* chain, const char* name);
 void launch_tc_chain(const TcChain* chain, cudaStream_t stream, LaunchCounter* lc);
 
 // ---- stem on tcgen05 (3-channel NCHW fp32 frame -> NHWC fp16) ---------------------------------------

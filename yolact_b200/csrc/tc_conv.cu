@@ -885,7 +885,9 @@ __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-__host__ __device__ constexpr int chain_stages(bool split) { return split ? 3 : 6; }
+// H epilogue groups of 4 warps; each group owns an 8 KB (x 2 planes) staging buffer: H = 2 leaves room for three
+// split-precision stages, H = 4 for two
+__host__ __device__ constexpr int chain_stages(bool split, int h) { return split ? (h == 4 ? 2 : 3) : 6; }
 __device__ __forceinline__ bool mbar_test_wait(uint32_t addr, uint32_t parity) {   // non-blocking
   uint32_t ok;
   asm volatile(
@@ -906,11 +908,16 @@ __device__ __forceinline__ int chain_first_unit(int cta, int ubase, int G) {
   return r < 0 ? r + G : r;
 }
 
-template <bool SPLIT>
-__global__ void __launch_bounds__(320)
-tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restrict__ info, int nl, int* __restrict__ done) {
+template <bool SPLIT, int H>
+__global__ void __launch_bounds__(64 + 128 * H)
+tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restrict__ info, int nl, int* __restrict__ done,
+                long long* __restrict__ stats) {
+  // stats (diagnostics, YB_CHAIN_STATS=1; null otherwise): per CTA 8 counters of SM cycles spent waiting --
+  // [0] producer: dependency counters, [1] producer: free ring slot, [2] MMA issuer: operands, [3] MMA issuer: free
+  // accumulator, [4] epilogue group 0: accumulator, [5] epilogue group 0: store completion before a signal, [6] whole kernel
+  const long long t_kernel0 = stats ? clock64() : 0;
+  long long w0 = 0, w1 = 0;
   constexpr int BN = 128;
-  constexpr int H = 2;
   constexpr int NPL = SPLIT ? 2 : 1;
   constexpr int B_PLANE_BYTES = BN * BLOCK_K * 2;
   constexpr int A_BYTES = NPL * A_STAGE_BYTES;
@@ -920,7 +927,7 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
   // buffer per epilogue group; two TMEM accumulator buffers.  The epilogue moves 32-channel chunks (8 KB tiles), which
   // leaves room for a THIRD split-precision stage (3 x 64 KB + 32 KB): the main loop is bound by the bytes a CTA can
   // keep in flight towards L2, not by the tensor pipe (profiles/ncu_tc_chain_r02.md)
-  constexpr int stages = chain_stages(SPLIT);
+  constexpr int stages = chain_stages(SPLIT, H);
 
   extern __shared__ uint8_t smem_dyn[];
   __shared__ uint64_t full_bar[MAX_STAGES];
@@ -981,7 +988,9 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
           uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           if (lane == 0) {
+            const long long t0 = stats ? clock64() : 0;
             mbar_wait(&empty_bar[s], (it & 1u) ^ 1u);
+            if (stats) w1 += clock64() - t0;
             mbar_expect_tx(&full_bar[s], tx_bytes);
 #pragma unroll
             for (int pl = 0; pl < NPL; ++pl)   // weights: constants, no dependency
@@ -1016,6 +1025,7 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
               tr = pr.target;
             }
             const int na = ib - ia + 1, nr = jb - ja + 1;
+            const long long tdep0 = stats ? clock64() : 0;
             __syncwarp();
             for (int i = lane; i < na + nr; i += 32) {
               const int* c = (i < na) ? ca + ia + i : cr + ja + (i - na);
@@ -1030,6 +1040,7 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
               }
             }
             __syncwarp();
+            if (stats) w0 += clock64() - tdep0;
             fence_proxy_async_all();   // the tiles were written through the async proxy (TMA stores) and are read through it
             ready = true;
           }
@@ -1043,6 +1054,10 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
         }
       }
     }
+    if (stats && lane == 0) {
+      stats[cta * 8 + 0] = w0;
+      stats[cta * 8 + 1] = w1;
+    }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
@@ -1055,13 +1070,17 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
         for (int u = chain_first_unit(cta, ubase, G); u < units; u += G, ++t) {
           const uint32_t acc = t & 1u;
           const uint32_t use = t >> 1;
+          long long t0 = stats ? clock64() : 0;
           mbar_wait(&tmem_empty_bar[acc], (use & 1u) ^ 1u);
+          if (stats) w1 += clock64() - t0;
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * (uint32_t)(NPL * BN);
           for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
             const uint32_t s = kbg % (uint32_t)stages;
             const uint32_t it = kbg / (uint32_t)stages;
+            t0 = stats ? clock64() : 0;
             mbar_wait(&full_bar[s], it & 1u);
+            if (stats) w0 += clock64() - t0;
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
             const uint32_t sb = sa + A_BYTES;
@@ -1085,24 +1104,26 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
           umma_commit(&tmem_full_bar[acc]);
         }
       }
+      if (stats) {
+        stats[cta * 8 + 2] = w0;
+        stats[cta * 8 + 3] = w1;
+      }
     }
   } else {
-    // ===================== epilogue: two groups of 4 warps, even / odd 64-channel chunks =====================
+    // ===================== epilogue: H groups of 4 warps, group g takes the 32-channel chunks g, g + H, ... =====================
     const int quad = warp & 3;
     const int hgrp = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const bool issuer = (warp == 2 + 4 * hgrp && lane == 0);
-    const uint32_t sw = (uint32_t)(row & 7);
     float* my_bias = sbias + hgrp * BN;
     uint8_t* out_tile = out_base + hgrp * BUF_BYTES;
-    auto group_sync = [&]() {
-      if (hgrp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-      else asm volatile("bar.sync 2, 128;" ::: "memory");
-    };
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(hgrp + 1) : "memory"); };
     // issuer only: counter to bump once this thread's outstanding stores (the previous tile's) have completed
     int* pending = nullptr;
     auto flush_pending = [&]() {
+      const long long t0 = stats ? clock64() : 0;
       bulk_wait_all();            // the stores have been performed, not just read out of shared memory
+      if (stats) w1 += clock64() - t0;
       fence_proxy_async_all();
       red_release_gpu_add(pending, 1);
       pending = nullptr;
@@ -1132,7 +1153,9 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
         // of this tile has been computed (by then the stores have long landed) -- safe, because a ready accumulator
         // means this tile depends on nothing that could be waiting for the deferred signal.
         if (issuer && pending && !mbar_test_wait(smem_u32(&tmem_full_bar[acc]), use & 1u)) flush_pending();
+        const long long tacc0 = stats ? clock64() : 0;
         mbar_wait(&tmem_full_bar[acc], use & 1u);
+        if (stats) w0 += clock64() - tacc0;
         tc_fence_after();
         group_sync();
         const int nchunks = (min(bn, Cout - n0) + 31) >> 5;   // 32-channel chunks: 4, or 2 for a 64-wide N tile
@@ -1195,6 +1218,11 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
     if (issuer) {
       if (pending) flush_pending();
       bulk_wait_read<0>();
+      if (stats && hgrp == 0) {
+        stats[cta * 8 + 4] = w0;
+        stats[cta * 8 + 5] = w1;
+        stats[cta * 8 + 6] = clock64() - t_kernel0;
+      }
     }
   }
 
@@ -1650,10 +1678,12 @@ static void launch_s(const TcConvPlan* plan, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------
 struct TcChain {
   int nl = 0, split = 0, grid = 0, n_done = 0;
+  int groups = 2;   // epilogue groups per CTA (2: three split stages, 4: two)
   size_t smem_bytes = 0;
   TcParams* d_layers = nullptr;
   ChainLayer* d_info = nullptr;
   int* d_done = nullptr;
+  long long* d_stats = nullptr;   // diagnostics (YB_CHAIN_STATS=1)
 };
 
 // a plan the chain kernel can run: its one tile shape (BN = 128, two epilogue groups, staged epilogue, two accumulator
@@ -1666,7 +1696,9 @@ bool tc_conv_plan_chainable(const TcConvPlan* pl) {
 
 // dep_a[i] / dep_r[i]: index (< i) of the plan that writes plan i's input / residual, -1 for a tensor that is complete
 // before the launch (or, for the residual, one whose completion the input dependency already implies)
-TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std::vector<int>& dep_a, const std::vector<int>& dep_r) {
+TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std::vector<int>& dep_a, const std::vector<int>& dep_r,
+                         int groups) {
+  YB_REQUIRE(groups == 2 || groups == 4, "tc_chain: 2 or 4 epilogue groups");
   YB_REQUIRE(!plans.empty() && plans.size() == dep_a.size() && plans.size() == dep_r.size(), "tc_chain: empty chain");
   const TcConvPlan* p0 = plans[0];
   std::vector<TcParams> lp;
@@ -1692,7 +1724,7 @@ TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std:
     c.tiles_x = pl->prm.tiles_x;
     c.tiles_y = pl->prm.tiles_y;
     c.done_off = done_off;
-    c.target = 2 * pl->prm.n_tiles;
+    c.target = groups * pl->prm.n_tiles;
     c.dep_a = dep_a[i];
     c.dep_r = dep_r[i];
     c.stride = pl->stride;
@@ -1706,10 +1738,12 @@ TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std:
   auto* ch = new TcChain();
   ch->nl = (int)plans.size();
   ch->split = p0->split;
+  ch->groups = groups;
   ch->n_done = done_off;
   {
     const int npl = p0->split ? 2 : 1;
-    ch->smem_bytes = (size_t)chain_stages(p0->split != 0) * npl * (A_STAGE_BYTES + 128 * BLOCK_K * 2) + (size_t)2 * npl * CHUNK32_BYTES + 1024;
+    ch->smem_bytes = (size_t)chain_stages(p0->split != 0, groups) * npl * (A_STAGE_BYTES + 128 * BLOCK_K * 2) +
+                     (size_t)groups * npl * CHUNK32_BYTES + 1024;
   }
   int dev = 0, sms = 148;
   YB_CHECK_CUDA(cudaGetDevice(&dev));
@@ -1727,20 +1761,22 @@ void tc_chain_destroy(TcChain* ch) {
   cudaFree(ch->d_layers);
   cudaFree(ch->d_info);
   cudaFree(ch->d_done);
+  cudaFree(ch->d_stats);
   delete ch;
 }
 int tc_chain_layers(const TcChain* ch) { return ch->nl; }
+int tc_chain_groups(const TcChain* ch) { return ch->groups; }
 
-template <bool SPLIT>
+template <bool SPLIT, int H>
 static void launch_chain_t(const TcChain* ch, cudaStream_t stream) {
   static PerDeviceOnce attr;
   if (attr.first())
-    YB_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024)));
+    YB_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<SPLIT, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024)));
   // Cooperative launch: the grid starts only when ALL its CTAs can be resident at once.  The tile dependencies make CTAs
   // wait for each other, so a partially scheduled grid (two chains from different streams sharing the SMs) could deadlock.
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)ch->grid);
-  cfg.blockDim = dim3(320);
+  cfg.blockDim = dim3(64 + 128 * H);
   cfg.dynamicSmemBytes = ch->smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
@@ -1748,8 +1784,34 @@ static void launch_chain_t(const TcChain* ch, cudaStream_t stream) {
   at[0].val.cooperative = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_chain_kernel<SPLIT>, (const TcParams*)ch->d_layers, (const ChainLayer*)ch->d_info,
-                                   ch->nl, ch->d_done));
+  YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_chain_kernel<SPLIT, H>, (const TcParams*)ch->d_layers, (const ChainLayer*)ch->d_info,
+                                   ch->nl, ch->d_done, ch->d_stats));
+}
+
+// diagnostics: one launch with the wait counters on, averaged over the CTAs -> stderr
+void tc_chain_print_stats(TcChain* ch, const char* name) {
+  const int G = ch->grid;
+  YB_CHECK_CUDA(cudaMalloc(&ch->d_stats, (size_t)G * 8 * sizeof(long long)));
+  YB_CHECK_CUDA(cudaMemset(ch->d_stats, 0, (size_t)G * 8 * sizeof(long long)));
+  launch_tc_chain(ch, 0, nullptr);
+  YB_CHECK_CUDA(cudaDeviceSynchronize());
+  std::vector<long long> hs((size_t)G * 8);
+  YB_CHECK_CUDA(cudaMemcpy(hs.data(), ch->d_stats, hs.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+  cudaFree(ch->d_stats);
+  ch->d_stats = nullptr;
+  double avg[8] = {}, mx[8] = {};
+  for (int c = 0; c < G; ++c)
+    for (int k = 0; k < 8; ++k) {
+      avg[k] += (double)hs[(size_t)c * 8 + k] / G;
+      mx[k] = std::max(mx[k], (double)hs[(size_t)c * 8 + k]);
+    }
+  const double tot = avg[6] > 0 ? avg[6] : 1.0;
+  fprintf(stderr,
+          "[yolact_b200] chain stats %s: kernel %.0f kcyc/CTA; share of it spent waiting (avg over CTAs / max): producer deps %.1f%% / %.1f%%, "
+          "producer ring slot %.1f%%, MMA operands %.1f%% / %.1f%%, MMA accumulator %.1f%%, epilogue accumulator %.1f%% / %.1f%%, epilogue store "
+          "completion %.1f%%\n",
+          name, tot / 1e3, 100 * avg[0] / tot, 100 * mx[0] / tot, 100 * avg[1] / tot, 100 * avg[2] / tot, 100 * mx[2] / tot, 100 * avg[3] / tot,
+          100 * avg[4] / tot, 100 * mx[4] / tot, 100 * avg[5] / tot);
 }
 
 // Can a chain launch be captured into a CUDA graph and replayed on this driver?  (One trial per process.)
@@ -1779,7 +1841,11 @@ bool tc_chain_graph_ok(const TcChain* ch) {
 }
 void launch_tc_chain(const TcChain* ch, cudaStream_t stream, LaunchCounter* lc) {
   YB_CHECK_CUDA(cudaMemsetAsync(ch->d_done, 0, (size_t)ch->n_done * sizeof(int), stream));   // (a memset node in the captured graph)
-  if (ch->split) launch_chain_t<true>(ch, stream); else launch_chain_t<false>(ch, stream);
+  if (ch->split) {
+    if (ch->groups == 4) launch_chain_t<true, 4>(ch, stream); else launch_chain_t<true, 2>(ch, stream);
+  } else {
+    if (ch->groups == 4) launch_chain_t<false, 4>(ch, stream); else launch_chain_t<false, 2>(ch, stream);
+  }
   YB_CHECK_LAUNCH();
   if (lc) lc->n++;
 }
