@@ -567,7 +567,9 @@ struct NetBuilder {
           return ms / 5.f;
         };
         float ms_chain = 1e30f;
-        const int force_groups = getenv("YB_CHAIN_GROUPS") ? atoi(getenv("YB_CHAIN_GROUPS")) : 0;
+        // measured (profiles/r2_call16_summary.txt): four groups + two stages lose to two groups + three stages on every
+        // chain of every config, so only YB_CHAIN_GROUPS=4 / =0 (time both) still builds the four-group variant
+        const int force_groups = getenv("YB_CHAIN_GROUPS") ? atoi(getenv("YB_CHAIN_GROUPS")) : 2;
         for (int groups = 2; groups <= 4; groups += 2) {
           if (force_groups && groups != force_groups) continue;
           TcChain* cand = nullptr;
