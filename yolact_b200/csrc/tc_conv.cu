@@ -215,12 +215,13 @@ __device__ __forceinline__ void epi_chunk(const uint32_t* r0, const uint32_t* r1
 
 // Chain-kernel variant: a 32-channel chunk of one accumulator row (r: the combined fp32 accumulator) into an 8 KB staging
 // tile of 128 rows x 64 bytes with the 64-byte TMA swizzle (16-byte unit index ^= (row >> 1) & 3); the lo plane's tile
-// follows the hi plane's.  The residual (has_res) was read from global memory into registers beforehand: rh / rl hold
-// this row's 32 channels of the hi / lo plane.
+// follows the hi plane's.  The residual always comes from global memory (res_g: this row's 32 channels, hi plane).
+// (Requesting the residual of all of a group's chunks up front, into registers, was measured SLOWER -- 4.01 vs 3.69 ms
+// for the 105-layer trunk chain, profiles/r2_call17_summary.txt: 168 registers, and the burst of loads delays the TMA.)
 constexpr int CHUNK32_BYTES = BLOCK_M * 32 * 2;   // 8 KB
 template <int ACT, bool RES_AFTER, bool SPLIT>
 __device__ __forceinline__ void epi_chunk32(const uint32_t* r, const float* sbias, uint8_t* out_tile, uint32_t row,
-                                            float out_scale, bool has_res, const uint4* rh, const uint4* rl) {
+                                            float out_scale, const __half* res_g, int res_lo_off) {
   const uint32_t sw = (row >> 1) & 3u;
 #pragma unroll
   for (int j8 = 0; j8 < 4; ++j8) {
@@ -234,8 +235,8 @@ __device__ __forceinline__ void epi_chunk32(const uint32_t* r, const float* sbia
       v[j] = SPLIT ? __fmaf_rn(a, out_scale, bb[j]) : a + bb[j];
       if (RES_AFTER) v[j] = act_t<ACT>(v[j]);
     }
-    if (has_res) {
-      const uint4 raw = rh[j8];
+    if (res_g) {
+      const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(res_g + j8 * 8));   // L2: other SMs wrote it during this launch
       const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -244,7 +245,7 @@ __device__ __forceinline__ void epi_chunk32(const uint32_t* r, const float* sbia
         v[2 * j + 1] += f.y;
       }
       if (SPLIT) {
-        const uint4 rawl = rl[j8];
+        const uint4 rawl = __ldcg(reinterpret_cast<const uint4*>(res_g + res_lo_off + j8 * 8));
         const __half2* l2 = reinterpret_cast<const __half2*>(&rawl);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -1168,30 +1169,8 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
             if (pending) flush_pending();
           }
         }
-        // the residual of ALL this group's chunks of the tile is requested at once, before the accumulator is read:
-        // the L2 round trips overlap the TMEM loads and the first chunk's arithmetic (L2 loads: inside a chain other
-        // SMs wrote the tensor during this launch)
-        constexpr int NCH = 4 / H;   // chunks of a 128-wide tile per group
-        uint4 rh[NCH][4], rl[NCH][4];
-        const bool has_res = res_direct && (x0 + row < Wo);
-        if (has_res) {
-          const __half* rrow = residual + (size_t)(x0 + row) * (size_t)(NPL * Cout) + n0;
-#pragma unroll
-          for (int ci = 0; ci < NCH; ++ci) {
-            const int c = hgrp + ci * H;
-            if (c < nchunks) {
-#pragma unroll
-              for (int j8 = 0; j8 < 4; ++j8) {
-                rh[ci][j8] = __ldcg(reinterpret_cast<const uint4*>(rrow + c * 32 + j8 * 8));
-                if (SPLIT) rl[ci][j8] = __ldcg(reinterpret_cast<const uint4*>(rrow + Cout + c * 32 + j8 * 8));
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int ci = 0; ci < NCH; ++ci) {
-          const int c = hgrp + ci * H;
-          if (c >= nchunks) break;
+#pragma unroll 1
+        for (int c = hgrp; c < nchunks; c += H, ++g) {
           if (g >= 1u) {
             if (issuer) bulk_wait_read<0>();   // the store that last used this group's staging tile has read it
             group_sync();
@@ -1209,15 +1188,17 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
           }
           const int nbase = n0 + c * 32;
           const float* sb = my_bias + c * 32;
+          const __half* rg = nullptr;
+          if (res_direct && x0 + row < Wo) rg = residual + (size_t)(x0 + row) * (size_t)(NPL * Cout) + nbase;
           switch (act) {
-            case ACT_RELU: epi_chunk32<ACT_RELU, false, SPLIT>(r, sb, out_tile, (uint32_t)row, out_scale, has_res, rh[ci], rl[ci]); break;
+            case ACT_RELU: epi_chunk32<ACT_RELU, false, SPLIT>(r, sb, out_tile, (uint32_t)row, out_scale, rg, Cout); break;
             case ACT_LEAKY:
               if (raa)
-                epi_chunk32<ACT_LEAKY, true, SPLIT>(r, sb, out_tile, (uint32_t)row, out_scale, has_res, rh[ci], rl[ci]);
+                epi_chunk32<ACT_LEAKY, true, SPLIT>(r, sb, out_tile, (uint32_t)row, out_scale, rg, Cout);
               else
-                epi_chunk32<ACT_LEAKY, false, SPLIT>(r, sb, out_tile, (uint32_t)row, out_scale, has_res, rh[ci], rl[ci]);
+                epi_chunk32<ACT_LEAKY, false, SPLIT>(r, sb, out_tile, (uint32_t)row, out_scale, rg, Cout);
               break;
-            default: epi_chunk32<ACT_NONE, false, SPLIT>(r, sb, out_tile, (uint32_t)row, out_scale, has_res, rh[ci], rl[ci]); break;
+            default: epi_chunk32<ACT_NONE, false, SPLIT>(r, sb, out_tile, (uint32_t)row, out_scale, rg, Cout); break;
           }
           fence_proxy_async();
           if (issuer && pending) flush_pending();   // deferred signal of the previous tile
@@ -1229,7 +1210,6 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
             if (SPLIT) tma_store_4d(&p.tmY32, out_tile + CHUNK32_BYTES, nbase + Cout, x0, y0, b);
             bulk_commit();
           }
-          ++g;
         }
         if (issuer) {
           if (nchunks > hgrp) pending = done + done_off + u / n_tiles;
