@@ -27,12 +27,12 @@ CASES = [
 ]
 
 
-def _run(cfg_name, B, H, W, chain, monkeypatch):
+def _run(cfg_name, B, H, W, chain, monkeypatch, precision="f16x3"):
     monkeypatch.setenv("YB_CHAIN", str(chain))
     monkeypatch.setenv("YB_SK", "0")
     cfg = cfg_for(cfg_name)
     yolact_b200.cfg.replace(cfg.copy())
-    net = yolact_b200.Yolact(cfg, precision="f16x3")
+    net = yolact_b200.Yolact(cfg, precision=precision)
     net.load_state_dict(deterministic_state_dict(net.state_dict(), 7))
     net.train()
     x = deterministic_input(B, H, W, seed=11).cuda()
@@ -47,14 +47,15 @@ def _run(cfg_name, B, H, W, chain, monkeypatch):
     return out, names
 
 
+@pytest.mark.parametrize("precision", ["f16x3", "f16tc"])
 @pytest.mark.parametrize("cfg_name,B,H,W", CASES)
-def test_chain_identical_to_separate_launches(cfg_name, B, H, W, monkeypatch):
-    sep, names_sep = _run(cfg_name, B, H, W, 0, monkeypatch)
-    ch, names_ch = _run(cfg_name, B, H, W, 2, monkeypatch)
+def test_chain_identical_to_separate_launches(cfg_name, B, H, W, precision, monkeypatch):
+    sep, names_sep = _run(cfg_name, B, H, W, 0, monkeypatch, precision)
+    ch, names_ch = _run(cfg_name, B, H, W, 2, monkeypatch, precision)
     assert not any(n.startswith("chain") for n in names_sep)
     chains = [n for n in names_ch if n.startswith("chain")]
     assert chains, "YB_CHAIN=2 formed no chain"
-    print(cfg_name, B, H, W, "chains:", [c.split(" [")[0] for c in chains], "ops", len(names_sep), "->", len(names_ch))
+    print(cfg_name, B, H, W, precision, "chains:", [c.split(" [")[0] for c in chains], "ops", len(names_sep), "->", len(names_ch))
     for k in sep:
         assert np.isfinite(ch[k]).all()
         assert np.array_equal(sep[k], ch[k]), (k, float(np.abs(sep[k] - ch[k]).max()))

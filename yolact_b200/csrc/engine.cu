@@ -495,12 +495,12 @@ struct NetBuilder {
     auto chain_plan = [&](const Op& op) -> TcConvPlan* {
       if (!op.has_prob) return nullptr;
       const ConvProblem& q = op.prob;
-      if (!(q.split && q.KH == q.KW && (q.KH == 1 || q.KH == 3) && (q.stride == 1 || q.stride == 2) && q.Cout % 64 == 0 &&
-            !q.y_f32 && q.nseg == 0 && q.y_pix_stride == 2 * q.Cout && q.y_batch_stride == (int64_t)q.Ho * q.Wo * q.y_pix_stride))
+      if (!(q.KH == q.KW && (q.KH == 1 || q.KH == 3) && (q.stride == 1 || q.stride == 2) && q.Cout % 64 == 0 && !q.y_f32 &&
+            q.nseg == 0 && q.y_pix_stride == (q.split ? 2 : 1) * q.Cout && q.y_batch_stride == (int64_t)q.Ho * q.Wo * q.y_pix_stride))
         return nullptr;
       TcConvPlan* pl = nullptr;
       try {
-        pl = tc_conv_plan_create(q, op.w_tc, (q.Cout % 128 == 0) ? 128 : 64, 2, 148, 0, 2, 0, 0);
+        pl = tc_conv_plan_create(q, op.w_tc, (q.Cout % 128 == 0) ? 128 : 64, 2, 148, 0, 2, 0, 0, /*chain=*/1);
       } catch (const Error&) {
         return nullptr;
       }

@@ -59,7 +59,8 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
                                 int stages_override = 0, int grid_override = 0, int pair_override = 0,
                                 int epi_override = 0,    // epi_override == 2: two 4-warp epilogue groups (320 threads)
                                 int pdl_override = 0,    // > 0: plan sized for 2 CTAs/SM + programmatic dependent launch
-                                int sk_override = 0);    // > 0: stream-K (needs tc_conv_plan_set_sk_workspace before launch)
+                                int sk_override = 0,     // > 0: stream-K (needs tc_conv_plan_set_sk_workspace before launch)
+                                int chain_override = 0); // > 0: a chain-kernel plan (residual read from global memory in every mode)
 int tc_conv_plan_sk(const TcConvPlan* plan);
 size_t tc_conv_sk_workspace_bytes();
 void tc_conv_plan_set_sk_workspace(TcConvPlan* plan, void* ws);

@@ -1314,7 +1314,8 @@ bool tc_conv_supported(const ConvProblem& p) {
 }
 
 TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override, int stages_override,
-                                int grid_override, int pair_override, int epi_override, int pdl_override, int sk_override) {
+                                int grid_override, int pair_override, int epi_override, int pdl_override, int sk_override,
+                                int chain_override) {
   YB_REQUIRE(tc_conv_supported(p), "tc_conv: unsupported problem");
   YB_REQUIRE(p.Ho == (p.H + 2 * p.pad - p.KH) / p.stride + 1, "tc_conv: bad Ho");
   YB_REQUIRE(p.Wo == (p.W + 2 * p.pad - p.KW) / p.stride + 1, "tc_conv: bad Wo");
@@ -1477,7 +1478,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   // (split: one buffer of two tiles per group)
   const int epi_tiles = split ? 2 * plan->epi_groups : 2;
   const int out_bytes = std::max(epi_tiles * A_STAGE_BYTES, plan->epi_groups == 2 ? 36 * 1024 : 2 * A_STAGE_BYTES);
-  q.res_direct = (split && plan->epi_groups == 2 && p.residual && flat && q.epi_tma) ? 1 : 0;
+  q.res_direct = ((split || chain_override > 0) && plan->epi_groups == 2 && p.residual && flat && q.epi_tma) ? 1 : 0;
   const int res_bytes = (q.epi_tma && p.residual && !q.res_direct) ? epi_tiles * A_STAGE_BYTES : 0;
   int stages = std::min(MAX_STAGES, ((pdlf ? 108 : (split ? 221 : 200)) * 1024 - out_bytes - res_bytes) / stage_bytes);
   if (stages < 1 && pdlf) {   // does not fit in half an SM: an ordinary plan
