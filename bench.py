@@ -569,7 +569,7 @@ def main():
         pass
     passes = 3 if args.precision == "f16x3" else 1
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "tc_conv_kernel (all conv launches of one step)",
+                "traffic": traffic, "kernel": "tc_chain_kernel + tc_conv_kernel (all conv launches of one step)",
                 "ms_conv_stack_per_step": ms_conv / args.steps, "peak_source": peak_src,
                 "algorithmic_gflop_per_step": gflop * B,
                 "mma_passes": passes, "tensor_pipe_tflops_issued": achieved * passes,
