@@ -293,6 +293,11 @@ YB_API int yb_last_forward_ms(yb_handle* h, float* total_ms, float* conv_ms);
 YB_API int yb_last_forward_profile(yb_handle* h, char* buf, int64_t cap);
 /* Enable/disable CUDA-graph replay of yb_forward (default on). */
 YB_API int yb_set_graphs(yb_handle* h, int enable);
+/* Host-only mirror of the chain kernel's dependency arithmetic (csrc/tc_conv.cu; no device needed): for a k x k / stride /
+ * pad convolution over a B x Hin x Win tensor written by a flattened (1x1 stride 1) or 2-D tiled producer layer, the
+ * tilings of both layers and the inclusive range of producer M tiles that consumer M tile `m` waits for.
+ * out[14] = consumer {flat, tw, th, tiles_x, tiles_y, m_tiles}, producer {same six}, first, last. */
+YB_API int yb_debug_chain_deps(int B, int Hin, int Win, int k, int stride, int pad, int producer_flat, int m, int32_t* out);
 
 #ifdef __cplusplus
 }

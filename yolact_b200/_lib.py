@@ -92,6 +92,7 @@ SIGNATURES = {
     "yb_set_profiling": (c_int, [c_void_p, c_int]),
     "yb_last_forward_ms": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float)]),
     "yb_last_forward_profile": (c_int, [c_void_p, c_char_p, c_int64]),
+    "yb_debug_chain_deps": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int32)]),
     "yb_set_graphs": (c_int, [c_void_p, c_int]),
 }
 

@@ -837,4 +837,10 @@ int yb_set_graphs(yb_handle* h, int enable) {
   YB_API_END
 }
 
+int yb_debug_chain_deps(int B, int Hin, int Win, int k, int stride, int pad, int producer_flat, int m, int32_t* out) {
+  YB_API_BEGIN
+  yb::tc_chain_debug_deps(B, Hin, Win, k, stride, pad, producer_flat, m, out);
+  YB_API_END
+}
+
 }  // extern "C"

@@ -85,6 +85,7 @@ void tc_chain_destroy(TcChain* chain);
 int tc_chain_layers(const TcChain* chain);
 bool tc_chain_graph_ok(const TcChain* chain);
 void tc_chain_print_stats(TcChain* chain, const char* name);
+void tc_chain_debug_deps(int B, int Hin, int Win, int k, int stride, int pad, int producer_flat, int m, int32_t* out);
 void launch_tc_chain(const TcChain* chain, cudaStream_t stream, LaunchCounter* lc);
 
 // ---- stem on tcgen05 (3-channel NCHW fp32 frame -> NHWC fp16) ---------------------------------------

@@ -23,6 +23,7 @@
 //   tile, so the bytes a CTA pulls from L2 per k-block drop from 16 KB + BN*128 to 16 KB + BN*64 -- the conv
 //   stack at batch 8 is L2->SM bandwidth bound, not tensor bound.  The even CTA issues
 //   the MMAs; both CTAs' TMA loads signal ITS full barrier; tcgen05.commit multicasts to both CTAs' barriers.
+#include <atomic>
 #include <vector>
 #include "tc_common.cuh"
 
@@ -864,8 +865,35 @@ struct ChainLayer {
   int stride, pad, kh;     // output row y reads input rows [y * stride - pad, y * stride - pad + kh)
 };
 
+// The dependency arithmetic, shared by the kernel and a host mirror (yb_debug_chain_deps: CPU property tests).
+// Global output rows [r0, r1] of M tile m of layer ci
+__host__ __device__ __forceinline__ void chain_rows_of_tile(const ChainLayer& ci, int m, int& r0, int& r1) {
+  if (ci.flat) {
+    const int lo = m * ci.tw;
+    int hi = lo + ci.tw;
+    if (hi > ci.rows * ci.W) hi = ci.rows * ci.W;
+    r0 = lo / ci.W;
+    r1 = (hi - 1) / ci.W;
+  } else {
+    const int ty = (m / ci.tiles_x) % ci.tiles_y, b = m / (ci.tiles_x * ci.tiles_y);
+    int y1 = ty * ci.th + ci.th;
+    if (y1 > ci.H) y1 = ci.H;
+    r0 = b * ci.H + ty * ci.th;
+    r1 = b * ci.H + y1 - 1;
+  }
+}
+// Rows [ra, rb] of the input tensor (written by layer pa: its image height differs under a stride) that output rows
+// [r0, r1] of layer ci read
+__host__ __device__ __forceinline__ void chain_input_rows(const ChainLayer& ci, const ChainLayer& pa, int r0, int r1, int& ra, int& rb) {
+  const int b0 = r0 / ci.H, y0 = r0 - b0 * ci.H, b1 = r1 / ci.H, y1 = r1 - b1 * ci.H;
+  int lo = y0 * ci.stride - ci.pad, hi = y1 * ci.stride - ci.pad + ci.kh - 1;
+  if (lo < 0) lo = 0;
+  if (hi > pa.H - 1) hi = pa.H - 1;
+  ra = b0 * pa.H + lo;
+  rb = b1 * pa.H + hi;
+}
 // M tiles of layer `pi` that overlap its global rows [ra, rb]
-__device__ __forceinline__ void chain_tiles_of_rows(const ChainLayer& pi, int ra, int rb, int& ia, int& ib) {
+__host__ __device__ __forceinline__ void chain_tiles_of_rows(const ChainLayer& pi, int ra, int rb, int& ia, int& ib) {
   if (pi.flat) {
     ia = (ra * pi.W) / pi.tw;
     ib = ((rb + 1) * pi.W - 1) / pi.tw;
@@ -1001,21 +1029,13 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
           if (!ready) {
             // global output rows [r0, r1] of this tile
             int r0, r1;
-            if (ci.flat) {
-              const int lo = tc_.x0, hi = min(tc_.x0 + ci.tw, ci.rows * ci.W) - 1;
-              r0 = lo / ci.W;
-              r1 = hi / ci.W;
-            } else {
-              r0 = tc_.b * ci.H + tc_.y0;
-              r1 = tc_.b * ci.H + min(tc_.y0 + ci.th, ci.H) - 1;
-            }
+            chain_rows_of_tile(ci, u / p.n_tiles, r0, r1);
             int ia = 0, ib = -1, ja = 0, jb = -1, ta = 0, tr = 0;
             const int *ca = done, *cr = done;
             if (ci.dep_a >= 0) {   // input rows, in the producer's row numbering (its image height differs under a stride)
               const ChainLayer pa = info[ci.dep_a];
-              const int b0 = r0 / ci.H, y0 = r0 - b0 * ci.H, b1 = r1 / ci.H, y1 = r1 - b1 * ci.H;
-              const int ra = b0 * pa.H + max(y0 * ci.stride - ci.pad, 0);
-              const int rb = b1 * pa.H + min(y1 * ci.stride - ci.pad + ci.kh - 1, pa.H - 1);
+              int ra, rb;
+              chain_input_rows(ci, pa, r0, r1, ra, rb);
               chain_tiles_of_rows(pa, ra, rb, ia, ib);
               ca = done + pa.done_off;
               ta = pa.target;
@@ -1313,6 +1333,62 @@ bool tc_conv_supported(const ConvProblem& p) {
   return true;
 }
 
+// spatial tile tw x th <= 128 accumulator rows with the best fill (ties: the wider tile)
+static void choose_tile(int Wov, int Hov, int& best_tw, int& best_th) {
+  best_tw = 1;
+  best_th = 1;
+  double best_eff = -1.0;
+  for (int tw = 1; tw <= std::min(Wov, 128); ++tw) {
+    int th = std::min(Hov, 128 / tw);
+    if (th < 1) continue;
+    if (tw > 256 || th > 256) continue;
+    long long tiles = (long long)ceil_div(Wov, tw) * ceil_div(Hov, th);
+    double eff = (double)Wov * Hov / ((double)tiles * 128.0);
+    if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && tw > best_tw)) {
+      best_eff = eff;
+      best_tw = tw;
+      best_th = th;
+    }
+  }
+}
+
+// Host mirror of the chain kernel's dependency arithmetic for ONE consumer layer (a k x k conv, stride, pad, on a
+// B x Hin x Win input written by a producer layer that is flattened (1x1 stride 1) or not): the tilings both layers
+// would get and, for consumer M tile m, the inclusive range of producer M tiles the kernel would wait for.
+// out[0..5] = consumer flat, tw, th, tiles_x, tiles_y, m_tiles; out[6..11] = producer flat, tw, th, tiles_x, tiles_y,
+// m_tiles; out[12], out[13] = first, last producer tile.  No device needed.
+void tc_chain_debug_deps(int B, int Hin, int Win, int k, int stride, int pad, int producer_flat, int m, int32_t* out) {
+  YB_REQUIRE(B >= 1 && Hin >= 1 && Win >= 1 && (k == 1 || k == 3) && (stride == 1 || stride == 2) && pad >= 0 && out,
+             "chain_debug_deps: bad argument");
+  const int Ho = (Hin + 2 * pad - k) / stride + 1, Wo = (Win + 2 * pad - k) / stride + 1;
+  YB_REQUIRE(Ho >= 1 && Wo >= 1, "chain_debug_deps: empty output");
+  auto layer = [&](int flat, int H, int W, int s, int p, int kh) {
+    ChainLayer c = {};
+    c.flat = flat;
+    c.W = W;
+    c.H = H;
+    c.rows = B * H;
+    const int Wov = flat ? B * H * W : W, Hov = flat ? 1 : H;
+    choose_tile(Wov, Hov, c.tw, c.th);
+    c.tiles_x = ceil_div(Wov, c.tw);
+    c.tiles_y = ceil_div(Hov, c.th);
+    c.stride = s;
+    c.pad = p;
+    c.kh = kh;
+    return c;
+  };
+  const ChainLayer ci = layer((k == 1 && stride == 1 && pad == 0) ? 1 : 0, Ho, Wo, stride, pad, k);
+  const ChainLayer pa = layer(producer_flat ? 1 : 0, Hin, Win, 1, 0, 1);
+  const int cm = ci.tiles_x * ci.tiles_y * (ci.flat ? 1 : B), pm = pa.tiles_x * pa.tiles_y * (pa.flat ? 1 : B);
+  YB_REQUIRE(m >= 0 && m < cm, "chain_debug_deps: tile out of range");
+  int r0, r1, ra, rb, ia, ib;
+  chain_rows_of_tile(ci, m, r0, r1);
+  chain_input_rows(ci, pa, r0, r1, ra, rb);
+  chain_tiles_of_rows(pa, ra, rb, ia, ib);
+  const int32_t v[14] = {ci.flat, ci.tw, ci.th, ci.tiles_x, ci.tiles_y, cm, pa.flat, pa.tw, pa.th, pa.tiles_x, pa.tiles_y, pm, ia, ib};
+  for (int i = 0; i < 14; ++i) out[i] = v[i];
+}
+
 TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, int bn_override, int stages_override,
                                 int grid_override, int pair_override, int epi_override, int pdl_override, int sk_override,
                                 int chain_override) {
@@ -1344,19 +1420,7 @@ TcConvPlan* tc_conv_plan_create(const ConvProblem& p, const __half* w_packed, in
   }
   // ---- spatial tile (tw x th <= 128) with the best fill
   int best_tw = 1, best_th = 1;
-  double best_eff = -1.0;
-  for (int tw = 1; tw <= std::min(Wov, 128); ++tw) {
-    int th = std::min(Hov, 128 / tw);
-    if (th < 1) continue;
-    if (tw > 256 || th > 256) continue;
-    long long tiles = (long long)ceil_div(Wov, tw) * ceil_div(Hov, th);
-    double eff = (double)Wov * Hov / ((double)tiles * 128.0);
-    if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && tw > best_tw)) {
-      best_eff = eff;
-      best_tw = tw;
-      best_th = th;
-    }
-  }
+  choose_tile(Wov, Hov, best_tw, best_th);
   plan->flat = flat ? 1 : 0;
   plan->B = p.B;
   plan->Ho = p.Ho;
@@ -1752,11 +1816,16 @@ TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std:
   YB_CHECK_CUDA(cudaGetDevice(&dev));
   YB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   ch->grid = std::min(sms, ubase);   // one CTA per SM (the shared memory of a CTA sees to that): all co-resident
-  YB_CHECK_CUDA(cudaMalloc(&ch->d_layers, lp.size() * sizeof(TcParams)));
-  YB_CHECK_CUDA(cudaMalloc(&ch->d_info, li.size() * sizeof(ChainLayer)));
-  YB_CHECK_CUDA(cudaMalloc(&ch->d_done, (size_t)done_off * sizeof(int)));
-  YB_CHECK_CUDA(cudaMemcpy(ch->d_layers, lp.data(), lp.size() * sizeof(TcParams), cudaMemcpyHostToDevice));
-  YB_CHECK_CUDA(cudaMemcpy(ch->d_info, li.data(), li.size() * sizeof(ChainLayer), cudaMemcpyHostToDevice));
+  try {
+    YB_CHECK_CUDA(cudaMalloc(&ch->d_layers, lp.size() * sizeof(TcParams)));
+    YB_CHECK_CUDA(cudaMalloc(&ch->d_info, li.size() * sizeof(ChainLayer)));
+    YB_CHECK_CUDA(cudaMalloc(&ch->d_done, (size_t)done_off * sizeof(int)));
+    YB_CHECK_CUDA(cudaMemcpy(ch->d_layers, lp.data(), lp.size() * sizeof(TcParams), cudaMemcpyHostToDevice));
+    YB_CHECK_CUDA(cudaMemcpy(ch->d_info, li.data(), li.size() * sizeof(ChainLayer), cudaMemcpyHostToDevice));
+  } catch (...) {
+    tc_chain_destroy(ch);
+    throw;
+  }
   return ch;
 }
 void tc_chain_destroy(TcChain* ch) {
@@ -1820,8 +1889,8 @@ void tc_chain_print_stats(TcChain* ch, const char* name) {
 
 // Can a chain launch be captured into a CUDA graph and replayed on this driver?  (One trial per process.)
 bool tc_chain_graph_ok(const TcChain* ch) {
-  static int cached = -1;
-  if (cached >= 0) return cached != 0;
+  static std::atomic<int> cached{-1};   // (executors of different handles may be built from different threads)
+  if (cached.load() >= 0) return cached.load() != 0;
   bool ok = false;
   cudaStream_t s = nullptr;
   cudaGraph_t g = nullptr;
@@ -1840,7 +1909,7 @@ bool tc_chain_graph_ok(const TcChain* ch) {
   if (g) cudaGraphDestroy(g);
   if (s) cudaStreamDestroy(s);
   cudaGetLastError();
-  cached = ok ? 1 : 0;
+  cached.store(ok ? 1 : 0);
   return ok;
 }
 void launch_tc_chain(const TcChain* ch, cudaStream_t stream, LaunchCounter* lc) {
