@@ -508,21 +508,9 @@ struct NetBuilder {
         tc_conv_plan_destroy(pl);
         return nullptr;
       }
-      // experiment (YB_CHAIN_BN64=1): a layer with fewer than two rounds of 128-wide tiles gets 64-wide ones, so that the
-      // tiles its consumers wait for were written two rounds earlier instead of one
-      if (getenv("YB_CHAIN_BN64") && atoi(getenv("YB_CHAIN_BN64")) && tc_conv_plan_bn(pl) == 128 && tc_conv_plan_units(pl) < 2 * 148) {
-        TcConvPlan* p64 = nullptr;
-        try {
-          p64 = tc_conv_plan_create(q, op.w_tc, 64, 2, 148, 0, 2, 0, 0, /*chain=*/1);
-        } catch (const Error&) {
-          p64 = nullptr;
-        }
-        if (p64 && tc_conv_plan_chainable(p64)) {
-          tc_conv_plan_destroy(pl);
-          return p64;
-        }
-        if (p64) tc_conv_plan_destroy(p64);
-      }
+      // (64-wide tiles for the layers with fewer than two rounds of 128-wide ones -- so that the tiles their consumers
+      // wait for were written two rounds earlier -- halve the dependency waits but lose overall: 4.35 vs 3.74 ms for the
+      // trunk chain, profiles/r2_call19_summary.txt)
       return pl;
     };
     size_t i = begin;

@@ -81,7 +81,6 @@ bool tc_conv_plan_chainable(const TcConvPlan* plan);
 TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std::vector<int>& dep_a, const std::vector<int>& dep_r,
                          int groups = 2);   // epilogue groups per CTA: 2 (three split-precision stages) or 4 (two stages)
 int tc_chain_groups(const TcChain* chain);
-int tc_conv_plan_units(const TcConvPlan* plan);   // work units (M tiles x N tiles) of a single-CTA plan
 void tc_chain_destroy(TcChain* chain);
 int tc_chain_layers(const TcChain* chain);
 bool tc_chain_graph_ok(const TcChain* chain);

@@ -941,8 +941,7 @@ __device__ __forceinline__ int chain_first_unit(int cta, int ubase, int G) {
 template <bool SPLIT, int H>
 __global__ void __launch_bounds__(64 + 128 * H)
 tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restrict__ info, int nl, int* __restrict__ done,
-                long long* __restrict__ stats, int flags) {
-  // flags bit 0: read the next tile's dependency counters ahead of time (YB_CHAIN_PREPOLL, default on)
+                long long* __restrict__ stats) {
   // stats (diagnostics, YB_CHAIN_STATS=1; null otherwise): per CTA 8 counters of SM cycles spent waiting --
   // [0] producer: dependency counters, [1] producer: free ring slot, [2] MMA issuer: operands, [3] MMA issuer: free
   // accumulator, [4] epilogue group 0: accumulator, [5] epilogue group 0: store completion before a signal, [6] whole kernel
@@ -1040,32 +1039,12 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
         }
         return na + nr;
       };
-      bool pre_ok = false;   // the NEXT tile's counters were read ahead and all of them had reached their target
+      // (Reading the NEXT tile's counters ahead of time, so that a satisfied check costs no L2 round trip in front of the
+      // tile, was tried: the producer's waiting share fell from 30 % to 18 %, the kernel time did not move -- 3.745 vs
+      // 3.740 ms, profiles/r2_call19_summary.txt: the MMA issuer waits for the operands themselves.  Removed.)
       for (int u = chain_first_unit(cta, ci.ubase, G); u < ci.units; u += G) {
         const TileCoord tc_ = decode_unit<false>(p, u, 0, bn);
         bool ready = nodeps;
-        if (!nodeps && pre_ok) {
-          fence_proxy_async_all();
-          ready = true;
-        }
-        pre_ok = false;
-        // Look ahead: a satisfied dependency check still costs an L2 round trip (~0.5 us) in front of every tile's first
-        // activation load -- a 1x1 layer with a short K has 4-5 such tiles per CTA.  The counters of this CTA's next tile
-        // of the layer are read NOW (the loads are in flight while this tile's k-blocks are issued) and looked at after.
-        int pv = 0, pt = 0;
-        bool have_pre = false;
-        if ((flags & 1) && !nodeps && u + G < ci.units) {
-          const int* c = done;
-          int tgt = 0;
-          const int n = dep_of((u + G) / p.n_tiles, lane, c, tgt);
-          if (n <= 32) {
-            have_pre = true;
-            if (lane < n) {
-              pv = ld_acquire_gpu(c);
-              pt = tgt;
-            }
-          }
-        }
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)stages;
           const uint32_t it = kbg / (uint32_t)stages;
@@ -1112,7 +1091,6 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
               tma_load_4d(sa + pl * A_STAGE_BYTES, ma, &full_bar[s], kc * BLOCK_K + pl * p.cin, ax, ay, tc_.b);
           }
         }
-        if (have_pre) pre_ok = __all_sync(0xffffffffu, pv >= pt) != 0;
       }
     }
     if (stats && lane == 0) {
@@ -1785,7 +1763,6 @@ static void launch_s(const TcConvPlan* plan, cudaStream_t stream) {
 struct TcChain {
   int nl = 0, split = 0, grid = 0, n_done = 0;
   int groups = 2;   // epilogue groups per CTA (2: three split stages, 4: two)
-  int flags = 1;    // kernel flags (bit 0: dependency look-ahead)
   size_t smem_bytes = 0;
   TcParams* d_layers = nullptr;
   ChainLayer* d_info = nullptr;
@@ -1846,7 +1823,6 @@ TcChain* tc_chain_create(const std::vector<const TcConvPlan*>& plans, const std:
   ch->nl = (int)plans.size();
   ch->split = p0->split;
   ch->groups = groups;
-  if (const char* pp = getenv("YB_CHAIN_PREPOLL")) ch->flags = (atoi(pp) != 0) ? 1 : 0;
   ch->n_done = done_off;
   {
     const int npl = p0->split ? 2 : 1;
@@ -1879,7 +1855,6 @@ void tc_chain_destroy(TcChain* ch) {
 }
 int tc_chain_layers(const TcChain* ch) { return ch->nl; }
 int tc_chain_groups(const TcChain* ch) { return ch->groups; }
-int tc_conv_plan_units(const TcConvPlan* plan) { return plan->prm.m_tiles * plan->prm.n_tiles; }
 
 template <bool SPLIT, int H>
 static void launch_chain_t(const TcChain* ch, cudaStream_t stream) {
@@ -1900,7 +1875,7 @@ static void launch_chain_t(const TcChain* ch, cudaStream_t stream) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_chain_kernel<SPLIT, H>, (const TcParams*)ch->d_layers, (const ChainLayer*)ch->d_info,
-                                   ch->nl, ch->d_done, ch->d_stats, ch->flags));
+                                   ch->nl, ch->d_done, ch->d_stats));
 }
 
 // diagnostics: one launch with the wait counters on, averaged over the CTAs -> stderr
