@@ -23,6 +23,9 @@
 //   tile, so the bytes a CTA pulls from L2 per k-block drop from 16 KB + BN*128 to 16 KB + BN*64 -- the conv
 //   stack at batch 8 is L2->SM bandwidth bound, not tensor bound.  The even CTA issues
 //   the MMAs; both CTAs' TMA loads signal ITS full barrier; tcgen05.commit multicasts to both CTAs' barriers.
+// Chain kernel (tc_chain_kernel, further down): a run of consecutive layers -- the whole ResNet trunk after the
+//   max-pool -- in ONE persistent cooperative launch; the layers' parameter blocks live in global memory, the work
+//   units of all layers are dealt round-robin to the CTAs, dependencies are tracked per M tile with counters.
 #include <atomic>
 #include <vector>
 #include "tc_common.cuh"
