@@ -151,3 +151,12 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_graft_entry_build_check_passes():
+    """The driver's "does it build" entry point: (re)builds the library if a source is newer, loads it, checks the ABI
+    version against the header and imports the oracle -- must hold on a machine without a GPU."""
+    import __graft_entry__ as g
+    assert g.build() is None
+    src = open(os.path.join(ROOT, "include", "yolact_b200.h")).read()
+    assert int(re.search(r"#define\s+YB_ABI_VERSION\s+(\d+)", src).group(1)) == _lib.ABI_VERSION == _lib.load().yb_abi_version()

@@ -50,6 +50,7 @@ YB_XFORM_NORMALIZE, YB_XFORM_SUBTRACT_MEANS, YB_XFORM_TO_FLOAT, YB_XFORM_NONE = 
 
 # name -> (restype, argtypes); kept in one table so tests can check that every symbol the header
 # declares is exported by the library.
+ABI_VERSION = 2   # include/yolact_b200.h YB_ABI_VERSION
 SIGNATURES = {
     "yb_abi_version": (c_int, []),
     "yb_last_error": (c_char_p, []),
@@ -117,7 +118,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.yb_abi_version() != 2:
+    if lib.yb_abi_version() != ABI_VERSION:
         raise YbError("yolact_b200: ABI version mismatch")
     _lib = lib
     return lib
