@@ -495,7 +495,8 @@ struct NetBuilder {
     auto chain_plan = [&](const Op& op) -> TcConvPlan* {
       if (!op.has_prob) return nullptr;
       const ConvProblem& q = op.prob;
-      if (!(q.KH == q.KW && (q.KH == 1 || q.KH == 3) && (q.stride == 1 || q.stride == 2) && q.Cout % 64 == 0 && !q.y_f32 &&
+      // "same" padding only: a stride-1 layer then keeps the resolution, which the residual-dependency pruning below relies on
+      if (!(q.KH == q.KW && (q.KH == 1 || q.KH == 3) && q.pad == q.KH / 2 && (q.stride == 1 || q.stride == 2) && q.Cout % 64 == 0 && !q.y_f32 &&
             q.nseg == 0 && q.y_pix_stride == (q.split ? 2 : 1) * q.Cout && q.y_batch_stride == (int64_t)q.Ho * q.Wo * q.y_pix_stride))
         return nullptr;
       TcConvPlan* pl = nullptr;
@@ -537,7 +538,9 @@ struct NetBuilder {
           if (ops[i + j].prob.residual && ops[i + q].prob.y == ops[i + j].prob.residual) dep_r[j] = (int)q;
         }
       // a residual written by a layer that the input chain leads back to through stride-1 layers is complete (on the
-      // rows this layer needs) whenever the input is: conv3's residual, the previous block's output, via conv2 and conv1
+      // rows this layer needs) whenever the input is: conv3's residual, the previous block's output, via conv2 and conv1.
+      // (Every link waits for producer tiles covering at least the consumer tile's own rows -- stride 1, "same" padding --
+      // and a tile only completes after its own wait was satisfied, so completion propagates down the links.)
       for (size_t j = 0; j < n; ++j) {
         if (dep_r[j] < 0) continue;
         int a = (int)j;
