@@ -1,5 +1,7 @@
 """Kernel time of single conv layers under explicit plan overrides (yb_conv2d, iters=30): which of plain / pair /
-stream-K / A-stationary wins per layer shape, outside the autotuner.  Usage: python scripts/bench_conv_modes.py"""
+stream-K / A-stationary wins per layer shape, outside the autotuner.  Usage: python scripts/bench_conv_modes.py
+HISTORICAL: written for the build that still had the A-stationary variant (YB_CONV2D_SK=2); it lost everywhere
+(profiles/conv_modes_r02.md) and was removed, so on the current library the "astat" rows repeat the stream-K ones."""
 import ctypes, itertools, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -1,3 +1,6 @@
+"""Single-layer timings of the epilogue-buffering variants (one / two epilogue groups, N tile) through yb_conv2d.
+HISTORICAL: the three-buffer variant (YB_CONV2D_EPI=3) it was written for lost (profiles/r2_call10_summary.txt) and was
+removed; on the current library EPI=3 is treated as one group."""
 import ctypes, os, sys
 sys.path.insert(0, "/root/repo")
 import torch
