@@ -958,8 +958,9 @@ tc_chain_kernel(const TcParams* __restrict__ layers, const ChainLayer* __restric
   constexpr int BUF_BYTES = NPL * CHUNK32_BYTES;
   // the chain's own shared-memory layout (the plans' stage counts / offsets are not used): ring, then one staging
   // buffer per epilogue group; two TMEM accumulator buffers.  The epilogue moves 32-channel chunks (8 KB tiles), which
-  // leaves room for a THIRD split-precision stage (3 x 64 KB + 32 KB): the main loop is bound by the bytes a CTA can
-  // keep in flight towards L2, not by the tensor pipe (profiles/ncu_tc_chain_r02.md)
+  // leaves room for a THIRD split-precision stage (3 x 64 KB + 32 KB).  Measured (profiles/r2_call14_summary.txt): the
+  // 105-layer trunk chain 2.14 -> 1.92 ms at batch 2, unchanged (3.59 ms) at batch 8, where the MMA issuer's operand
+  // waits are set by the L2 -> SM rate rather than by the bytes a CTA keeps in flight
   constexpr int stages = chain_stages(SPLIT, H);
 
   extern __shared__ uint8_t smem_dyn[];
