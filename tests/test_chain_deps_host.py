@@ -84,3 +84,38 @@ def test_bad_arguments_are_rejected():
     lib = _lib.load()
     assert lib.yb_debug_chain_deps(1, 8, 8, 5, 1, 2, 0, 0, out) != 0          # 5x5: not a chain layer
     assert lib.yb_debug_chain_deps(1, 8, 8, 3, 1, 1, 0, 10 ** 6, out) != 0    # tile out of range
+
+
+def _check_tile(B, Hin, Win, k, s, p, producer_flat, m, d0):
+    cflat, ctw, cth, ctx, cty, cm = d0[0:6]
+    pflat, ptw, pth, ptx, pty, pm = d0[6:12]
+    Ho, Wo = (Hin + 2 * p - k) // s + 1, (Win + 2 * p - k) // s + 1
+    d = deps(B, Hin, Win, k, s, p, producer_flat, m)
+    first, last = d[12], d[13]
+    assert 0 <= first <= last < pm
+    b, y, x = tile_pixels(cflat, ctw, cth, ctx, cty, B, Ho, Wo, m)
+    need = set()
+    for dy, dx in itertools.product(range(k), range(k)):
+        iy, ix = y * s - p + dy, x * s - p + dx
+        ok = (iy >= 0) & (iy < Hin) & (ix >= 0) & (ix < Win)
+        need.update(np.unique(tile_of_pixel(pflat, ptw, pth, ptx, pty, Hin, Win, b[ok], iy[ok], ix[ok])).tolist())
+    assert need and min(need) >= first and max(need) <= last, (B, Hin, Win, k, s, p, producer_flat, m, first, last)
+
+
+def test_random_geometries():
+    """Hypothesis sweep over batch / image sizes the fixed grid above does not contain (first, middle and last tiles)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None, derandomize=True)
+    @given(B=st.integers(1, 9), Hin=st.integers(1, 150), Win=st.integers(1, 150), layer=st.sampled_from(LAYERS),
+           producer_flat=st.integers(0, 1), pick=st.floats(0, 1))
+    def run(B, Hin, Win, layer, producer_flat, pick):
+        k, s, p = layer
+        if (Hin + 2 * p - k) // s + 1 < 1 or (Win + 2 * p - k) // s + 1 < 1:
+            return
+        d0 = deps(B, Hin, Win, k, s, p, producer_flat, 0)
+        cm = d0[5]
+        for m in sorted({0, cm - 1, int(pick * (cm - 1))}):
+            _check_tile(B, Hin, Win, k, s, p, producer_flat, m, d0)
+
+    run()
